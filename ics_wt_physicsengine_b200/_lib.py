@@ -1,0 +1,90 @@
+"""ctypes binding of the C ABI in include/wt_b200.h (csrc/libwt_b200.so).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no
+CPU fallback: if the shared library is missing, or no CUDA device is present when a compute
+entry point is called, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libwt_b200.so")
+
+NPAR = 12
+NBND = 10
+NCNT = 8
+
+ST_SOLVER_FAILED = 1
+ST_T_RANGE = 2
+ST_CLIP_PH = 4
+ST_CLIP_CL = 8
+ST_CLIP_T = 16
+ST_NONFINITE = 32
+ST_T_RANGE_DERIVED = 64
+ST_WORK_LIMIT = 128
+ST_HALT_MASK = ST_T_RANGE | ST_WORK_LIMIT
+
+CNT_NAMES = ("nfev", "njev", "nlu", "nsteps", "nnewton", "nreject", "nnewton_fail", "jac_retry")
+
+EXPORTS = (
+    "wt_abi_version", "wt_device_count", "wt_last_error", "wt_step", "wt_advance", "wt_derivatives",
+    "wt_step_host", "wt_calc_ph", "wt_measure_fp64_peak",
+)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(
+            f"{LIB_PATH} is missing: build the CUDA extension first "
+            "(python -c 'import __graft_entry__ as g; g.build()').  There is no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, dp, ip, up = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p  # raw device addresses
+    L.wt_abi_version.restype = C.c_int
+    L.wt_device_count.restype = C.c_int
+    L.wt_last_error.restype = C.c_char_p
+    L.wt_step.argtypes = [C.c_int, C.c_int, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, up, ip, C.c_int, vp]
+    L.wt_step.restype = C.c_int
+    L.wt_advance.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, up, ip,
+                             C.c_int, vp]
+    L.wt_advance.restype = C.c_int
+    L.wt_derivatives.argtypes = [C.c_int, C.c_int, dp, dp, C.c_int, dp, dp, ip, vp]
+    L.wt_derivatives.restype = C.c_int
+    L.wt_step_host.argtypes = [C.c_int, C.c_int, C.c_double, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int]
+    L.wt_step_host.restype = C.c_int
+    L.wt_calc_ph.argtypes = [C.c_int, dp, dp, dp, dp, dp, ip, ip, vp]
+    L.wt_calc_ph.restype = C.c_int
+    L.wt_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.c_int]
+    L.wt_measure_fp64_peak.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().wt_last_error().decode(errors="replace")
+        raise EngineError(f"{what} failed (rc={rc}): {msg}")
+
+
+def require_device() -> None:
+    if lib().wt_device_count() <= 0:
+        raise EngineError("no CUDA device visible: the engine has no CPU fallback")
+
+
+def measure_fp64_peak(iters: int = 200000) -> float:
+    require_device()
+    out = C.c_double(0.0)
+    check(lib().wt_measure_fp64_peak(C.byref(out), iters), "wt_measure_fp64_peak")
+    return out.value

@@ -1,0 +1,384 @@
+// wt_kernels.cu -- sm_100a kernels and the C ABI (include/wt_b200.h).
+//
+// K1  wt_step_kernel         fused plant step (wt_step_core.h): zones -> lanes, PCR solves
+// K1b wt_derivatives_kernel  batched RHS only
+// K2  wt_calc_ph_kernel      batched charge-balance Newton-Raphson (chemistry.py:271-330)
+//     wt_dfma_peak_kernel    FP64 pipe saturation probe for the roofline denominator
+//
+// Nothing here is GEMM shaped, so there are no tensor-core / TMA paths: the step kernel is
+// bound by the FP64 FMA pipe and touches HBM only at entry and exit.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/wt_b200.h"
+#include "wt_step_core.h"
+
+static_assert((int)WT_NPAR == (int)WTP_NPAR && (int)WT_NBND == (int)WTB_NBND && (int)WT_NCNT == (int)WTC_NCNT,
+              "ABI enums out of sync with the core");
+static_assert(WT_ST_HALT_MASK == WTS_HALT_MASK, "status bits out of sync");
+
+static thread_local char g_err[256] = "";
+static int set_err(int code, const char *msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+static int cuda_err(cudaError_t e, const char *where) {
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return (int)e;
+}
+
+// ---------------------------------------------------------------------------------------
+// per-warp shared-memory store of the PCR factorizations
+// ---------------------------------------------------------------------------------------
+struct SmemLu {
+  double *p;  // &region[lane]; slot stride = 32 doubles
+  __device__ __forceinline__ void put(int slot, double x, bool mask) { if (mask) p[slot * 32] = x; }
+  __device__ __forceinline__ double get(int slot) const { return p[slot * 32]; }
+};
+
+__host__ __device__ inline int wt_lu_slots(int n) {
+  int L = 0;
+  for (int s = 1; s < n; s <<= 1) ++L;
+  return 3 * (2 * L + 1) + 3 * (4 * L + 2);
+}
+
+struct StepArgs {
+  int P, n, n_steps, bnd_stride, max_attempts;
+  double dt;
+  const double *par, *bnd;
+  double *time, *y, *flow, *derived;
+  uint32_t *status;
+  int32_t *counters;
+};
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = a.n, gpw = 32 / n;
+  const long long wg = (long long)blockIdx.x * WARPS + warp;
+  const int gi = lane / n;
+  const long long pl = wg * gpw + gi;
+  const bool in_plant = gi < gpw && pl < a.P;
+  const int p = in_plant ? (int)pl : 0;
+  const int z = in_plant ? lane - gi * n : 0;
+  const size_t P = (size_t)a.P;
+
+  uint32_t st_in = in_plant ? a.status[p] : 0u;
+  bool on = in_plant && !(st_in & WTS_HALT_MASK);
+  if (!__any_sync(0xffffffffu, on)) return;
+
+  SmemLu lu;
+  lu.p = smem + (size_t)warp * wt_lu_slots(n) * 32 + lane;
+
+  WtPlantStep<SmemLu> ps;
+  ps.g = wt_make_group(n);
+  ps.lu = &lu;
+  {
+    double par[WTP_NPAR], bnd[WTB_NBND];
+#pragma unroll
+    for (int k = 0; k < WTP_NPAR; ++k) par[k] = a.par[(size_t)k * P + p];
+#pragma unroll
+    for (int k = 0; k < WTB_NBND; ++k) bnd[k] = a.bnd[(size_t)k * a.bnd_stride + (a.bnd_stride ? p : 0)];
+    ps.c = wt_make_const(par, bnd);
+  }
+  double t = a.time[p];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) ps.y[v] = a.y[((size_t)v * n + z) * P + p];
+
+  int32_t acc[WTC_NCNT];
+#pragma unroll
+  for (int k = 0; k < WTC_NCNT; ++k) acc[k] = 0;
+  uint32_t st = st_in;
+  double der[3] = {0.0, 0.0, 0.0};
+  bool stepped = false;
+
+  for (int s = 0; s < a.n_steps; ++s) {
+    if (!__any_sync(0xffffffffu, on)) break;
+    double yin[3] = {ps.y[0], ps.y[1], ps.y[2]};
+    ps.integrate(t, a.dt, on, a.max_attempts);
+    bool adv;
+    int sb = wt_finish_step(ps, yin, der, adv);
+    if (on) {
+      st = (uint32_t)sb;
+      if (adv) { t += a.dt; stepped = true; }
+#pragma unroll
+      for (int k = 0; k < WTC_NCNT; ++k) acc[k] += ps.cnt[k];
+      if (sb & WTS_HALT_MASK) on = false;
+    }
+  }
+
+  if (in_plant && !(st_in & WTS_HALT_MASK)) {
+#pragma unroll
+    for (int v = 0; v < 3; ++v) a.y[((size_t)v * n + z) * P + p] = ps.y[v];
+    if (a.derived && stepped) {
+#pragma unroll
+      for (int v = 0; v < 3; ++v) a.derived[((size_t)v * n + z) * P + p] = der[v];
+    }
+    if (z == 0) {
+      a.time[p] = t;
+      a.status[p] = st;
+      if (stepped && a.flow) {
+        const size_t bs = a.bnd_stride, bp = a.bnd_stride ? p : 0;
+        a.flow[p] = a.bnd[WTB_INLET_FLOW * bs + bp] + a.bnd[WTB_ACID_FLOW * bs + bp] + a.bnd[WTB_CL_FLOW * bs + bp];
+      }
+      if (a.counters) {
+#pragma unroll
+        for (int k = 0; k < WTC_NCNT; ++k) a.counters[(size_t)k * P + p] += acc[k];
+      }
+    }
+  }
+}
+
+__global__ void wt_derivatives_kernel(int P, int n, const double *par_, const double *bnd_, int bnd_stride,
+                                      const double *y, double *dy, int32_t *bad_out) {
+  const int lane = threadIdx.x & 31;
+  const int gpw = 32 / n;
+  const long long wg = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int gi = lane / n;
+  const long long pl = wg * gpw + gi;
+  const bool in_plant = gi < gpw && pl < P;
+  const int p = in_plant ? (int)pl : 0;
+  const int z = in_plant ? lane - gi * n : 0;
+  WtGroup g = wt_make_group(n);
+  double par[WTP_NPAR], bnd[WTB_NBND];
+#pragma unroll
+  for (int k = 0; k < WTP_NPAR; ++k) par[k] = par_[(size_t)k * P + p];
+#pragma unroll
+  for (int k = 0; k < WTB_NBND; ++k) bnd[k] = bnd_[(size_t)k * bnd_stride + (bnd_stride ? p : 0)];
+  WtConst c = wt_make_const(par, bnd);
+  double yy[3], d[3];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) yy[v] = y[((size_t)v * n + z) * P + p];
+  bool bad;
+  wt_rhs(g, c, yy[0], yy[1], yy[2], d[0], d[1], d[2], bad);
+  bool gbad = wt_gany(g, bad);
+  if (in_plant) {
+#pragma unroll
+    for (int v = 0; v < 3; ++v) dy[((size_t)v * n + z) * P + p] = d[v];
+    if (z == 0 && bad_out) bad_out[p] = gbad ? 1 : 0;
+  }
+}
+
+// chemistry.py:193-330, one thread per buffer system
+__global__ void wt_calc_ph_kernel(int P, const double *alk, const double *ct, const double *temp,
+                                  const double *guess, double *ph, int32_t *iters, int32_t *status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const double tc = temp[i];
+  if (tc < 0.0 || tc > 100.0) {  // thermodynamics.py:146-157 via chemistry.py:118
+    ph[i] = nan("");
+    iters[i] = 0;
+    status[i] = 3;
+    return;
+  }
+  const double TK = tc + 273.15;
+  const double Kw = 1.0e-14 * exp((55900.0 / 8.314) * (1.0 / 298.15 - 1.0 / TK));
+  const double Ka1 = exp10(-(6.35 + (-0.008) * (tc - 25.0)));
+  const double Ka2 = exp10(-(10.33 + (-0.008) * (tc - 25.0)));
+  const double C_T = ct[i] / 1000.0;
+  const double alk_eq = alk[i] / 50000.0;
+  double pH = guess[i];
+  int st = 2, it = 0;
+  for (it = 0; it < 100; ++it) {
+    const double H = exp10(-pH);
+    const double OH = Kw / H;
+    const double D = H * H + Ka1 * H + Ka1 * Ka2;
+    const double a1 = (Ka1 * H) / D;
+    const double a2 = (Ka1 * Ka2) / D;
+    const double f = H - OH + a1 * C_T + 2.0 * (a2 * C_T) - alk_eq;
+    const double dH = -WT_LN10 * H;
+    const double dOH = -(Kw / (H * H)) * dH;
+    const double dD = 2.0 * H + Ka1;
+    const double da1 = Ka1 * (D - H * dD) / (D * D);
+    const double da2 = -Ka1 * Ka2 * dD / (D * D);
+    const double df = dH - dOH + C_T * da1 * dH + 2.0 * (C_T * da2 * dH);
+    if (fabs(df) < 1e-15) { st = 1; ++it; break; }
+    const double delta = -f / df;
+    double pn = pH + delta;
+    pn = pn != pn ? pn : fmin(fmax(pn, 0.0), 14.0);  // np.clip keeps NaN
+    if (fabs(delta) < 1e-6) { pH = pn; st = 0; ++it; break; }
+    pH = pn;
+  }
+  ph[i] = pH;
+  iters[i] = it;
+  status[i] = st;
+}
+
+// 8 independent DFMA chains per thread: saturates the FP64 pipe without memory traffic
+__global__ void wt_dfma_peak_kernel(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 12345.678) out[0] = s;  // never true; keeps the loop alive
+}
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int wt_abi_version(void) { return WT_ABI_VERSION; }
+const char *wt_last_error(void) { return g_err; }
+int wt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+static int check_common(int P, int n) {
+  if (P <= 0) return set_err(WT_ERR_BAD_ARG, "P must be positive");
+  if (n < 2 || n > WT_MAX_ZONES) return set_err(WT_ERR_BAD_ARG, "n_zones must be in [2, 32]");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  return 0;
+}
+
+#define WT_STEP_WARPS 4
+
+static int launch_step(StepArgs a, cudaStream_t s) {
+  const int gpw = 32 / a.n;
+  const long long warps = ((long long)a.P + gpw - 1) / gpw;
+  const long long blocks = (warps + WT_STEP_WARPS - 1) / WT_STEP_WARPS;
+  const size_t smem = (size_t)WT_STEP_WARPS * wt_lu_slots(a.n) * 32 * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wt_step_kernel<WT_STEP_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute");
+    attr_done = true;
+  }
+  wt_step_kernel<WT_STEP_WARPS><<<(unsigned)blocks, WT_STEP_WARPS * 32, smem, s>>>(a);
+  return cuda_err(cudaGetLastError(), "wt_step_kernel launch");
+}
+
+int wt_advance(int P, int n, int n_steps, double dt, const double *par, const double *bnd, int bnd_stride,
+               double *time, double *y, double *flow, double *derived, uint32_t *status, int32_t *counters,
+               int max_attempts, void *stream) {
+  int rc = check_common(P, n);
+  if (rc) return rc;
+  if (!(dt > 0.0)) return set_err(WT_ERR_BAD_ARG, "dt must be positive");
+  if (n_steps < 1) return set_err(WT_ERR_BAD_ARG, "n_steps must be >= 1");
+  if (!par || !bnd || !time || !y || !status) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  if (bnd_stride != 0 && bnd_stride != P) return set_err(WT_ERR_BAD_ARG, "bnd_stride must be 0 or P");
+  StepArgs a;
+  a.P = P; a.n = n; a.n_steps = n_steps; a.bnd_stride = bnd_stride; a.max_attempts = max_attempts;
+  a.dt = dt; a.par = par; a.bnd = bnd; a.time = time; a.y = y; a.flow = flow; a.derived = derived;
+  a.status = status; a.counters = counters;
+  return launch_step(a, (cudaStream_t)stream);
+}
+
+int wt_step(int P, int n, double dt, const double *par, const double *bnd, int bnd_stride, double *time,
+            double *y, double *flow, double *derived, uint32_t *status, int32_t *counters, int max_attempts,
+            void *stream) {
+  return wt_advance(P, n, 1, dt, par, bnd, bnd_stride, time, y, flow, derived, status, counters, max_attempts, stream);
+}
+
+int wt_derivatives(int P, int n, const double *par, const double *bnd, int bnd_stride, const double *y,
+                   double *dy, int32_t *bad, void *stream) {
+  int rc = check_common(P, n);
+  if (rc) return rc;
+  if (!par || !bnd || !y || !dy) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  const int gpw = 32 / n;
+  const long long warps = ((long long)P + gpw - 1) / gpw;
+  const int wpb = 4;
+  const long long blocks = (warps + wpb - 1) / wpb;
+  wt_derivatives_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(P, n, par, bnd, bnd_stride, y, dy, bad);
+  return cuda_err(cudaGetLastError(), "wt_derivatives_kernel launch");
+}
+
+int wt_calc_ph(int P, const double *alk, const double *ct, const double *temp, const double *guess, double *ph,
+               int32_t *iters, int32_t *status, void *stream) {
+  if (P <= 0) return set_err(WT_ERR_BAD_ARG, "P must be positive");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (!alk || !ct || !temp || !guess || !ph || !iters || !status) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  const int tpb = 128;
+  wt_calc_ph_kernel<<<(P + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(P, alk, ct, temp, guess, ph, iters, status);
+  return cuda_err(cudaGetLastError(), "wt_calc_ph_kernel launch");
+}
+
+// Host-buffer path: one workspace per process, grown on demand.
+static struct {
+  size_t cap_bytes;
+  char *dev;
+} g_ws = {0, nullptr};
+
+int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, int bnd_stride, double *time,
+                 double *y, double *flow, uint32_t *status, int max_attempts) {
+  int rc = check_common(P, n);
+  if (rc) return rc;
+  if (!par || !bnd || !time || !y || !status) return set_err(WT_ERR_BAD_ARG, "null host pointer");
+  if (bnd_stride != 0 && bnd_stride != P) return set_err(WT_ERR_BAD_ARG, "bnd_stride must be 0 or P");
+  const size_t Pz = (size_t)P;
+  const size_t b_par = WT_NPAR * Pz * 8, b_bnd = WT_NBND * (bnd_stride ? Pz : 1) * 8, b_t = Pz * 8,
+               b_y = 3 * (size_t)n * Pz * 8, b_f = Pz * 8, b_s = Pz * 4;
+  const size_t total = b_par + b_bnd + b_t + b_y + b_f + b_s + 256 * 6;
+  if (total > g_ws.cap_bytes) {
+    if (g_ws.dev) cudaFree(g_ws.dev);
+    g_ws.dev = nullptr;
+    g_ws.cap_bytes = 0;
+    cudaError_t e = cudaMalloc((void **)&g_ws.dev, total);
+    if (e != cudaSuccess) { cuda_err(e, "cudaMalloc workspace"); return WT_ERR_ALLOC; }
+    g_ws.cap_bytes = total;
+  }
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  char *q = g_ws.dev;
+  double *d_par = (double *)q; q += al(b_par);
+  double *d_bnd = (double *)q; q += al(b_bnd);
+  double *d_t = (double *)q; q += al(b_t);
+  double *d_y = (double *)q; q += al(b_y);
+  double *d_f = (double *)q; q += al(b_f);
+  uint32_t *d_s = (uint32_t *)q;
+  cudaStream_t s = 0;
+  cudaMemcpyAsync(d_par, par, b_par, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_bnd, bnd, b_bnd, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_t, time, b_t, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_y, y, b_y, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_s, status, b_s, cudaMemcpyHostToDevice, s);
+  if (flow) cudaMemcpyAsync(d_f, flow, b_f, cudaMemcpyHostToDevice, s);
+  rc = wt_step(P, n, dt, d_par, d_bnd, bnd_stride, d_t, d_y, flow ? d_f : nullptr, nullptr, d_s, nullptr, max_attempts, s);
+  if (rc) return rc;
+  cudaMemcpyAsync(time, d_t, b_t, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(y, d_y, b_y, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(status, d_s, b_s, cudaMemcpyDeviceToHost, s);
+  if (flow) cudaMemcpyAsync(flow, d_f, b_f, cudaMemcpyDeviceToHost, s);
+  return cuda_err(cudaStreamSynchronize(s), "wt_step_host");
+}
+
+int wt_measure_fp64_peak(double *tflops_out, int iters) {
+  if (!tflops_out || iters <= 0) return set_err(WT_ERR_BAD_ARG, "bad argument");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device");
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double *out = nullptr;
+  cudaError_t e = cudaMalloc((void **)&out, 8);
+  if (e != cudaSuccess) { cuda_err(e, "cudaMalloc"); return WT_ERR_ALLOC; }
+  const int tpb = 256, blocks = sms * 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  wt_dfma_peak_kernel<<<blocks, tpb>>>(out, iters / 8 + 1, 1.0000001, 1e-9);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    wt_dfma_peak_kernel<<<blocks, tpb>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double flops = 2.0 * 8.0 * (double)iters * (double)tpb * (double)blocks;
+    double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops_out = best;
+  return cuda_err(cudaGetLastError(), "wt_measure_fp64_peak");
+}
+
+}  // extern "C"

@@ -1,0 +1,1044 @@
+// wt_step_core.h -- the fused plant step: one IntegratedCSTR.step(dt, boundary) per plant.
+//
+// What it replaces (reference, src/wt_simulator/core/reactor.py):
+//   step()                      :450-509   one scipy solve_ivp(method="Radau") over [t, t+dt]
+//   derivatives()               :272-448   the ODE right-hand side
+//   _update_derived_state()     :511-524
+//   _enforce_physical_bounds()  :526-541
+// and, from scipy 1.18.1 (scipy/integrate/_ivp/), the pieces step() executes:
+//   radau.py:48-136 (simplified Newton), :139-176 (step factor), :295-347 (setup),
+//   :405-545 (_step_impl), :547-578 (dense output); common.py:63-134 (norm, initial step),
+//   :260-382 (finite-difference Jacobian num_jac); base.py:179-210; ivp.py:659-666.
+//
+// B200 mapping (not a translation of the above):
+//   * zones -> lanes, floor(32/n) plants per warp, everything in registers; neighbours by SHFL.
+//   * Every RHS row i depends only on zones i-1, i, i+1 and dT depends on T only, dpH on
+//     (pH, T), dCl on (pH_i, Cl, T).  In the ordering (T, pH, Cl) the Newton matrix
+//     gamma*I - J is block lower triangular with TRIDIAGONAL blocks, so LAPACK's dense
+//     real + complex LU becomes six scalar tridiagonal factorizations, done across lanes by
+//     parallel cyclic reduction (PCR).  Algebraically the same linear solves.
+//   * The finite-difference Jacobian is rebuilt from perturbed evaluations of the affected
+//     rows only (rows outside the 3-zone stencil difference to an exact 0 in the reference).
+//     scipy's column logic (first arg-max row, retry with 10x step, factor adaptation) is
+//     applied unchanged on the lane that owns the column.
+//   * Plants sharing a warp run in lockstep; per-plant decisions are masks.
+//
+// Written against wt_simt.h only, so the same source is the sm_100a kernel body and the
+// CPU lane-emulation test build.
+#pragma once
+
+#include "wt_simt.h"
+
+// parameter / boundary / status / counter indices (shared with include/wt_b200.h)
+enum {
+  WTP_KW = 0, WTP_KA1, WTP_KA2, WTP_KACL, WTP_CT, WTP_KX, WTP_V, WTP_ZH, WTP_VZL, WTP_VOLUME,
+  WTP_AT, WTP_STRAT, WTP_NPAR
+};
+enum {
+  WTB_INLET_FLOW = 0, WTB_INLET_PH, WTB_INLET_CL, WTB_INLET_T, WTB_ACID_FLOW, WTB_ACID_CONC,
+  WTB_CL_FLOW, WTB_CL_CONC, WTB_AMBIENT_T, WTB_HEAT_LOSS, WTB_NBND
+};
+enum {
+  WTS_SOLVER_FAILED = 1, WTS_T_RANGE = 2, WTS_CLIP_PH = 4, WTS_CLIP_CL = 8, WTS_CLIP_T = 16,
+  WTS_NONFINITE = 32, WTS_T_RANGE_DERIVED = 64, WTS_WORK_LIMIT = 128
+};
+#define WTS_HALT_MASK (WTS_T_RANGE | WTS_WORK_LIMIT)
+enum {
+  WTC_NFEV = 0, WTC_NJEV, WTC_NLU, WTC_NSTEPS, WTC_NNEWTON, WTC_NREJECT, WTC_NNEWTON_FAIL,
+  WTC_JAC_RETRY, WTC_NCNT
+};
+
+#define WT_RTOL 1e-6  // reactor.py:482
+#define WT_ATOL 1e-8  // reactor.py:483
+#define WT_LN10 2.302585092994046
+#define WT_EPS 2.220446049250313e-16
+
+// radau.py:11-45
+#define WT_S6 2.449489742783178
+#define WT_C0 ((4.0 - WT_S6) / 10.0)
+#define WT_C1 ((4.0 + WT_S6) / 10.0)
+#define WT_E0 ((-13.0 - 7.0 * WT_S6) / 3.0)
+#define WT_E1 ((-13.0 + 7.0 * WT_S6) / 3.0)
+#define WT_E2 (-1.0 / 3.0)
+#define WT_MU_REAL 3.6378342527444957          // 3 + 3**(2/3) - 3**(1/3)
+#define WT_MU_CRE 2.6810828736277523           // 3 + 0.5*(3**(1/3) - 3**(2/3))
+#define WT_MU_CIM (-3.0504301992474105)        // -0.5*(3**(5/6) + 3**(7/6))
+#define WT_T00 0.09443876248897524
+#define WT_T01 (-0.14125529502095421)
+#define WT_T02 0.03002919410514742
+#define WT_T10 0.25021312296533332
+#define WT_T11 0.20412935229379994
+#define WT_T12 (-0.38294211275726192)
+#define WT_TI00 4.17871859155190428
+#define WT_TI01 0.32768282076106237
+#define WT_TI02 0.52337644549944951
+#define WT_TI10 (-4.17871859155190428)
+#define WT_TI11 (-0.32768282076106237)
+#define WT_TI12 0.47662355450055044
+#define WT_TI20 0.50287263494578682
+#define WT_TI21 (-2.57192694985560522)
+#define WT_TI22 0.59603920482822492
+#define WT_P00 (13.0 / 3.0 + 7.0 * WT_S6 / 3.0)
+#define WT_P01 (-23.0 / 3.0 - 22.0 * WT_S6 / 3.0)
+#define WT_P02 (10.0 / 3.0 + 5.0 * WT_S6)
+#define WT_P10 (13.0 / 3.0 - 7.0 * WT_S6 / 3.0)
+#define WT_P11 (-23.0 / 3.0 + 22.0 * WT_S6 / 3.0)
+#define WT_P12 (10.0 / 3.0 - 5.0 * WT_S6)
+#define WT_P20 (1.0 / 3.0)
+#define WT_P21 (-8.0 / 3.0)
+#define WT_P22 (10.0 / 3.0)
+#define WT_NEWTON_MAXITER 6
+#define WT_HARD_MAX_ATTEMPTS 2000000
+#define WT_NEWTON_TOL 1e-3  // max(10*EPS/rtol, min(0.03, sqrt(rtol))), radau.py:315
+
+// ----------------------------------------------------------------------------------------
+// lane <-> (plant, zone) geometry of one warp
+// ----------------------------------------------------------------------------------------
+struct WtGroup {
+  int n;       // zones per plant (warp-uniform)
+  vi z;        // zone index of this lane inside its plant
+  vi base;     // first lane of this lane's plant
+  vi gmask;    // bit mask of the plant's lanes
+  vb first;    // z == 0
+  vb last;     // z == n-1
+};
+
+WT_DEV WtGroup wt_make_group(int n) {
+  WtGroup g;
+  g.n = n;
+  vi lane = lane_id();
+  int gpw = WT_WARP / n;
+  // lanes past the last whole plant form harmless one-lane pseudo groups
+  vb in = lane < gpw * n;
+  vi q = vbroadcast_i(0);
+  for (int k = 1; k < gpw; ++k) q = q + seli(lane >= k * n, 1, 0);
+  g.base = seli(in, q * n, lane);
+  g.z = seli(in, lane - g.base, 0);
+  uint32_t full = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+  vi m = vbroadcast_i(0);
+  for (int k = 0; k < gpw; ++k) m = seli(in & (q == k), (int)(full << (k * n)), m);
+  vi one = vbroadcast_i(0);
+  for (int k = 0; k < WT_WARP; ++k) one = seli(lane == k, (int)(1u << k), one);
+  g.gmask = seli(in, m, one);
+  g.first = g.z == 0;
+  g.last = selb(in, g.z == (n - 1), vbroadcast_b(true));
+  return g;
+}
+
+// neighbour access inside the plant; `dflt` outside
+WT_DEV vd wt_dn(const WtGroup &g, vd x, double dflt) { return sel(g.first, dflt, shfl_up(x, 1)); }
+WT_DEV vd wt_up(const WtGroup &g, vd x, double dflt) { return sel(g.last, dflt, shfl_down(x, 1)); }
+WT_DEV vd wt_dn_s(const WtGroup &g, vd x, int s) { return sel(g.z >= s, shfl_up(x, s), 0.0); }
+WT_DEV vd wt_up_s(const WtGroup &g, vd x, int s) { return sel((g.z + s) < g.n, shfl_down(x, s), 0.0); }
+
+// sum over the plant's lanes, result replicated on all of them
+WT_DEV vd wt_gsum(const WtGroup &g, vd x) {
+  for (int s = 1; s < g.n; s <<= 1) x = x + wt_up_s(g, x, s);
+  return shfl_idx(x, g.base);
+}
+WT_DEV vb wt_gany(const WtGroup &g, vb c) { return vmask_any(vballot(c), g.gmask); }
+
+// ----------------------------------------------------------------------------------------
+// per-plant constants and boundary, replicated per lane
+// ----------------------------------------------------------------------------------------
+struct WtConst {
+  vd Kw, Ka1, Ka12, KaCl, CT2303, Kx, zh, v2;
+  vb strat, v_ok;
+  // boundary-derived (reactor.py:336, 349-368, 388-395, 420, 426-443)
+  vd QV, Hin, dHd, cl_dose, inCl, inT, hlA, amb, hl_den;
+  vb acid_on, cl_on, hl_on;
+};
+
+// par / bnd hold this lane's plant values (already loaded)
+WT_DEV WtConst wt_make_const(const vd *par, const vd *bnd) {
+  WtConst c;
+  c.Kw = par[WTP_KW];
+  c.Ka1 = par[WTP_KA1];
+  c.Ka12 = par[WTP_KA1] * par[WTP_KA2];
+  c.KaCl = par[WTP_KACL];
+  c.CT2303 = 2.303 * par[WTP_CT];
+  c.Kx = par[WTP_KX];
+  c.zh = par[WTP_ZH];
+  c.v2 = par[WTP_V] * par[WTP_V];
+  c.v_ok = par[WTP_V] > 1e-6;
+  c.strat = par[WTP_STRAT] != 0.0;
+  c.QV = (bnd[WTB_INLET_FLOW] / 60.0) / par[WTP_VOLUME];
+  c.Hin = vexp10(-bnd[WTB_INLET_PH]);
+  c.acid_on = bnd[WTB_ACID_FLOW] > 0.0;
+  c.dHd = ((bnd[WTB_ACID_FLOW] / 60.0) * bnd[WTB_ACID_CONC]) / par[WTP_VZL];
+  c.cl_on = bnd[WTB_CL_FLOW] > 0.0;
+  c.cl_dose = ((bnd[WTB_CL_FLOW] / 60.0) * bnd[WTB_CL_CONC]) / par[WTP_VZL];
+  c.inCl = bnd[WTB_INLET_CL];
+  c.inT = bnd[WTB_INLET_T];
+  c.hl_on = bnd[WTB_HEAT_LOSS] > 0.0;
+  c.hlA = bnd[WTB_HEAT_LOSS] * par[WTP_AT];
+  c.amb = bnd[WTB_AMBIENT_T];
+  c.hl_den = (998.2 * 4184.0) * (par[WTP_VOLUME] / 1000.0);
+  return c;
+}
+
+// ----------------------------------------------------------------------------------------
+// right-hand-side building blocks
+// ----------------------------------------------------------------------------------------
+
+// spatial.py:175-195
+WT_DEV vd wt_density(vd T) {
+  vd d4 = T - 4.0;
+  vd cold = 999.97 + (-0.008) * (d4 * d4);
+  vd warm = 998.2 + (-2.1e-4 * 998.2) * (T - 20.0);
+  return sel(T <= 8.0, cold, warm);
+}
+
+// spatial.py:266-275, 293, 313-316: exchange multiplier of the interface between a zone
+// (rho_lo) and the zone above it (rho_hi)
+WT_DEV vd wt_suppression(const WtConst &c, vd rho_lo, vd rho_hi) {
+  vd drho = rho_hi - rho_lo;
+  vd ravg = 0.5 * (rho_lo + rho_hi);
+  vd Ri = ((9.81 * drho) * c.zh) / (ravg * c.v2);
+  vb stable = (!c.v_ok) | (Ri > 0.25);  // v <= 1e-6 -> Ri = +inf
+  return sel(c.strat & stable, 0.5, 1.0);
+}
+
+// thermodynamics.py:187-193
+WT_DEV vd wt_arrhenius(vd T) {
+  vd TK = T + 273.15;
+  vd e = -(45000.0 / 8.314) * (1.0 / TK - 1.0 / 293.15);
+  return 0.0001 * vexp(e);
+}
+WT_DEV vb wt_t_out_of_range(vd T) { return (T < 0.0) | (T > 100.0); }  // thermodynamics.py:146-157
+
+// chemistry.py:422-437 (+ :181-191): beta(pH) * ln(10)
+WT_DEV vd wt_beta_ln10(const WtConst &c, vd H, vb &bpos) {
+  vd bw = 2.303 * (H + c.Kw / H);
+  vd HH = H * H;
+  vd D = HH + c.Ka1 * H + c.Ka12;
+  vd a0 = HH / D;
+  vd a1 = (c.Ka1 * H) / D;
+  vd a2 = c.Ka12 / D;
+  vd bc = c.CT2303 * (a0 * a1 + (4.0 * a1) * a2 + a0 * a2);
+  vd beta = bw + bc;
+  bpos = beta > 0.0;
+  return beta * WT_LN10;
+}
+
+// chemistry.py:510-523
+WT_DEV vd wt_decay_factor(const WtConst &c, vd H) {
+  vd den = H + c.KaCl;
+  return (H / den) * 1.0 + (c.KaCl / den) * 0.02;
+}
+
+struct WtMix { vd off_dn, off_up, diag; };
+
+// reactor.py:318-337: row z of the stratification-scaled exchange matrix
+WT_DEV WtMix wt_mix_row(const WtGroup &g, const WtConst &c, vd s_dn, vd s_up) {
+  WtMix m;
+  m.off_up = sel(g.last, 0.0, c.Kx * s_up);
+  m.off_dn = sel(g.first, 0.0, c.Kx * s_dn);
+  vd d = -(m.off_dn + m.off_up);
+  m.diag = sel(g.last, d - c.QV, d);
+  return m;
+}
+WT_DEV vd wt_mix(const WtMix &m, vd xdn, vd x, vd xup) { return (m.off_dn * xdn + m.diag * x) + m.off_up * xup; }
+
+// reactor.py:349-368: the zone-0-only acid dosing + inlet terms of dpH (0 elsewhere)
+WT_DEV vd wt_dph_inlet(const WtGroup &g, const WtConst &c, vd H, vd bl, vb bpos) {
+  vd t1 = sel(g.first & c.acid_on & bpos, -c.dHd / bl, 0.0);
+  vd dHin = c.QV * (c.Hin - H);
+  vd t2 = sel(g.first & bpos, -dHin / bl, 0.0);
+  return (0.0 + t1) + t2;
+}
+// reactor.py:371-376
+WT_DEV vd wt_dph(vd t12, vd mixH, vd bl, vb bpos) { return t12 + sel(bpos, -mixH / bl, 0.0); }
+// reactor.py:388-411
+WT_DEV vd wt_dcl(const WtGroup &g, const WtConst &c, vd Cl, vd mixCl, vd kf) {
+  vd r = sel(g.first & c.cl_on, c.cl_dose, 0.0);
+  r = r + sel(g.first, c.QV * (c.inCl - Cl), 0.0);
+  r = r + mixCl;
+  return r - kf * Cl;
+}
+// reactor.py:420-443
+WT_DEV vd wt_dt(const WtGroup &g, const WtConst &c, vd T, vd mixT) {
+  vd r = sel(g.first, c.QV * (c.inT - T), 0.0);
+  r = r + mixT;
+  vd loss = (c.hlA * (T - c.amb)) / c.hl_den;
+  return sel(c.hl_on, r - loss, r);
+}
+
+// Full RHS for this lane's zone.  `bad` is set where the reference would raise ValueError.
+WT_DEV void wt_rhs(const WtGroup &g, const WtConst &c, vd pH, vd Cl, vd T, vd &dpH, vd &dCl, vd &dT,
+                   vb &bad) {
+  vd rho = wt_density(T);
+  vd s_up = wt_suppression(c, rho, shfl_down(rho, 1));
+  vd s_dn = shfl_up(s_up, 1);
+  WtMix m = wt_mix_row(g, c, s_dn, s_up);
+  vd H = vexp10(-pH);
+  vb bpos;
+  vd bl = wt_beta_ln10(c, H, bpos);
+  vd mixH = wt_mix(m, wt_dn(g, H, 0.0), H, wt_up(g, H, 0.0));
+  dpH = wt_dph(wt_dph_inlet(g, c, H, bl, bpos), mixH, bl, bpos);
+  vd kf = wt_arrhenius(T) * wt_decay_factor(c, H);
+  dCl = wt_dcl(g, c, Cl, wt_mix(m, wt_dn(g, Cl, 0.0), Cl, wt_up(g, Cl, 0.0)), kf);
+  dT = wt_dt(g, c, T, wt_mix(m, wt_dn(g, T, 0.0), T, wt_up(g, T, 0.0)));
+  bad = wt_t_out_of_range(T);
+}
+
+// ----------------------------------------------------------------------------------------
+// tridiagonal systems across lanes: parallel cyclic reduction
+// ----------------------------------------------------------------------------------------
+// LuStore (backend-specific, see the kernel / the emulation harness) keeps, per lane, the
+// elimination multipliers of each level and the final reciprocal pivot:
+//   void put(int slot, vd x, vb mask);   vd get(int slot);
+
+WT_DEV int wt_pcr_levels(int n) { int L = 0; for (int s = 1; s < n; s <<= 1) ++L; return L; }
+WT_DEV int wt_slots_real(int n) { return 2 * wt_pcr_levels(n) + 1; }
+
+template <class LuStore>
+WT_DEV void wt_pcr_factor_real(const WtGroup &g, LuStore &lu, int slot0, vd a, vd b, vd c, vb mask) {
+  int l = 0;
+  for (int s = 1; s < g.n; s <<= 1, ++l) {
+    vd r = 1.0 / b;
+    vd k1 = a * wt_dn_s(g, r, s);
+    vd k2 = c * wt_up_s(g, r, s);
+    vd a_dn = wt_dn_s(g, a, s), c_dn = wt_dn_s(g, c, s);
+    vd a_up = wt_up_s(g, a, s), c_up = wt_up_s(g, c, s);
+    b = b - c_dn * k1 - a_up * k2;
+    a = -(a_dn * k1);
+    c = -(c_up * k2);
+    lu.put(slot0 + 2 * l, k1, mask);
+    lu.put(slot0 + 2 * l + 1, k2, mask);
+  }
+  lu.put(slot0 + 2 * l, 1.0 / b, mask);
+}
+template <class LuStore>
+WT_DEV vd wt_pcr_solve_real(const WtGroup &g, LuStore &lu, int slot0, vd d) {
+  int l = 0;
+  for (int s = 1; s < g.n; s <<= 1, ++l)
+    d = d - wt_dn_s(g, d, s) * lu.get(slot0 + 2 * l) - wt_up_s(g, d, s) * lu.get(slot0 + 2 * l + 1);
+  return d * lu.get(slot0 + 2 * l);
+}
+
+// complex: (ar + i ai) etc.; slots hold (re, im) pairs
+template <class LuStore>
+WT_DEV void wt_pcr_factor_cplx(const WtGroup &g, LuStore &lu, int slot0, vd ar, vd br, vd bi, vd cr,
+                               vb mask) {
+  vd ai = vbroadcast(0.0), ci = vbroadcast(0.0);
+  int l = 0;
+  for (int s = 1; s < g.n; s <<= 1, ++l) {
+    vd den = br * br + bi * bi;
+    vd rr = br / den, ri = -bi / den;  // 1 / b
+    vd rdr = wt_dn_s(g, rr, s), rdi = wt_dn_s(g, ri, s);
+    vd rur = wt_up_s(g, rr, s), rui = wt_up_s(g, ri, s);
+    vd k1r = ar * rdr - ai * rdi, k1i = ar * rdi + ai * rdr;
+    vd k2r = cr * rur - ci * rui, k2i = cr * rui + ci * rur;
+    vd adr = wt_dn_s(g, ar, s), adi = wt_dn_s(g, ai, s), cdr = wt_dn_s(g, cr, s), cdi = wt_dn_s(g, ci, s);
+    vd aur = wt_up_s(g, ar, s), aui = wt_up_s(g, ai, s), cur = wt_up_s(g, cr, s), cui = wt_up_s(g, ci, s);
+    br = br - (cdr * k1r - cdi * k1i) - (aur * k2r - aui * k2i);
+    bi = bi - (cdr * k1i + cdi * k1r) - (aur * k2i + aui * k2r);
+    ar = -(adr * k1r - adi * k1i);
+    ai = -(adr * k1i + adi * k1r);
+    cr = -(cur * k2r - cui * k2i);
+    ci = -(cur * k2i + cui * k2r);
+    lu.put(slot0 + 4 * l + 0, k1r, mask);
+    lu.put(slot0 + 4 * l + 1, k1i, mask);
+    lu.put(slot0 + 4 * l + 2, k2r, mask);
+    lu.put(slot0 + 4 * l + 3, k2i, mask);
+  }
+  vd den = br * br + bi * bi;
+  lu.put(slot0 + 4 * l + 0, br / den, mask);
+  lu.put(slot0 + 4 * l + 1, -bi / den, mask);
+}
+template <class LuStore>
+WT_DEV void wt_pcr_solve_cplx(const WtGroup &g, LuStore &lu, int slot0, vd &dr, vd &di) {
+  int l = 0;
+  for (int s = 1; s < g.n; s <<= 1, ++l) {
+    vd k1r = lu.get(slot0 + 4 * l + 0), k1i = lu.get(slot0 + 4 * l + 1);
+    vd k2r = lu.get(slot0 + 4 * l + 2), k2i = lu.get(slot0 + 4 * l + 3);
+    vd ddr = wt_dn_s(g, dr, s), ddi = wt_dn_s(g, di, s), dur = wt_up_s(g, dr, s), dui = wt_up_s(g, di, s);
+    vd nr = dr - (ddr * k1r - ddi * k1i) - (dur * k2r - dui * k2i);
+    vd ni = di - (ddr * k1i + ddi * k1r) - (dur * k2i + dui * k2r);
+    dr = nr;
+    di = ni;
+  }
+  vd rr = lu.get(slot0 + 4 * l + 0), ri = lu.get(slot0 + 4 * l + 1);
+  vd xr = dr * rr - di * ri, xi = dr * ri + di * rr;
+  dr = xr;
+  di = xi;
+}
+
+// ----------------------------------------------------------------------------------------
+// finite-difference Jacobian rows of this lane's zone (index 0: column zone z-1, 1: z, 2: z+1)
+// ----------------------------------------------------------------------------------------
+struct WtJac {
+  vd tt[3];  // d(dT_z)/dT
+  vd pp[3];  // d(dpH_z)/dpH
+  vd pt[3];  // d(dpH_z)/dT   (non-zero only when a perturbation flips a Richardson switch)
+  vd cc[3];  // d(dCl_z)/dCl
+  vd ct[3];  // d(dCl_z)/dT
+  vd cp;     // d(dCl_z)/dpH_z
+};
+
+// One plant-step worth of solver state, per lane.
+template <class LuStore>
+struct WtPlantStep {
+  WtGroup g;
+  WtConst c;
+  LuStore *lu;
+  // state vector of this zone: 0 pH, 1 Cl, 2 T  (and f = dy/dt)
+  vd y[3], f[3];
+  WtJac J;
+  vd jfac[3];
+  vb have_jfac;
+  vd W[3][3];     // W[k][var]
+  vd Q[3][3];     // dense output, Q[var][k]   (radau.py:547-553)
+  vd yold[3];
+  vd sol_told, sol_h;
+  vb have_sol;
+  vi cnt[WTC_NCNT];
+  vb trange;      // the reference would have raised ValueError inside the solve
+  vb failed;      // TOO_SMALL_STEP
+  vb worklimit;   // engine policy: attempt budget exhausted (not reference behaviour)
+
+  WT_DEV int slot_real(int sys) const { return sys * wt_slots_real(g.n); }
+  WT_DEV int slot_cplx(int sys) const { return 3 * wt_slots_real(g.n) + sys * (4 * wt_pcr_levels(g.n) + 2); }
+
+  // -------------------------------------------------------------------------------------
+  // linear algebra on the block-triangular structure.  System order: 0 = T, 1 = pH, 2 = Cl.
+  // -------------------------------------------------------------------------------------
+  WT_DEV void factor(vd h, vb mask) {
+    vd mr = WT_MU_REAL / h;
+    vd cr = WT_MU_CRE / h, ci = WT_MU_CIM / h;
+    wt_pcr_factor_real(g, *lu, slot_real(0), -J.tt[0], mr - J.tt[1], -J.tt[2], mask);
+    wt_pcr_factor_real(g, *lu, slot_real(1), -J.pp[0], mr - J.pp[1], -J.pp[2], mask);
+    wt_pcr_factor_real(g, *lu, slot_real(2), -J.cc[0], mr - J.cc[1], -J.cc[2], mask);
+    wt_pcr_factor_cplx(g, *lu, slot_cplx(0), -J.tt[0], cr - J.tt[1], ci, -J.tt[2], mask);
+    wt_pcr_factor_cplx(g, *lu, slot_cplx(1), -J.pp[0], cr - J.pp[1], ci, -J.pp[2], mask);
+    wt_pcr_factor_cplx(g, *lu, slot_cplx(2), -J.cc[0], cr - J.cc[1], ci, -J.cc[2], mask);
+  }
+  WT_DEV vd tri_mv(const vd *row, vd x) const {
+    return (row[0] * wt_dn(g, x, 0.0) + row[1] * x) + row[2] * wt_up(g, x, 0.0);
+  }
+  // (mu/h I - J) x = b, b and x indexed [0 pH, 1 Cl, 2 T]
+  WT_DEV void solve_real(vd *b) {
+    vd xT = wt_pcr_solve_real(g, *lu, slot_real(0), b[2]);
+    vd xp = wt_pcr_solve_real(g, *lu, slot_real(1), b[0] + tri_mv(J.pt, xT));
+    vd xc = wt_pcr_solve_real(g, *lu, slot_real(2), b[1] + tri_mv(J.ct, xT) + J.cp * xp);
+    b[0] = xp; b[1] = xc; b[2] = xT;
+  }
+  WT_DEV void solve_cplx(vd *br, vd *bi) {
+    vd tr = br[2], ti = bi[2];
+    wt_pcr_solve_cplx(g, *lu, slot_cplx(0), tr, ti);
+    vd pr = br[0] + tri_mv(J.pt, tr), pi = bi[0] + tri_mv(J.pt, ti);
+    wt_pcr_solve_cplx(g, *lu, slot_cplx(1), pr, pi);
+    vd qr = br[1] + tri_mv(J.ct, tr) + J.cp * pr, qi = bi[1] + tri_mv(J.ct, ti) + J.cp * pi;
+    wt_pcr_solve_cplx(g, *lu, slot_cplx(2), qr, qi);
+    br[0] = pr; bi[0] = pi; br[1] = qr; bi[1] = qi; br[2] = tr; bi[2] = ti;
+  }
+
+  // common.py:63-65 over the plant's 3n unknowns
+  WT_DEV vd rms3(vd a, vd b, vd cc_) const {
+    vd s = wt_gsum(g, (a * a + b * b) + cc_ * cc_);
+    return vsqrt(s) / sqrt((double)(3 * g.n));
+  }
+
+  // -------------------------------------------------------------------------------------
+  // num_jac (common.py:311-382) at (y, f), restricted to the plants in `m`
+  // -------------------------------------------------------------------------------------
+  WT_DEV void num_jac(vb m) {
+    const double REJECT = 2.0097183471152322e-14;  // EPS ** 0.875
+    const double SMALL = 1.8189894035458565e-12;   // EPS ** 0.75
+    const double BIG = 1.220703125e-4;             // EPS ** 0.25
+    const double MINF = 1e3 * WT_EPS;
+    cnt[WTC_NJEV] = cnt[WTC_NJEV] + seli(m, 1, 0);
+
+    WT_UNROLL
+    for (int v = 0; v < 3; ++v) jfac[v] = sel(m & !have_jfac, 1.4901161193847656e-08, jfac[v]);  // EPS ** 0.5
+    have_jfac = have_jfac | m;
+
+    // ---- base intermediates at y (identical bits to the evaluation that produced f)
+    const vd pH = y[0], Cl = y[1], T = y[2];
+    vd rho = wt_density(T);
+    vd rho_up = shfl_down(rho, 1), rho_dn = shfl_up(rho, 1);
+    vd s_up = wt_suppression(c, rho, rho_up);
+    vd s_dn = shfl_up(s_up, 1);
+    WtMix mx = wt_mix_row(g, c, s_dn, s_up);
+    vd H = vexp10(-pH);
+    vb bpos;
+    vd bl = wt_beta_ln10(c, H, bpos);
+    vd t12 = wt_dph_inlet(g, c, H, bl, bpos);
+    vd kk = wt_arrhenius(T);
+    vd kf = kk * wt_decay_factor(c, H);
+    vd Hdn = wt_dn(g, H, 0.0), Hup = wt_up(g, H, 0.0);
+    vd Cldn = wt_dn(g, Cl, 0.0), Clup = wt_up(g, Cl, 0.0);
+    vd Tdn = wt_dn(g, T, 0.0), Tup = wt_up(g, T, 0.0);
+    vd mixCl = wt_mix(mx, Cldn, Cl, Clup);
+    // base f of the neighbours (rows of the column's stencil) and of row 0
+    vd fdn[3], fup[3];
+    WT_UNROLL
+    for (int v = 0; v < 3; ++v) { fdn[v] = shfl_up(f[v], 1); fup[v] = shfl_down(f[v], 1); }
+    vd f_row0 = vabs(shfl_idx(f[0], g.base));
+
+    // ---- perturbation steps (common.py:330-345)
+    vd ysc[3], hh[3];
+    WT_UNROLL
+    for (int v = 0; v < 3; ++v) {
+      vd sgn = sel(f[v] >= 0.0, 1.0, -1.0);
+      ysc[v] = sgn * vmax(vabs(y[v]), WT_ATOL);
+      hh[v] = (y[v] + jfac[v] * ysc[v]) - y[v];
+      vb zero = m & (hh[v] == 0.0);
+      while (vany(zero)) {
+        jfac[v] = sel(zero, jfac[v] * 10.0, jfac[v]);
+        hh[v] = sel(zero, (y[v] + jfac[v] * ysc[v]) - y[v], hh[v]);
+        zero = m & (hh[v] == 0.0);
+      }
+    }
+
+    // results of the accepted evaluation of each column this lane's row sees
+    vd d_pp[3], d_pt[3], d_cc[3], d_ct[3], d_tt[3], d_cp = vbroadcast(0.0);  // f_new - f
+    WT_UNROLL
+    for (int k = 0; k < 3; ++k) {
+      d_pp[k] = vbroadcast(0.0); d_pt[k] = vbroadcast(0.0); d_cc[k] = vbroadcast(0.0);
+      d_ct[k] = vbroadcast(0.0); d_tt[k] = vbroadcast(0.0);
+    }
+    vd maxd[3], scl[3];
+    vb retry[3];
+    WT_UNROLL
+    for (int v = 0; v < 3; ++v) { retry[v] = vbroadcast_b(false); maxd[v] = vbroadcast(0.0); scl[v] = vbroadcast(0.0); }
+
+    for (int pass = 0; pass < 2; ++pass) {
+      vd hc[3];
+      if (pass == 1) {
+        vb anyretry = m & (retry[0] | retry[1] | retry[2]);
+        if (!vany(anyretry)) break;
+        cnt[WTC_JAC_RETRY] = cnt[WTC_JAC_RETRY] + seli(anyretry, 1, 0);
+      }
+      WT_UNROLL
+      for (int v = 0; v < 3; ++v)
+        hc[v] = (pass == 0) ? hh[v] : sel(retry[v], (y[v] + (10.0 * jfac[v]) * ysc[v]) - y[v], hh[v]);
+
+      // own perturbed quantities
+      vd pHp = pH + hc[0];
+      vd Hp = vexp10(-pHp);
+      vb bposp;
+      vd blp = wt_beta_ln10(c, Hp, bposp);
+      vd kfp_pH = kk * wt_decay_factor(c, Hp);
+      vd Clp = Cl + hc[1];
+      vd Tp = T + hc[2];
+      trange = trange | (m & wt_gany(g, wt_t_out_of_range(Tp) | wt_t_out_of_range(T)));
+      vd kfp_T = wt_arrhenius(Tp) * wt_decay_factor(c, H);
+      vd rhop = wt_density(Tp);
+
+      // ---- new f values of row z under each single-column perturbation
+      vd n_pp[3], n_pt[3], n_cc[3], n_ct[3], n_tt[3], n_cp;
+      // pH columns
+      n_pp[1] = wt_dph(wt_dph_inlet(g, c, Hp, blp, bposp), wt_mix(mx, Hdn, Hp, Hup), blp, bposp);
+      n_cp = wt_dcl(g, c, Cl, mixCl, kfp_pH);
+      n_pp[0] = wt_dph(t12, wt_mix(mx, wt_dn(g, Hp, 0.0), H, Hup), bl, bpos);
+      n_pp[2] = wt_dph(t12, wt_mix(mx, Hdn, H, wt_up(g, Hp, 0.0)), bl, bpos);
+      // Cl columns
+      n_cc[1] = wt_dcl(g, c, Clp, wt_mix(mx, Cldn, Clp, Clup), kf);
+      n_cc[0] = wt_dcl(g, c, Cl, wt_mix(mx, wt_dn(g, Clp, 0.0), Cl, Clup), kf);
+      n_cc[2] = wt_dcl(g, c, Cl, wt_mix(mx, Cldn, Cl, wt_up(g, Clp, 0.0)), kf);
+      // T columns: the perturbed density can flip the Richardson switch of either interface
+      {
+        WtMix mo = wt_mix_row(g, c, wt_suppression(c, rho_dn, rhop), wt_suppression(c, rhop, rho_up));
+        n_pt[1] = wt_dph(t12, wt_mix(mo, Hdn, H, Hup), bl, bpos);
+        n_ct[1] = wt_dcl(g, c, Cl, wt_mix(mo, Cldn, Cl, Clup), kfp_T);
+        n_tt[1] = wt_dt(g, c, Tp, wt_mix(mo, Tdn, Tp, Tup));
+        WtMix ml = wt_mix_row(g, c, wt_suppression(c, shfl_up(rhop, 1), rho), s_up);
+        n_pt[0] = wt_dph(t12, wt_mix(ml, Hdn, H, Hup), bl, bpos);
+        n_ct[0] = wt_dcl(g, c, Cl, wt_mix(ml, Cldn, Cl, Clup), kf);
+        n_tt[0] = wt_dt(g, c, T, wt_mix(ml, wt_dn(g, Tp, 0.0), T, Tup));
+        WtMix mr = wt_mix_row(g, c, s_dn, wt_suppression(c, rho, shfl_down(rhop, 1)));
+        n_pt[2] = wt_dph(t12, wt_mix(mr, Hdn, H, Hup), bl, bpos);
+        n_ct[2] = wt_dcl(g, c, Cl, wt_mix(mr, Cldn, Cl, Clup), kf);
+        n_tt[2] = wt_dt(g, c, T, wt_mix(mr, Tdn, T, wt_up(g, Tp, 0.0)));
+      }
+
+      // ---- column owner: arg-max row in species-major order (np.argmax: first maximum)
+      vd best[3], bf[3], bn[3];
+      WT_UNROLL
+      for (int v = 0; v < 3; ++v) { best[v] = vbroadcast(0.0); bf[v] = vbroadcast(0.0); bn[v] = vbroadcast(0.0); }
+      vb hasdn = !g.first, hasup = !g.last;
+#define WT_CONSIDER(v, fbase, fnew, ok)                                   \
+  {                                                                       \
+    vd fb_ = (fbase), fn_ = (fnew);                                       \
+    vd ad_ = vabs(fn_ - fb_);                                             \
+    vb take_ = (ok) & (ad_ > best[v]);                                    \
+    best[v] = sel(take_, ad_, best[v]);                                   \
+    bf[v] = sel(take_, vabs(fb_), bf[v]);                                 \
+    bn[v] = sel(take_, vabs(fn_), bn[v]);                                 \
+  }
+      vb yes = vbroadcast_b(true);
+      // column pH_z: rows pH_{z-1}, pH_z, pH_{z+1}, Cl_z
+      WT_CONSIDER(0, fdn[0], shfl_up(n_pp[2], 1), hasdn)
+      WT_CONSIDER(0, f[0], n_pp[1], yes)
+      WT_CONSIDER(0, fup[0], shfl_down(n_pp[0], 1), hasup)
+      WT_CONSIDER(0, f[1], n_cp, yes)
+      // column Cl_z: rows Cl_{z-1}, Cl_z, Cl_{z+1}
+      WT_CONSIDER(1, fdn[1], shfl_up(n_cc[2], 1), hasdn)
+      WT_CONSIDER(1, f[1], n_cc[1], yes)
+      WT_CONSIDER(1, fup[1], shfl_down(n_cc[0], 1), hasup)
+      // column T_z: rows pH, Cl, T of zones z-1, z, z+1
+      WT_CONSIDER(2, fdn[0], shfl_up(n_pt[2], 1), hasdn)
+      WT_CONSIDER(2, f[0], n_pt[1], yes)
+      WT_CONSIDER(2, fup[0], shfl_down(n_pt[0], 1), hasup)
+      WT_CONSIDER(2, fdn[1], shfl_up(n_ct[2], 1), hasdn)
+      WT_CONSIDER(2, f[1], n_ct[1], yes)
+      WT_CONSIDER(2, fup[1], shfl_down(n_ct[0], 1), hasup)
+      WT_CONSIDER(2, fdn[2], shfl_up(n_tt[2], 1), hasdn)
+      WT_CONSIDER(2, f[2], n_tt[1], yes)
+      WT_CONSIDER(2, fup[2], shfl_down(n_tt[0], 1), hasup)
+#undef WT_CONSIDER
+
+      vb upd[3];
+      WT_UNROLL
+      for (int v = 0; v < 3; ++v) {
+        // all differences zero -> argmax is row 0 of the system (pH of zone 0)
+        vd sc = sel(best[v] > 0.0, vmax(bf[v], bn[v]), f_row0);
+        if (pass == 0) {
+          maxd[v] = best[v];
+          scl[v] = sc;
+          retry[v] = best[v] < REJECT * sc;
+          upd[v] = vbroadcast_b(true);
+        } else {
+          upd[v] = retry[v] & (maxd[v] * sc < best[v] * scl[v]);
+          jfac[v] = sel(m & upd[v], 10.0 * jfac[v], jfac[v]);
+          hh[v] = sel(upd[v], hc[v], hh[v]);
+          maxd[v] = sel(upd[v], best[v], maxd[v]);
+          scl[v] = sel(upd[v], sc, scl[v]);
+        }
+      }
+      // commit the evaluations of the columns that were (re)accepted: own column by this
+      // lane's flag, neighbour columns by the owner's flag
+      WT_UNROLL
+      for (int v = 0; v < 3; ++v) {
+        vb uo = upd[v], ud, uu;
+        {
+          vi ui = seli(upd[v], 1, 0);
+          ud = shfl_up_i(ui, 1) != 0;
+          uu = shfl_down_i(ui, 1) != 0;
+        }
+        if (v == 0) {
+          d_pp[0] = sel(ud, n_pp[0] - f[0], d_pp[0]);
+          d_pp[1] = sel(uo, n_pp[1] - f[0], d_pp[1]);
+          d_pp[2] = sel(uu, n_pp[2] - f[0], d_pp[2]);
+          d_cp = sel(uo, n_cp - f[1], d_cp);
+        } else if (v == 1) {
+          d_cc[0] = sel(ud, n_cc[0] - f[1], d_cc[0]);
+          d_cc[1] = sel(uo, n_cc[1] - f[1], d_cc[1]);
+          d_cc[2] = sel(uu, n_cc[2] - f[1], d_cc[2]);
+        } else {
+          d_pt[0] = sel(ud, n_pt[0] - f[0], d_pt[0]);
+          d_pt[1] = sel(uo, n_pt[1] - f[0], d_pt[1]);
+          d_pt[2] = sel(uu, n_pt[2] - f[0], d_pt[2]);
+          d_ct[0] = sel(ud, n_ct[0] - f[1], d_ct[0]);
+          d_ct[1] = sel(uo, n_ct[1] - f[1], d_ct[1]);
+          d_ct[2] = sel(uu, n_ct[2] - f[1], d_ct[2]);
+          d_tt[0] = sel(ud, n_tt[0] - f[2], d_tt[0]);
+          d_tt[1] = sel(uo, n_tt[1] - f[2], d_tt[1]);
+          d_tt[2] = sel(uu, n_tt[2] - f[2], d_tt[2]);
+        }
+      }
+    }
+
+    // ---- J = diff / h (column-wise h), edge columns do not exist -> 0
+    vd hdn[3], hup[3];
+    WT_UNROLL
+    for (int v = 0; v < 3; ++v) { hdn[v] = shfl_up(hh[v], 1); hup[v] = shfl_down(hh[v], 1); }
+    vb hasdn = !g.first, hasup = !g.last;
+#define WT_JSET(dst, val) dst = sel(m, (val), dst)
+    WT_JSET(J.pp[0], sel(hasdn, d_pp[0] / hdn[0], 0.0));
+    WT_JSET(J.pp[1], d_pp[1] / hh[0]);
+    WT_JSET(J.pp[2], sel(hasup, d_pp[2] / hup[0], 0.0));
+    WT_JSET(J.cp, d_cp / hh[0]);
+    WT_JSET(J.cc[0], sel(hasdn, d_cc[0] / hdn[1], 0.0));
+    WT_JSET(J.cc[1], d_cc[1] / hh[1]);
+    WT_JSET(J.cc[2], sel(hasup, d_cc[2] / hup[1], 0.0));
+    WT_JSET(J.pt[0], sel(hasdn, d_pt[0] / hdn[2], 0.0));
+    WT_JSET(J.pt[1], d_pt[1] / hh[2]);
+    WT_JSET(J.pt[2], sel(hasup, d_pt[2] / hup[2], 0.0));
+    WT_JSET(J.ct[0], sel(hasdn, d_ct[0] / hdn[2], 0.0));
+    WT_JSET(J.ct[1], d_ct[1] / hh[2]);
+    WT_JSET(J.ct[2], sel(hasup, d_ct[2] / hup[2], 0.0));
+    WT_JSET(J.tt[0], sel(hasdn, d_tt[0] / hdn[2], 0.0));
+    WT_JSET(J.tt[1], d_tt[1] / hh[2]);
+    WT_JSET(J.tt[2], sel(hasup, d_tt[2] / hup[2], 0.0));
+#undef WT_JSET
+    // ---- factor adaptation (common.py:377-380)
+    WT_UNROLL
+    for (int v = 0; v < 3; ++v) {
+      vd fnew = jfac[v];
+      fnew = sel(maxd[v] < SMALL * scl[v], fnew * 10.0, fnew);
+      fnew = sel(maxd[v] > BIG * scl[v], fnew * 0.1, fnew);
+      fnew = vmax(fnew, MINF);
+      jfac[v] = sel(m, fnew, jfac[v]);
+    }
+  }
+
+  // radau.py:139-176
+  WT_DEV vd predict_factor(vd h_abs, vd h_abs_old, vd err, vd err_old, vb have_old) const {
+    vb noh = (!have_old) | (err == 0.0);
+    vd mult = sel(noh, 1.0, h_abs / h_abs_old * vpow(err_old / err, 0.25));
+    return vmin(mult, 1.0) * vpow(err, -0.25);
+  }
+
+  // Z_i[var] = sum_k T[i][k] W[k][var]   (radau.py:126)
+  WT_DEV vd zrow(int i, int v) const {
+    if (i == 0) return (WT_T00 * W[0][v] + WT_T01 * W[1][v]) + WT_T02 * W[2][v];
+    if (i == 1) return (WT_T10 * W[0][v] + WT_T11 * W[1][v]) + WT_T12 * W[2][v];
+    return (1.0 * W[0][v] + 1.0 * W[1][v]) + 0.0 * W[2][v];
+  }
+
+  // -------------------------------------------------------------------------------------
+  // the whole step: solve_ivp(Radau) over [t0, t0+dt] from (y) -> y at t0+dt
+  // -------------------------------------------------------------------------------------
+  WT_DEV void integrate(vd t0, vd dt, vb plant_on, int max_attempts) {
+    if (max_attempts <= 0 || max_attempts > WT_HARD_MAX_ATTEMPTS) max_attempts = WT_HARD_MAX_ATTEMPTS;
+    const double sqrt3N = sqrt((double)(9 * g.n));  // dW has shape (3, 3n)
+    vd t = t0;
+    const vd t_bound = t0 + dt;
+    const vd max_step = vmin(dt, 10.0);
+    WT_UNROLL
+    for (int k = 0; k < WTC_NCNT; ++k) cnt[k] = vbroadcast_i(0);
+    trange = vbroadcast_b(false);
+    failed = vbroadcast_b(false);
+    worklimit = vbroadcast_b(false);
+    have_jfac = vbroadcast_b(false);
+    have_sol = vbroadcast_b(false);
+    sol_told = vbroadcast(0.0);
+    sol_h = vbroadcast(1.0);
+    WT_UNROLL
+    for (int v = 0; v < 3; ++v) {
+      jfac[v] = vbroadcast(0.0);
+      yold[v] = y[v];
+      WT_UNROLL
+      for (int k = 0; k < 3; ++k) { W[k][v] = vbroadcast(0.0); Q[v][k] = vbroadcast(0.0); }
+    }
+    J.cp = vbroadcast(0.0);
+    WT_UNROLL
+    for (int k = 0; k < 3; ++k) {
+      J.tt[k] = vbroadcast(0.0); J.pp[k] = vbroadcast(0.0); J.pt[k] = vbroadcast(0.0);
+      J.cc[k] = vbroadcast(0.0); J.ct[k] = vbroadcast(0.0);
+    }
+
+    vb running = plant_on;
+    // ---- Radau.__init__: f0 and select_initial_step (radau.py:303-311, common.py:68-134)
+    vd self_h_abs;
+    {
+      vb bad;
+      wt_rhs(g, c, y[0], y[1], y[2], f[0], f[1], f[2], bad);
+      cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(running, 1, 0);
+      trange = trange | (running & wt_gany(g, bad));
+      vd sc[3];
+      WT_UNROLL
+      for (int v = 0; v < 3; ++v) sc[v] = WT_ATOL + vabs(y[v]) * WT_RTOL;
+      vd d0 = rms3(y[0] / sc[0], y[1] / sc[1], y[2] / sc[2]);
+      vd d1 = rms3(f[0] / sc[0], f[1] / sc[1], f[2] / sc[2]);
+      vd h0 = sel((d0 < 1e-5) | (d1 < 1e-5), 1e-6, 0.01 * d0 / d1);
+      vd interval = vabs(t_bound - t0);
+      h0 = vmin(h0, interval);
+      vd f1[3];
+      wt_rhs(g, c, y[0] + h0 * f[0], y[1] + h0 * f[1], y[2] + h0 * f[2], f1[0], f1[1], f1[2], bad);
+      cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(running, 1, 0);
+      trange = trange | (running & wt_gany(g, bad));
+      vd d2 = rms3((f1[0] - f[0]) / sc[0], (f1[1] - f[1]) / sc[1], (f1[2] - f[2]) / sc[2]) / h0;
+      vd h1 = sel((d1 <= 1e-15) & (d2 <= 1e-15), vmax(h0 * 1e-3, 1e-6), vpow(0.01 / vmax(d1, d2), 0.25));
+      self_h_abs = vmin(vmin(100.0 * h0, h1), vmin(interval, max_step));
+    }
+    running = running & !trange;
+
+    vd self_h_abs_old = vbroadcast(0.0), self_err_old = vbroadcast(0.0);
+    vb self_have_old = vbroadcast_b(false);
+    vb need_jac = running;      // first Jacobian (radau.py:363-369)
+    vb current_jac = vbroadcast_b(true);
+    vb lu_valid = vbroadcast_b(false);
+    vb new_step = vbroadcast_b(true);
+    vd h_abs = self_h_abs, h_abs_old = vbroadcast(0.0), err_old = vbroadcast(0.0);
+    vb have_old = vbroadcast_b(false);
+    vb rejected = vbroadcast_b(false);
+    vd min_step = vbroadcast(0.0);
+
+    vi attempts = vbroadcast_i(0);
+    while (vany(running)) {
+      // (1) Jacobian: first one, stale-J refresh (radau.py:467-473) or post-accept refresh (:519-521)
+      {
+        vb m = running & need_jac;
+        if (vany(m)) {
+          num_jac(m);
+          current_jac = current_jac | m;
+          lu_valid = lu_valid & !m;
+          need_jac = need_jac & !m;
+          running = running & !trange;
+        }
+      }
+      // base.py:204-208: finished once t reached t_bound
+      running = running & !(t == t_bound);
+      if (!vany(running)) break;
+
+      // (2) _step_impl entry (radau.py:413-428)
+      {
+        vb m = running & new_step;
+        vd ms = 10.0 * vabs(vnextafter_up(t) - t);
+        min_step = sel(m, ms, min_step);
+        vb big = self_h_abs > max_step, small = self_h_abs < ms;
+        vd hh_ = sel(big, max_step, sel(small, ms, self_h_abs));
+        h_abs = sel(m, hh_, h_abs);
+        h_abs_old = sel(m, self_h_abs_old, h_abs_old);
+        err_old = sel(m, self_err_old, err_old);
+        have_old = selb(m, self_have_old & !(big | small), have_old);
+        rejected = rejected & !m;
+        new_step = new_step & !m;
+      }
+      // (3) attempt setup (radau.py:439-457)
+      {
+        vb f_ = running & (h_abs < min_step);
+        failed = failed | f_;
+        running = running & !f_;
+      }
+      vd t_new = t + h_abs;
+      t_new = sel(t_new - t_bound > 0.0, t_bound, t_new);
+      const vd h = t_new - t;
+      h_abs = sel(running, vabs(h), h_abs);
+      vd scale[3];
+      WT_UNROLL
+      for (int v = 0; v < 3; ++v) scale[v] = WT_ATOL + vabs(y[v]) * WT_RTOL;
+      {
+        // Z0 = sol(t + h*C).T - y, W = TI.dot(Z0)   (radau.py:451-454, 555-578, :64)
+        vd x0 = ((t + h * WT_C0) - sol_told) / sol_h;
+        vd x1 = ((t + h * WT_C1) - sol_told) / sol_h;
+        vd x2 = ((t + h * 1.0) - sol_told) / sol_h;
+        WT_UNROLL
+        for (int v = 0; v < 3; ++v) {
+          vd z0 = (((Q[v][0] * x0 + Q[v][1] * (x0 * x0)) + Q[v][2] * ((x0 * x0) * x0)) + yold[v]) - y[v];
+          vd z1 = (((Q[v][0] * x1 + Q[v][1] * (x1 * x1)) + Q[v][2] * ((x1 * x1) * x1)) + yold[v]) - y[v];
+          vd z2 = (((Q[v][0] * x2 + Q[v][1] * (x2 * x2)) + Q[v][2] * ((x2 * x2) * x2)) + yold[v]) - y[v];
+          z0 = sel(have_sol, z0, 0.0);
+          z1 = sel(have_sol, z1, 0.0);
+          z2 = sel(have_sol, z2, 0.0);
+          W[0][v] = (WT_TI00 * z0 + WT_TI01 * z1) + WT_TI02 * z2;
+          W[1][v] = (WT_TI10 * z0 + WT_TI11 * z1) + WT_TI12 * z2;
+          W[2][v] = (WT_TI20 * z0 + WT_TI21 * z1) + WT_TI22 * z2;
+        }
+      }
+      // (4) LU of (MU/h I - J), real and complex (radau.py:460-462)
+      {
+        vb m = running & !lu_valid;
+        if (vany(m)) {
+          factor(h, m);
+          cnt[WTC_NLU] = cnt[WTC_NLU] + seli(m, 2, 0);
+          lu_valid = lu_valid | m;
+        }
+      }
+      // Engine policy (straggler policy): budget of collocation solves per step.
+      // The reference has none; plants sitting on the 8 C density discontinuity make it grind
+      // through millions of micro-steps.  Exhausted budget == exception: state left untouched.
+      {
+        attempts = attempts + seli(running, 1, 0);
+        vb over = running & (attempts > max_attempts);
+        worklimit = worklimit | over;
+        running = running & !over;
+      }
+      // (5) simplified Newton (radau.py:48-136)
+      const vd M_real = WT_MU_REAL / h, Mc_re = WT_MU_CRE / h, Mc_im = WT_MU_CIM / h;
+      vb converged = vbroadcast_b(false);
+      vb active = running;
+      vd dW_norm_old = vbroadcast(0.0), rate = vbroadcast(0.0);
+      vb have_norm_old = vbroadcast_b(false), have_rate = vbroadcast_b(false);
+      vi n_iter = vbroadcast_i(0);
+      for (int k = 0; k < WT_NEWTON_MAXITER; ++k) {
+        if (!vany(active)) break;
+        cnt[WTC_NNEWTON] = cnt[WTC_NNEWTON] + seli(active, 1, 0);
+        n_iter = seli(active, k + 1, n_iter);
+        vd fr[3], cr[3], ci[3];
+        WT_UNROLL
+        for (int v = 0; v < 3; ++v) { fr[v] = vbroadcast(0.0); cr[v] = vbroadcast(0.0); ci[v] = vbroadcast(0.0); }
+        vb finite = vbroadcast_b(true), bad_any = vbroadcast_b(false);
+        for (int i = 0; i < 3; ++i) {
+          vd F[3];
+          vb bad;
+          wt_rhs(g, c, y[0] + zrow(i, 0), y[1] + zrow(i, 1), y[2] + zrow(i, 2), F[0], F[1], F[2], bad);
+          bad_any = bad_any | bad;
+          finite = finite & visfinite(F[0]) & visfinite(F[1]) & visfinite(F[2]);
+          const double tr = i == 0 ? WT_TI00 : (i == 1 ? WT_TI01 : WT_TI02);
+          const double t1 = i == 0 ? WT_TI10 : (i == 1 ? WT_TI11 : WT_TI12);
+          const double t2 = i == 0 ? WT_TI20 : (i == 1 ? WT_TI21 : WT_TI22);
+          WT_UNROLL
+          for (int v = 0; v < 3; ++v) {
+            fr[v] = fr[v] + F[v] * tr;
+            cr[v] = cr[v] + F[v] * t1;
+            ci[v] = ci[v] + F[v] * t2;
+          }
+        }
+        cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(active, 3, 0);
+        {
+          vb tb = active & wt_gany(g, bad_any);
+          trange = trange | tb;
+          running = running & !tb;
+          active = active & !tb;
+        }
+        active = active & !wt_gany(g, !finite);  // radau.py:91-92: break, not converged
+        WT_UNROLL
+        for (int v = 0; v < 3; ++v) {
+          fr[v] = fr[v] - M_real * W[0][v];
+          vd re = cr[v] - (Mc_re * W[1][v] - Mc_im * W[2][v]);
+          vd im = ci[v] - (Mc_re * W[2][v] + Mc_im * W[1][v]);
+          cr[v] = re;
+          ci[v] = im;
+        }
+        solve_real(fr);
+        solve_cplx(cr, ci);
+        vd q = vbroadcast(0.0);
+        WT_UNROLL
+        for (int v = 0; v < 3; ++v) {
+          vd a = fr[v] / scale[v], b = cr[v] / scale[v], d = ci[v] / scale[v];
+          q = q + ((a * a + b * b) + d * d);
+        }
+        vd dW_norm = vsqrt(wt_gsum(g, q)) / sqrt3N;
+        vd new_rate = dW_norm / dW_norm_old;
+        rate = sel(active & have_norm_old, new_rate, rate);
+        have_rate = have_rate | (active & have_norm_old);
+        // rate ** (NEWTON_MAXITER - k)
+        vd rp = rate;
+        for (int e = 1; e < WT_NEWTON_MAXITER - k; ++e) rp = rp * rate;
+        vb brk = active & have_rate & ((rate >= 1.0) | (rp / (1.0 - rate) * dW_norm > WT_NEWTON_TOL));
+        active = active & !brk;
+        WT_UNROLL
+        for (int v = 0; v < 3; ++v) {
+          W[0][v] = sel(active, W[0][v] + fr[v], W[0][v]);
+          W[1][v] = sel(active, W[1][v] + cr[v], W[1][v]);
+          W[2][v] = sel(active, W[2][v] + ci[v], W[2][v]);
+        }
+        vb cv = active & ((dW_norm == 0.0) | (have_rate & (rate / (1.0 - rate) * dW_norm < WT_NEWTON_TOL)));
+        converged = converged | cv;
+        active = active & !cv;
+        dW_norm_old = dW_norm;
+        have_norm_old = vbroadcast_b(true);
+      }
+      // (6) outcome of the collocation solve (radau.py:464-481)
+      {
+        vb nc = running & !converged;
+        cnt[WTC_NNEWTON_FAIL] = cnt[WTC_NNEWTON_FAIL] + seli(nc, 1, 0);
+        vb stale = nc & !current_jac;
+        need_jac = need_jac | stale;  // recompute J at (t, y, f), same h
+        vb halve = nc & current_jac;
+        h_abs = sel(halve, h_abs * 0.5, h_abs);
+        lu_valid = lu_valid & !halve;
+      }
+      vb cv = running & converged;
+      if (!vany(cv)) continue;
+
+      // (7) error estimate and step control (radau.py:483-512)
+      vd Z[3][3], y_new[3], ZE[3], err[3], escale[3];
+      WT_UNROLL
+      for (int v = 0; v < 3; ++v) {
+        Z[0][v] = zrow(0, v); Z[1][v] = zrow(1, v); Z[2][v] = zrow(2, v);
+        y_new[v] = y[v] + Z[2][v];
+        ZE[v] = ((Z[0][v] * WT_E0 + Z[1][v] * WT_E1) + Z[2][v] * WT_E2) / h;
+        err[v] = f[v] + ZE[v];
+      }
+      solve_real(err);
+      WT_UNROLL
+      for (int v = 0; v < 3; ++v) escale[v] = WT_ATOL + vmax(vabs(y[v]), vabs(y_new[v])) * WT_RTOL;
+      vd err_norm = rms3(err[0] / escale[0], err[1] / escale[1], err[2] / escale[2]);
+      vd safety = (0.9 * (2 * WT_NEWTON_MAXITER + 1)) / vfromint(n_iter + 2 * WT_NEWTON_MAXITER);
+      {
+        vb again = cv & rejected & (err_norm > 1.0);
+        if (vany(again)) {  // radau.py:493-495
+          vd fe[3];
+          vb bad;
+          wt_rhs(g, c, y[0] + err[0], y[1] + err[1], y[2] + err[2], fe[0], fe[1], fe[2], bad);
+          cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(again, 1, 0);
+          vb tb = again & wt_gany(g, bad);
+          trange = trange | tb;
+          running = running & !tb;
+          cv = cv & !tb;
+          vd e2[3];
+          WT_UNROLL
+          for (int v = 0; v < 3; ++v) e2[v] = fe[v] + ZE[v];
+          solve_real(e2);
+          vd en2 = rms3(e2[0] / escale[0], e2[1] / escale[1], e2[2] / escale[2]);
+          err_norm = sel(again, en2, err_norm);
+        }
+      }
+      vb rej = cv & (err_norm > 1.0);
+      vb acc = cv & !rej;
+      vd pf = predict_factor(h_abs, h_abs_old, err_norm, err_old, have_old);
+      {
+        h_abs = sel(rej, h_abs * vmax(safety * pf, 0.2), h_abs);
+        lu_valid = lu_valid & !rej;
+        rejected = rejected | rej;
+        cnt[WTC_NREJECT] = cnt[WTC_NREJECT] + seli(rej, 1, 0);
+      }
+      if (vany(acc)) {  // radau.py:514-545
+        vb recompute = (n_iter > 2) & (rate > 1e-3);
+        vd fct = vmin(safety * pf, 10.0);
+        vb keep = (!recompute) & (fct < 1.2);
+        fct = sel(keep, 1.0, fct);
+        lu_valid = lu_valid & !(acc & !keep);
+        vd fn[3];
+        vb bad;
+        wt_rhs(g, c, y_new[0], y_new[1], y_new[2], fn[0], fn[1], fn[2], bad);
+        cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(acc, 1, 0);
+        {
+          vb tb = acc & wt_gany(g, bad);
+          trange = trange | tb;
+          running = running & !tb;
+          acc = acc & !tb;
+        }
+        need_jac = need_jac | (acc & recompute);
+        current_jac = selb(acc, vbroadcast_b(false), current_jac);  // set again by num_jac when recomputed
+        self_h_abs_old = sel(acc, self_h_abs, self_h_abs_old);
+        self_err_old = sel(acc, err_norm, self_err_old);
+        self_have_old = self_have_old | acc;
+        self_h_abs = sel(acc, h_abs * fct, self_h_abs);
+        WT_UNROLL
+        for (int v = 0; v < 3; ++v) {
+          Q[v][0] = sel(acc, (Z[0][v] * WT_P00 + Z[1][v] * WT_P10) + Z[2][v] * WT_P20, Q[v][0]);
+          Q[v][1] = sel(acc, (Z[0][v] * WT_P01 + Z[1][v] * WT_P11) + Z[2][v] * WT_P21, Q[v][1]);
+          Q[v][2] = sel(acc, (Z[0][v] * WT_P02 + Z[1][v] * WT_P12) + Z[2][v] * WT_P22, Q[v][2]);
+          yold[v] = sel(acc, y[v], yold[v]);
+          y[v] = sel(acc, y_new[v], y[v]);
+          f[v] = sel(acc, fn[v], f[v]);
+        }
+        sol_told = sel(acc, t, sol_told);
+        sol_h = sel(acc, t_new - t, sol_h);
+        have_sol = have_sol | acc;
+        t = sel(acc, t_new, t);
+        new_step = new_step | acc;
+        cnt[WTC_NSTEPS] = cnt[WTC_NSTEPS] + seli(acc, 1, 0);
+      }
+    }
+  }
+};
+
+// ----------------------------------------------------------------------------------------
+// reactor.py:490-541: post-processing of one step for this lane's zone.
+// Returns the plant's status bits (replicated); writes derived[3] = {H, density, decay rate}.
+// ----------------------------------------------------------------------------------------
+template <class LuStore>
+WT_DEV vi wt_finish_step(WtPlantStep<LuStore> &ps, const vd *y_in, vd *derived, vb &advance) {
+  const WtGroup &g = ps.g;
+  vi st = seli(ps.failed, (int)WTS_SOLVER_FAILED, 0);
+  st = st | seli(ps.trange, (int)WTS_T_RANGE, 0) | seli(ps.worklimit, (int)WTS_WORK_LIMIT, 0);
+  advance = !(ps.trange | ps.worklimit);  // exception inside solve_ivp: state untouched, time not advanced
+  WT_UNROLL
+  for (int v = 0; v < 3; ++v) ps.y[v] = sel(advance, ps.y[v], y_in[v]);
+  vb nonfin = !(visfinite(ps.y[0]) & visfinite(ps.y[1]) & visfinite(ps.y[2]));
+  st = st | seli(advance & wt_gany(g, nonfin), (int)WTS_NONFINITE, 0);
+  // _update_derived_state (reactor.py:511-524); the decay rate raises when T is out of range
+  derived[0] = vexp10(-ps.y[0]);
+  derived[1] = wt_density(ps.y[2]);
+  derived[2] = wt_arrhenius(ps.y[2]);
+  vb tder = advance & wt_gany(g, wt_t_out_of_range(ps.y[2]));
+  st = st | seli(tder, (int)WTS_T_RANGE_DERIVED, 0);
+  // _enforce_physical_bounds (reactor.py:526-541), skipped when the line above raised
+  vb clipok = advance & !tder;
+  vb cp = clipok & wt_gany(g, (ps.y[0] < 0.0) | (ps.y[0] > 14.0));
+  vb cc = clipok & wt_gany(g, ps.y[1] < 0.0);
+  vb ct = clipok & wt_gany(g, (ps.y[2] < 0.0) | (ps.y[2] > 100.0));
+  ps.y[0] = sel(cp, vmin(vmax(ps.y[0], 0.0), 14.0), ps.y[0]);
+  ps.y[1] = sel(cc, vmax(ps.y[1], 0.0), ps.y[1]);
+  ps.y[2] = sel(ct, vmin(vmax(ps.y[2], 0.0), 100.0), ps.y[2]);
+  st = st | seli(cp, (int)WTS_CLIP_PH, 0) | seli(cc, (int)WTS_CLIP_CL, 0) | seli(ct, (int)WTS_CLIP_T, 0);
+  return st;
+}

@@ -1,0 +1,132 @@
+/*
+ * wt_b200.h -- C ABI of the B200-native batched plant-stepping engine.
+ *
+ * Drop-in boundary for the data-parallel hot path of wt_simulator.core / wt_simulator.sensors
+ * (reference: Guivernoir/ICS-WT-PhysicsEngine).  The reference has no FFI: its boundary is the
+ * Python object API.  Each entry point below names the reference interface it stands in for;
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, every function returns 0 on success or a negative
+ *     WT_ERR_* code (a positive value is a cudaError_t).  No exceptions cross the boundary.
+ *   - "dev" pointers are device pointers of the current CUDA device; `stream` is a
+ *     cudaStream_t passed as void* (NULL = default stream).  Calls are stream-ordered and
+ *     asynchronous; buffers are borrowed for the duration of the enqueued work only.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Data layout in HBM (fp64, structure of arrays, plant index fastest):
+ *   state   y[(var * n_zones + zone) * P + p]     var: 0 pH, 1 chlorine [mg/L], 2 temperature [C]
+ *   params  par[k * P + p]                        k: WT_PAR_*   (derived per-plant constants)
+ *   bnd     bnd[k * bnd_stride + p]               k: WT_BND_*   bnd_stride = P, or 0 to broadcast
+ *   time[p], flow_rate[p], status[p] (uint32 bit mask WT_ST_*), counters[k * P + p] (int32)
+ */
+#ifndef WT_B200_H
+#define WT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WT_ABI_VERSION 1
+#define WT_MAX_ZONES 32
+
+/* derived per-plant constants; computed on the host exactly as the reference constructors do
+ * (reactor.py:228-270, chemistry.py:116-132, transport.py:202-254, 282-290) */
+enum {
+  WT_PAR_KW = 0, WT_PAR_KA1, WT_PAR_KA2, WT_PAR_KACL, WT_PAR_CT, WT_PAR_KX, WT_PAR_V, WT_PAR_ZH,
+  WT_PAR_VZL, WT_PAR_VOLUME, WT_PAR_AT, WT_PAR_STRAT, WT_NPAR
+};
+/* BoundaryConditions fields in declaration order (reactor.py:168-186) */
+enum {
+  WT_BND_INLET_FLOW = 0, WT_BND_INLET_PH, WT_BND_INLET_CL, WT_BND_INLET_T, WT_BND_ACID_FLOW,
+  WT_BND_ACID_CONC, WT_BND_CL_FLOW, WT_BND_CL_CONC, WT_BND_AMBIENT_T, WT_BND_HEAT_LOSS, WT_NBND
+};
+/* per-plant status bits written by wt_step (what the reference signals by logging / raising) */
+enum {
+  WT_ST_SOLVER_FAILED = 1u << 0,   /* solve_ivp status -1; reactor.py:486-487 only logs */
+  WT_ST_T_RANGE = 1u << 1,         /* ValueError from celsius_to_kelvin (thermodynamics.py:146-157)
+                                      inside the solve: state and time left untouched; plant HALTS */
+  WT_ST_CLIP_PH = 1u << 2,         /* reactor.py:528-531 */
+  WT_ST_CLIP_CL = 1u << 3,         /* reactor.py:533-536 */
+  WT_ST_CLIP_T = 1u << 4,          /* reactor.py:538-541 */
+  WT_ST_NONFINITE = 1u << 5,
+  WT_ST_T_RANGE_DERIVED = 1u << 6, /* ValueError in _update_derived_state (reactor.py:521-524) */
+  WT_ST_WORK_LIMIT = 1u << 7       /* engine policy, not reference behaviour: attempt budget
+                                      exhausted, state untouched; plant HALTS */
+};
+#define WT_ST_HALT_MASK (WT_ST_T_RANGE | WT_ST_WORK_LIMIT)
+/* solver path counters, accumulated per plant */
+enum {
+  WT_CNT_NFEV = 0, WT_CNT_NJEV, WT_CNT_NLU, WT_CNT_NSTEPS, WT_CNT_NNEWTON, WT_CNT_NREJECT,
+  WT_CNT_NNEWTON_FAIL, WT_CNT_JAC_RETRY, WT_NCNT
+};
+
+enum {
+  WT_OK = 0,
+  WT_ERR_BAD_ARG = -1,
+  WT_ERR_NO_DEVICE = -2,
+  WT_ERR_ALLOC = -3
+};
+
+/* Library identification / device probe.  wt_device_count returns the number of CUDA devices
+ * (0 when there is none -- the compute entry points then return WT_ERR_NO_DEVICE). */
+int wt_abi_version(void);
+int wt_device_count(void);
+const char *wt_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * IntegratedCSTR.step(dt, boundary) for P plants          (reactor.py:450-541)
+ *
+ * One launch advances every non-halted plant by one step(dt): scipy-Radau solve over
+ * [time[p], time[p]+dt], derived-state update, bound clipping.  In place on y/time/flow_rate.
+ *   derived    optional [3 * n_zones * P]: H_concentration, density, chlorine_decay_rate
+ *              (ReactorState derived fields, reactor.py:136-147), may be NULL
+ *   status     [P] in/out: plants whose word has a WT_ST_HALT_MASK bit are skipped
+ *   counters   optional [WT_NCNT * P], accumulated, may be NULL
+ *   max_attempts  budget of collocation solves per plant-step; 0 = unlimited (reference)
+ * ------------------------------------------------------------------------------------- */
+int wt_step(int P, int n_zones, double dt, const double *par_dev, const double *bnd_dev,
+            int bnd_stride, double *time_dev, double *y_dev, double *flow_rate_dev,
+            double *derived_dev, uint32_t *status_dev, int32_t *counters_dev, int max_attempts,
+            void *stream);
+
+/* Same, `n_steps` consecutive step(dt) calls fused in one launch (state stays in registers
+ * between steps; plants are independent so no grid-wide synchronisation is needed).
+ * Equivalent to calling wt_step n_steps times with unchanged boundary conditions. */
+int wt_advance(int P, int n_zones, int n_steps, double dt, const double *par_dev,
+               const double *bnd_dev, int bnd_stride, double *time_dev, double *y_dev,
+               double *flow_rate_dev, double *derived_dev, uint32_t *status_dev,
+               int32_t *counters_dev, int max_attempts, void *stream);
+
+/* IntegratedCSTR.derivatives(t, y, boundary) for P plants (reactor.py:272-448).
+ * dy has the layout of y; bad[p] != 0 where the reference would raise ValueError. */
+int wt_derivatives(int P, int n_zones, const double *par_dev, const double *bnd_dev,
+                   int bnd_stride, const double *y_dev, double *dy_dev, int32_t *bad_dev,
+                   void *stream);
+
+/* Host-buffer convenience used for end-to-end timing: copies state / boundary in, runs
+ * wt_step, copies state / status back, all on `stream`, and waits for completion.
+ * All pointers are HOST pointers with the SoA layouts above; bnd_stride is P or 0. */
+int wt_step_host(int P, int n_zones, double dt, const double *par, const double *bnd,
+                 int bnd_stride, double *time, double *y, double *flow_rate, uint32_t *status,
+                 int max_attempts);
+
+/* ---------------------------------------------------------------------------------------
+ * AqueousChemistry.calculate_pH(initial_guess) for P buffer systems   (chemistry.py:271-330)
+ *   status: 0 converged, 1 |df/dpH| < 1e-15 (RuntimeError), 2 no convergence in 100 iterations
+ *   (RuntimeError), 3 temperature outside [0,100] C (ValueError from the constructor)
+ * ------------------------------------------------------------------------------------- */
+int wt_calc_ph(int P, const double *alk_dev, const double *ct_dev, const double *temp_dev,
+               const double *guess_dev, double *ph_dev, int32_t *iters_dev, int32_t *status_dev,
+               void *stream);
+
+/* Measured-peak helper for the roofline denominator: runs a dependent-chain-free DFMA loop on
+ * every SM and returns the sustained FP64 rate in TFLOP/s (2 flops per DFMA). */
+int wt_measure_fp64_peak(double *tflops_out, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

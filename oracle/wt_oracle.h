@@ -85,7 +85,8 @@ enum {
   WT_ST_CLIP_CL = 1u << 3,         /* reactor.py:533-536 */
   WT_ST_CLIP_T = 1u << 4,          /* reactor.py:538-541 */
   WT_ST_NONFINITE = 1u << 5,       /* a state value is NaN/inf after the step */
-  WT_ST_T_RANGE_DERIVED = 1u << 6  /* ValueError in _update_derived_state (reactor.py:521-524): state assigned, not clipped */
+  WT_ST_T_RANGE_DERIVED = 1u << 6, /* ValueError in _update_derived_state (reactor.py:521-524): state assigned, not clipped */
+  WT_ST_WORK_LIMIT = 1u << 7       /* engine policy (not in the reference): attempt budget exhausted; state unchanged */
 };
 
 /* ---- solver path counters */
@@ -122,6 +123,9 @@ void wt_oracle_num_jac(const double *par, const double *bnd, int n, const double
 uint32_t wt_oracle_step(const double *par, const double *bnd, int n, double dt,
                         double *t, double *y, double *flow_rate, double *derived,
                         int32_t *counters);
+
+/* Engine policy knob mirrored for tests: budget of collocation solves per step (0 = unlimited). */
+void wt_oracle_set_max_attempts(int m);
 
 /* Batched driver: plant p uses cfg-derived par[p*WT_NPAR..], bnd[p*WT_NBND..] (or
  * bnd broadcast when bnd_stride == 0), y[p*3n..].  Runs `nsteps` steps of dt on

@@ -39,6 +39,8 @@ ST_CLIP_CL = 8
 ST_CLIP_T = 16
 ST_NONFINITE = 32
 ST_T_RANGE_DERIVED = 64
+ST_WORK_LIMIT = 128
+ST_HALT_MASK = ST_T_RANGE | ST_WORK_LIMIT
 
 
 def build(force: bool = False) -> str:
@@ -69,12 +71,18 @@ def lib():
         L.wt_oracle_step_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, dp, dp, C.c_int,
                                            dp, dp, dp, up, ip, C.c_int]
         L.wt_oracle_step_batch.restype = None
+        L.wt_oracle_set_max_attempts.argtypes = [C.c_int]
+        L.wt_oracle_set_max_attempts.restype = None
         L.wt_oracle_calc_ph.argtypes = [C.c_double] * 5 + [C.c_int, dp, ip]
         L.wt_oracle_calc_ph.restype = C.c_int
         L.wt_oracle_calc_ph_batch.argtypes = [C.c_int, dp, dp, dp, dp, dp, ip, ip, C.c_int]
         L.wt_oracle_calc_ph_batch.restype = None
         _lib = L
     return _lib
+
+
+def set_max_attempts(m: int) -> None:
+    lib().wt_oracle_set_max_attempts(int(m))
 
 
 def _dp(a):

