@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
 #pragma unroll
     for (int k = 0; k < WTP_NPAR; ++k) par[k] = a.par[(size_t)k * P + p];
 #pragma unroll
-    for (int k = 0; k < WTB_NBND; ++k) bnd[k] = a.bnd[(size_t)k * a.bnd_stride + (a.bnd_stride ? p : 0)];
+    for (int k = 0; k < WTB_NBND; ++k) bnd[k] = a.bnd[a.bnd_stride ? (size_t)k * P + p : (size_t)k];
     ps.c = wt_make_const(par, bnd);
   }
   double t = a.time[p];
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
       a.time[p] = t;
       a.status[p] = st;
       if (stepped && a.flow) {
-        const size_t bs = a.bnd_stride, bp = a.bnd_stride ? p : 0;
+        const size_t bs = a.bnd_stride ? P : 1, bp = a.bnd_stride ? p : 0;
         a.flow[p] = a.bnd[WTB_INLET_FLOW * bs + bp] + a.bnd[WTB_ACID_FLOW * bs + bp] + a.bnd[WTB_CL_FLOW * bs + bp];
       }
       if (a.counters) {
@@ -147,7 +147,7 @@ __global__ void wt_derivatives_kernel(int P, int n, const double *par_, const do
 #pragma unroll
   for (int k = 0; k < WTP_NPAR; ++k) par[k] = par_[(size_t)k * P + p];
 #pragma unroll
-  for (int k = 0; k < WTB_NBND; ++k) bnd[k] = bnd_[(size_t)k * bnd_stride + (bnd_stride ? p : 0)];
+  for (int k = 0; k < WTB_NBND; ++k) bnd[k] = bnd_[bnd_stride ? (size_t)k * P + p : (size_t)k];
   WtConst c = wt_make_const(par, bnd);
   double yy[3], d[3];
 #pragma unroll

@@ -101,6 +101,10 @@ struct WtGroup {
   vi gmask;    // bit mask of the plant's lanes
   vb first;    // z == 0
   vb last;     // z == n-1
+  int L;       // PCR levels = ceil(log2 n)
+  double inv_sqrtN, inv_sqrt3N;  // 1/sqrt(3n), 1/sqrt(9n) for the RMS norms (common.py:63-65)
+  vi lane;     // this lane
+  vi last_lane;  // last lane of this lane's plant
 };
 
 WT_DEV WtGroup wt_make_group(int n) {
@@ -122,6 +126,12 @@ WT_DEV WtGroup wt_make_group(int n) {
   g.gmask = seli(in, m, one);
   g.first = g.z == 0;
   g.last = selb(in, g.z == (n - 1), vbroadcast_b(true));
+  g.L = 0;
+  for (int s = 1; s < n; s <<= 1) ++g.L;
+  g.inv_sqrtN = 1.0 / sqrt((double)(3 * n));
+  g.inv_sqrt3N = 1.0 / sqrt((double)(9 * n));
+  g.lane = lane;
+  g.last_lane = seli(in, g.base + (n - 1), lane);
   return g;
 }
 
@@ -130,6 +140,11 @@ WT_DEV vd wt_dn(const WtGroup &g, vd x, double dflt) { return sel(g.first, dflt,
 WT_DEV vd wt_up(const WtGroup &g, vd x, double dflt) { return sel(g.last, dflt, shfl_down(x, 1)); }
 WT_DEV vd wt_dn_s(const WtGroup &g, vd x, int s) { return sel(g.z >= s, shfl_up(x, s), 0.0); }
 WT_DEV vd wt_up_s(const WtGroup &g, vd x, int s) { return sel((g.z + s) < g.n, shfl_down(x, s), 0.0); }
+// Source lanes at stride s CLAMPED to the plant: a lane never reads another plant's values (no
+// foreign NaNs), and in the PCR recurrences the coefficient multiplying a clamped (i.e.
+// non-existent) neighbour is exactly zero, so no select is needed on the fetched value.
+WT_DEV vi wt_src_dn(const WtGroup &g, int s) { return vmaxi(g.lane - s, g.base); }
+WT_DEV vi wt_src_up(const WtGroup &g, int s) { return vmini(g.lane + s, g.last_lane); }
 
 // sum over the plant's lanes, result replicated on all of them
 WT_DEV vd wt_gsum(const WtGroup &g, vd x) {
@@ -145,7 +160,7 @@ struct WtConst {
   vd Kw, Ka1, Ka12, KaCl, CT2303, Kx, zh, v2;
   vb strat, v_ok;
   // boundary-derived (reactor.py:336, 349-368, 388-395, 420, 426-443)
-  vd QV, Hin, dHd, cl_dose, inCl, inT, hlA, amb, hl_den;
+  vd QV, Hin, dHd, cl_dose, inCl, inT, hlA, amb, inv_hl_den, Ri_thr;
   vb acid_on, cl_on, hl_on;
 };
 
@@ -162,18 +177,19 @@ WT_DEV WtConst wt_make_const(const vd *par, const vd *bnd) {
   c.v2 = par[WTP_V] * par[WTP_V];
   c.v_ok = par[WTP_V] > 1e-6;
   c.strat = par[WTP_STRAT] != 0.0;
-  c.QV = (bnd[WTB_INLET_FLOW] / 60.0) / par[WTP_VOLUME];
+  c.QV = wt_div(bnd[WTB_INLET_FLOW] / 60.0, par[WTP_VOLUME]);
   c.Hin = vexp10(-bnd[WTB_INLET_PH]);
   c.acid_on = bnd[WTB_ACID_FLOW] > 0.0;
-  c.dHd = ((bnd[WTB_ACID_FLOW] / 60.0) * bnd[WTB_ACID_CONC]) / par[WTP_VZL];
+  c.dHd = wt_div((bnd[WTB_ACID_FLOW] / 60.0) * bnd[WTB_ACID_CONC], par[WTP_VZL]);
   c.cl_on = bnd[WTB_CL_FLOW] > 0.0;
-  c.cl_dose = ((bnd[WTB_CL_FLOW] / 60.0) * bnd[WTB_CL_CONC]) / par[WTP_VZL];
+  c.cl_dose = wt_div((bnd[WTB_CL_FLOW] / 60.0) * bnd[WTB_CL_CONC], par[WTP_VZL]);
   c.inCl = bnd[WTB_INLET_CL];
   c.inT = bnd[WTB_INLET_T];
   c.hl_on = bnd[WTB_HEAT_LOSS] > 0.0;
   c.hlA = bnd[WTB_HEAT_LOSS] * par[WTP_AT];
   c.amb = bnd[WTB_AMBIENT_T];
-  c.hl_den = (998.2 * 4184.0) * (par[WTP_VOLUME] / 1000.0);
+  c.inv_hl_den = wt_rcp((998.2 * 4184.0) * (par[WTP_VOLUME] / 1000.0));
+  c.Ri_thr = 0.25 * c.v2;
   return c;
 }
 
@@ -194,27 +210,29 @@ WT_DEV vd wt_density(vd T) {
 WT_DEV vd wt_suppression(const WtConst &c, vd rho_lo, vd rho_hi) {
   vd drho = rho_hi - rho_lo;
   vd ravg = 0.5 * (rho_lo + rho_hi);
-  vd Ri = ((9.81 * drho) * c.zh) / (ravg * c.v2);
-  vb stable = (!c.v_ok) | (Ri > 0.25);  // v <= 1e-6 -> Ri = +inf
+  // Ri = (g drho zh)/(ravg v^2) > 0.25, cross-multiplied (ravg v^2 > 0): same decision except
+  // within an ulp of the threshold; v <= 1e-6 -> Ri = +inf
+  vb stable = (!c.v_ok) | (((9.81 * drho) * c.zh) > ravg * c.Ri_thr);
   return sel(c.strat & stable, 0.5, 1.0);
 }
 
 // thermodynamics.py:187-193
 WT_DEV vd wt_arrhenius(vd T) {
   vd TK = T + 273.15;
-  vd e = -(45000.0 / 8.314) * (1.0 / TK - 1.0 / 293.15);
+  vd e = -(45000.0 / 8.314) * (wt_rcp(TK) - 1.0 / 293.15);
   return 0.0001 * vexp(e);
 }
 WT_DEV vb wt_t_out_of_range(vd T) { return (T < 0.0) | (T > 100.0); }  // thermodynamics.py:146-157
 
 // chemistry.py:422-437 (+ :181-191): beta(pH) * ln(10)
 WT_DEV vd wt_beta_ln10(const WtConst &c, vd H, vb &bpos) {
-  vd bw = 2.303 * (H + c.Kw / H);
+  vd bw = 2.303 * (H + c.Kw * wt_rcp(H));
   vd HH = H * H;
   vd D = HH + c.Ka1 * H + c.Ka12;
-  vd a0 = HH / D;
-  vd a1 = (c.Ka1 * H) / D;
-  vd a2 = c.Ka12 / D;
+  vd iD = wt_rcp(D);  // the three alphas share one reciprocal (<= 1 ulp from three divisions)
+  vd a0 = HH * iD;
+  vd a1 = (c.Ka1 * H) * iD;
+  vd a2 = c.Ka12 * iD;
   vd bc = c.CT2303 * (a0 * a1 + (4.0 * a1) * a2 + a0 * a2);
   vd beta = bw + bc;
   bpos = beta > 0.0;
@@ -223,8 +241,8 @@ WT_DEV vd wt_beta_ln10(const WtConst &c, vd H, vb &bpos) {
 
 // chemistry.py:510-523
 WT_DEV vd wt_decay_factor(const WtConst &c, vd H) {
-  vd den = H + c.KaCl;
-  return (H / den) * 1.0 + (c.KaCl / den) * 0.02;
+  vd iden = wt_rcp(H + c.KaCl);
+  return (H * iden) * 1.0 + (c.KaCl * iden) * 0.02;
 }
 
 struct WtMix { vd off_dn, off_up, diag; };
@@ -241,14 +259,15 @@ WT_DEV WtMix wt_mix_row(const WtGroup &g, const WtConst &c, vd s_dn, vd s_up) {
 WT_DEV vd wt_mix(const WtMix &m, vd xdn, vd x, vd xup) { return (m.off_dn * xdn + m.diag * x) + m.off_up * xup; }
 
 // reactor.py:349-368: the zone-0-only acid dosing + inlet terms of dpH (0 elsewhere)
-WT_DEV vd wt_dph_inlet(const WtGroup &g, const WtConst &c, vd H, vd bl, vb bpos) {
-  vd t1 = sel(g.first & c.acid_on & bpos, -c.dHd / bl, 0.0);
+// (ibl = 1 / (beta ln10): the up-to-three quotients of zone 0 share one reciprocal)
+WT_DEV vd wt_dph_inlet(const WtGroup &g, const WtConst &c, vd H, vd ibl, vb bpos) {
+  vd t1 = sel(g.first & c.acid_on & bpos, -c.dHd * ibl, 0.0);
   vd dHin = c.QV * (c.Hin - H);
-  vd t2 = sel(g.first & bpos, -dHin / bl, 0.0);
+  vd t2 = sel(g.first & bpos, -dHin * ibl, 0.0);
   return (0.0 + t1) + t2;
 }
 // reactor.py:371-376
-WT_DEV vd wt_dph(vd t12, vd mixH, vd bl, vb bpos) { return t12 + sel(bpos, -mixH / bl, 0.0); }
+WT_DEV vd wt_dph(vd t12, vd mixH, vd ibl, vb bpos) { return t12 + sel(bpos, -mixH * ibl, 0.0); }
 // reactor.py:388-411
 WT_DEV vd wt_dcl(const WtGroup &g, const WtConst &c, vd Cl, vd mixCl, vd kf) {
   vd r = sel(g.first & c.cl_on, c.cl_dose, 0.0);
@@ -260,8 +279,11 @@ WT_DEV vd wt_dcl(const WtGroup &g, const WtConst &c, vd Cl, vd mixCl, vd kf) {
 WT_DEV vd wt_dt(const WtGroup &g, const WtConst &c, vd T, vd mixT) {
   vd r = sel(g.first, c.QV * (c.inT - T), 0.0);
   r = r + mixT;
-  vd loss = (c.hlA * (T - c.amb)) / c.hl_den;
-  return sel(c.hl_on, r - loss, r);
+  if (vany(c.hl_on)) {  // warp-uniform: adiabatic ensembles skip the term entirely
+    vd loss = (c.hlA * (T - c.amb)) * c.inv_hl_den;
+    r = sel(c.hl_on, r - loss, r);
+  }
+  return r;
 }
 
 // Full RHS for this lane's zone.  `bad` is set where the reference would raise ValueError.
@@ -273,9 +295,9 @@ WT_DEV void wt_rhs(const WtGroup &g, const WtConst &c, vd pH, vd Cl, vd T, vd &d
   WtMix m = wt_mix_row(g, c, s_dn, s_up);
   vd H = vexp10(-pH);
   vb bpos;
-  vd bl = wt_beta_ln10(c, H, bpos);
+  vd ibl = wt_rcp(wt_beta_ln10(c, H, bpos));
   vd mixH = wt_mix(m, wt_dn(g, H, 0.0), H, wt_up(g, H, 0.0));
-  dpH = wt_dph(wt_dph_inlet(g, c, H, bl, bpos), mixH, bl, bpos);
+  dpH = wt_dph(wt_dph_inlet(g, c, H, ibl, bpos), mixH, ibl, bpos);
   vd kf = wt_arrhenius(T) * wt_decay_factor(c, H);
   dCl = wt_dcl(g, c, Cl, wt_mix(m, wt_dn(g, Cl, 0.0), Cl, wt_up(g, Cl, 0.0)), kf);
   dT = wt_dt(g, c, T, wt_mix(m, wt_dn(g, T, 0.0), T, wt_up(g, T, 0.0)));
@@ -290,30 +312,33 @@ WT_DEV void wt_rhs(const WtGroup &g, const WtConst &c, vd pH, vd Cl, vd T, vd &d
 //   void put(int slot, vd x, vb mask);   vd get(int slot);
 
 WT_DEV int wt_pcr_levels(int n) { int L = 0; for (int s = 1; s < n; s <<= 1) ++L; return L; }
-WT_DEV int wt_slots_real(int n) { return 2 * wt_pcr_levels(n) + 1; }
 
+// Rows: a x[z-1] + b x[z] + c x[z+1] = d, with a = 0 on the first and c = 0 on the last zone.
+// At the level of stride s the multipliers that would touch a neighbour outside the plant are
+// exactly 0 (a stays 0 on zones < s, c on zones >= n-s), so fetched values need no masking.
 template <class LuStore>
 WT_DEV void wt_pcr_factor_real(const WtGroup &g, LuStore &lu, int slot0, vd a, vd b, vd c, vb mask) {
   int l = 0;
   for (int s = 1; s < g.n; s <<= 1, ++l) {
-    vd r = 1.0 / b;
-    vd k1 = a * wt_dn_s(g, r, s);
-    vd k2 = c * wt_up_s(g, r, s);
-    vd a_dn = wt_dn_s(g, a, s), c_dn = wt_dn_s(g, c, s);
-    vd a_up = wt_up_s(g, a, s), c_up = wt_up_s(g, c, s);
+    const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
+    vd r = wt_rcp(b);
+    vd k1 = a * shfl_idx(r, sd);
+    vd k2 = c * shfl_idx(r, su);
+    vd a_dn = shfl_idx(a, sd), c_dn = shfl_idx(c, sd);
+    vd a_up = shfl_idx(a, su), c_up = shfl_idx(c, su);
     b = b - c_dn * k1 - a_up * k2;
     a = -(a_dn * k1);
     c = -(c_up * k2);
     lu.put(slot0 + 2 * l, k1, mask);
     lu.put(slot0 + 2 * l + 1, k2, mask);
   }
-  lu.put(slot0 + 2 * l, 1.0 / b, mask);
+  lu.put(slot0 + 2 * l, wt_rcp(b), mask);
 }
 template <class LuStore>
 WT_DEV vd wt_pcr_solve_real(const WtGroup &g, LuStore &lu, int slot0, vd d) {
   int l = 0;
   for (int s = 1; s < g.n; s <<= 1, ++l)
-    d = d - wt_dn_s(g, d, s) * lu.get(slot0 + 2 * l) - wt_up_s(g, d, s) * lu.get(slot0 + 2 * l + 1);
+    d = d - shfl_idx(d, wt_src_dn(g, s)) * lu.get(slot0 + 2 * l) - shfl_idx(d, wt_src_up(g, s)) * lu.get(slot0 + 2 * l + 1);
   return d * lu.get(slot0 + 2 * l);
 }
 
@@ -324,14 +349,15 @@ WT_DEV void wt_pcr_factor_cplx(const WtGroup &g, LuStore &lu, int slot0, vd ar, 
   vd ai = vbroadcast(0.0), ci = vbroadcast(0.0);
   int l = 0;
   for (int s = 1; s < g.n; s <<= 1, ++l) {
-    vd den = br * br + bi * bi;
-    vd rr = br / den, ri = -bi / den;  // 1 / b
-    vd rdr = wt_dn_s(g, rr, s), rdi = wt_dn_s(g, ri, s);
-    vd rur = wt_up_s(g, rr, s), rui = wt_up_s(g, ri, s);
+    const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
+    vd iden = wt_rcp(br * br + bi * bi);
+    vd rr = br * iden, ri = -(bi * iden);  // 1 / b
+    vd rdr = shfl_idx(rr, sd), rdi = shfl_idx(ri, sd);
+    vd rur = shfl_idx(rr, su), rui = shfl_idx(ri, su);
     vd k1r = ar * rdr - ai * rdi, k1i = ar * rdi + ai * rdr;
     vd k2r = cr * rur - ci * rui, k2i = cr * rui + ci * rur;
-    vd adr = wt_dn_s(g, ar, s), adi = wt_dn_s(g, ai, s), cdr = wt_dn_s(g, cr, s), cdi = wt_dn_s(g, ci, s);
-    vd aur = wt_up_s(g, ar, s), aui = wt_up_s(g, ai, s), cur = wt_up_s(g, cr, s), cui = wt_up_s(g, ci, s);
+    vd adr = shfl_idx(ar, sd), adi = shfl_idx(ai, sd), cdr = shfl_idx(cr, sd), cdi = shfl_idx(ci, sd);
+    vd aur = shfl_idx(ar, su), aui = shfl_idx(ai, su), cur = shfl_idx(cr, su), cui = shfl_idx(ci, su);
     br = br - (cdr * k1r - cdi * k1i) - (aur * k2r - aui * k2i);
     bi = bi - (cdr * k1i + cdi * k1r) - (aur * k2i + aui * k2r);
     ar = -(adr * k1r - adi * k1i);
@@ -343,17 +369,18 @@ WT_DEV void wt_pcr_factor_cplx(const WtGroup &g, LuStore &lu, int slot0, vd ar, 
     lu.put(slot0 + 4 * l + 2, k2r, mask);
     lu.put(slot0 + 4 * l + 3, k2i, mask);
   }
-  vd den = br * br + bi * bi;
-  lu.put(slot0 + 4 * l + 0, br / den, mask);
-  lu.put(slot0 + 4 * l + 1, -bi / den, mask);
+  vd iden = wt_rcp(br * br + bi * bi);
+  lu.put(slot0 + 4 * l + 0, br * iden, mask);
+  lu.put(slot0 + 4 * l + 1, -(bi * iden), mask);
 }
 template <class LuStore>
 WT_DEV void wt_pcr_solve_cplx(const WtGroup &g, LuStore &lu, int slot0, vd &dr, vd &di) {
   int l = 0;
   for (int s = 1; s < g.n; s <<= 1, ++l) {
+    const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
     vd k1r = lu.get(slot0 + 4 * l + 0), k1i = lu.get(slot0 + 4 * l + 1);
     vd k2r = lu.get(slot0 + 4 * l + 2), k2i = lu.get(slot0 + 4 * l + 3);
-    vd ddr = wt_dn_s(g, dr, s), ddi = wt_dn_s(g, di, s), dur = wt_up_s(g, dr, s), dui = wt_up_s(g, di, s);
+    vd ddr = shfl_idx(dr, sd), ddi = shfl_idx(di, sd), dur = shfl_idx(dr, su), dui = shfl_idx(di, su);
     vd nr = dr - (ddr * k1r - ddi * k1i) - (dur * k2r - dui * k2i);
     vd ni = di - (ddr * k1i + ddi * k1r) - (dur * k2i + dui * k2r);
     dr = nr;
@@ -398,15 +425,16 @@ struct WtPlantStep {
   vb failed;      // TOO_SMALL_STEP
   vb worklimit;   // engine policy: attempt budget exhausted (not reference behaviour)
 
-  WT_DEV int slot_real(int sys) const { return sys * wt_slots_real(g.n); }
-  WT_DEV int slot_cplx(int sys) const { return 3 * wt_slots_real(g.n) + sys * (4 * wt_pcr_levels(g.n) + 2); }
+  WT_DEV int slot_real(int sys) const { return sys * (2 * g.L + 1); }
+  WT_DEV int slot_cplx(int sys) const { return 3 * (2 * g.L + 1) + sys * (4 * g.L + 2); }
 
   // -------------------------------------------------------------------------------------
   // linear algebra on the block-triangular structure.  System order: 0 = T, 1 = pH, 2 = Cl.
   // -------------------------------------------------------------------------------------
   WT_DEV void factor(vd h, vb mask) {
-    vd mr = WT_MU_REAL / h;
-    vd cr = WT_MU_CRE / h, ci = WT_MU_CIM / h;
+    vd ih = wt_rcp(h);
+    vd mr = WT_MU_REAL * ih;
+    vd cr = WT_MU_CRE * ih, ci = WT_MU_CIM * ih;
     wt_pcr_factor_real(g, *lu, slot_real(0), -J.tt[0], mr - J.tt[1], -J.tt[2], mask);
     wt_pcr_factor_real(g, *lu, slot_real(1), -J.pp[0], mr - J.pp[1], -J.pp[2], mask);
     wt_pcr_factor_real(g, *lu, slot_real(2), -J.cc[0], mr - J.cc[1], -J.cc[2], mask);
@@ -437,7 +465,7 @@ struct WtPlantStep {
   // common.py:63-65 over the plant's 3n unknowns
   WT_DEV vd rms3(vd a, vd b, vd cc_) const {
     vd s = wt_gsum(g, (a * a + b * b) + cc_ * cc_);
-    return vsqrt(s) / sqrt((double)(3 * g.n));
+    return vsqrt(s) * g.inv_sqrtN;
   }
 
   // -------------------------------------------------------------------------------------
@@ -463,7 +491,7 @@ struct WtPlantStep {
     WtMix mx = wt_mix_row(g, c, s_dn, s_up);
     vd H = vexp10(-pH);
     vb bpos;
-    vd bl = wt_beta_ln10(c, H, bpos);
+    vd bl = wt_rcp(wt_beta_ln10(c, H, bpos));  // 1 / (beta ln10)
     vd t12 = wt_dph_inlet(g, c, H, bl, bpos);
     vd kk = wt_arrhenius(T);
     vd kf = kk * wt_decay_factor(c, H);
@@ -519,7 +547,7 @@ struct WtPlantStep {
       vd pHp = pH + hc[0];
       vd Hp = vexp10(-pHp);
       vb bposp;
-      vd blp = wt_beta_ln10(c, Hp, bposp);
+      vd blp = wt_rcp(wt_beta_ln10(c, Hp, bposp));
       vd kfp_pH = kk * wt_decay_factor(c, Hp);
       vd Clp = Cl + hc[1];
       vd Tp = T + hc[2];
@@ -642,27 +670,27 @@ struct WtPlantStep {
     }
 
     // ---- J = diff / h (column-wise h), edge columns do not exist -> 0
-    vd hdn[3], hup[3];
+    vd hdn[3], hup[3];  // reciprocal steps of this and the neighbouring columns
     WT_UNROLL
-    for (int v = 0; v < 3; ++v) { hdn[v] = shfl_up(hh[v], 1); hup[v] = shfl_down(hh[v], 1); }
+    for (int v = 0; v < 3; ++v) { hh[v] = wt_rcp(hh[v]); hdn[v] = shfl_up(hh[v], 1); hup[v] = shfl_down(hh[v], 1); }
     vb hasdn = !g.first, hasup = !g.last;
 #define WT_JSET(dst, val) dst = sel(m, (val), dst)
-    WT_JSET(J.pp[0], sel(hasdn, d_pp[0] / hdn[0], 0.0));
-    WT_JSET(J.pp[1], d_pp[1] / hh[0]);
-    WT_JSET(J.pp[2], sel(hasup, d_pp[2] / hup[0], 0.0));
-    WT_JSET(J.cp, d_cp / hh[0]);
-    WT_JSET(J.cc[0], sel(hasdn, d_cc[0] / hdn[1], 0.0));
-    WT_JSET(J.cc[1], d_cc[1] / hh[1]);
-    WT_JSET(J.cc[2], sel(hasup, d_cc[2] / hup[1], 0.0));
-    WT_JSET(J.pt[0], sel(hasdn, d_pt[0] / hdn[2], 0.0));
-    WT_JSET(J.pt[1], d_pt[1] / hh[2]);
-    WT_JSET(J.pt[2], sel(hasup, d_pt[2] / hup[2], 0.0));
-    WT_JSET(J.ct[0], sel(hasdn, d_ct[0] / hdn[2], 0.0));
-    WT_JSET(J.ct[1], d_ct[1] / hh[2]);
-    WT_JSET(J.ct[2], sel(hasup, d_ct[2] / hup[2], 0.0));
-    WT_JSET(J.tt[0], sel(hasdn, d_tt[0] / hdn[2], 0.0));
-    WT_JSET(J.tt[1], d_tt[1] / hh[2]);
-    WT_JSET(J.tt[2], sel(hasup, d_tt[2] / hup[2], 0.0));
+    WT_JSET(J.pp[0], sel(hasdn, d_pp[0] * hdn[0], 0.0));
+    WT_JSET(J.pp[1], d_pp[1] * hh[0]);
+    WT_JSET(J.pp[2], sel(hasup, d_pp[2] * hup[0], 0.0));
+    WT_JSET(J.cp, d_cp * hh[0]);
+    WT_JSET(J.cc[0], sel(hasdn, d_cc[0] * hdn[1], 0.0));
+    WT_JSET(J.cc[1], d_cc[1] * hh[1]);
+    WT_JSET(J.cc[2], sel(hasup, d_cc[2] * hup[1], 0.0));
+    WT_JSET(J.pt[0], sel(hasdn, d_pt[0] * hdn[2], 0.0));
+    WT_JSET(J.pt[1], d_pt[1] * hh[2]);
+    WT_JSET(J.pt[2], sel(hasup, d_pt[2] * hup[2], 0.0));
+    WT_JSET(J.ct[0], sel(hasdn, d_ct[0] * hdn[2], 0.0));
+    WT_JSET(J.ct[1], d_ct[1] * hh[2]);
+    WT_JSET(J.ct[2], sel(hasup, d_ct[2] * hup[2], 0.0));
+    WT_JSET(J.tt[0], sel(hasdn, d_tt[0] * hdn[2], 0.0));
+    WT_JSET(J.tt[1], d_tt[1] * hh[2]);
+    WT_JSET(J.tt[2], sel(hasup, d_tt[2] * hup[2], 0.0));
 #undef WT_JSET
     // ---- factor adaptation (common.py:377-380)
     WT_UNROLL
@@ -678,8 +706,10 @@ struct WtPlantStep {
   // radau.py:139-176
   WT_DEV vd predict_factor(vd h_abs, vd h_abs_old, vd err, vd err_old, vb have_old) const {
     vb noh = (!have_old) | (err == 0.0);
-    vd mult = sel(noh, 1.0, h_abs / h_abs_old * vpow(err_old / err, 0.25));
-    return vmin(mult, 1.0) * vpow(err, -0.25);
+    // x ** 0.25 = sqrt(sqrt(x)) (differs from pow by rounding only)
+    vd ie = wt_rcp(err);
+    vd mult = sel(noh, 1.0, wt_div(h_abs, h_abs_old) * vsqrt(vsqrt(err_old * ie)));
+    return vmin(mult, 1.0) * vsqrt(vsqrt(ie));
   }
 
   // Z_i[var] = sum_k T[i][k] W[k][var]   (radau.py:126)
@@ -694,7 +724,6 @@ struct WtPlantStep {
   // -------------------------------------------------------------------------------------
   WT_DEV void integrate(vd t0, vd dt, vb plant_on, int max_attempts) {
     if (max_attempts <= 0 || max_attempts > WT_HARD_MAX_ATTEMPTS) max_attempts = WT_HARD_MAX_ATTEMPTS;
-    const double sqrt3N = sqrt((double)(9 * g.n));  // dW has shape (3, 3n)
     vd t = t0;
     const vd t_bound = t0 + dt;
     const vd max_step = vmin(dt, 10.0);
@@ -729,20 +758,20 @@ struct WtPlantStep {
       wt_rhs(g, c, y[0], y[1], y[2], f[0], f[1], f[2], bad);
       cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(running, 1, 0);
       trange = trange | (running & wt_gany(g, bad));
-      vd sc[3];
+      vd sc[3];  // 1 / scale
       WT_UNROLL
-      for (int v = 0; v < 3; ++v) sc[v] = WT_ATOL + vabs(y[v]) * WT_RTOL;
-      vd d0 = rms3(y[0] / sc[0], y[1] / sc[1], y[2] / sc[2]);
-      vd d1 = rms3(f[0] / sc[0], f[1] / sc[1], f[2] / sc[2]);
-      vd h0 = sel((d0 < 1e-5) | (d1 < 1e-5), 1e-6, 0.01 * d0 / d1);
+      for (int v = 0; v < 3; ++v) sc[v] = wt_rcp(WT_ATOL + vabs(y[v]) * WT_RTOL);
+      vd d0 = rms3(y[0] * sc[0], y[1] * sc[1], y[2] * sc[2]);
+      vd d1 = rms3(f[0] * sc[0], f[1] * sc[1], f[2] * sc[2]);
+      vd h0 = sel((d0 < 1e-5) | (d1 < 1e-5), 1e-6, wt_div(0.01 * d0, d1));
       vd interval = vabs(t_bound - t0);
       h0 = vmin(h0, interval);
       vd f1[3];
       wt_rhs(g, c, y[0] + h0 * f[0], y[1] + h0 * f[1], y[2] + h0 * f[2], f1[0], f1[1], f1[2], bad);
       cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(running, 1, 0);
       trange = trange | (running & wt_gany(g, bad));
-      vd d2 = rms3((f1[0] - f[0]) / sc[0], (f1[1] - f[1]) / sc[1], (f1[2] - f[2]) / sc[2]) / h0;
-      vd h1 = sel((d1 <= 1e-15) & (d2 <= 1e-15), vmax(h0 * 1e-3, 1e-6), vpow(0.01 / vmax(d1, d2), 0.25));
+      vd d2 = wt_div(rms3((f1[0] - f[0]) * sc[0], (f1[1] - f[1]) * sc[1], (f1[2] - f[2]) * sc[2]), h0);
+      vd h1 = sel((d1 <= 1e-15) & (d2 <= 1e-15), vmax(h0 * 1e-3, 1e-6), vsqrt(vsqrt(wt_div(0.01, vmax(d1, d2)))));
       self_h_abs = vmin(vmin(100.0 * h0, h1), vmin(interval, max_step));
     }
     running = running & !trange;
@@ -799,14 +828,16 @@ struct WtPlantStep {
       t_new = sel(t_new - t_bound > 0.0, t_bound, t_new);
       const vd h = t_new - t;
       h_abs = sel(running, vabs(h), h_abs);
-      vd scale[3];
+      vd scale[3];  // 1 / (atol + |y| rtol)
       WT_UNROLL
-      for (int v = 0; v < 3; ++v) scale[v] = WT_ATOL + vabs(y[v]) * WT_RTOL;
+      for (int v = 0; v < 3; ++v) scale[v] = wt_rcp(WT_ATOL + vabs(y[v]) * WT_RTOL);
+      const vd ih = wt_rcp(h);
       {
+        const vd isolh = wt_rcp(sol_h);
         // Z0 = sol(t + h*C).T - y, W = TI.dot(Z0)   (radau.py:451-454, 555-578, :64)
-        vd x0 = ((t + h * WT_C0) - sol_told) / sol_h;
-        vd x1 = ((t + h * WT_C1) - sol_told) / sol_h;
-        vd x2 = ((t + h * 1.0) - sol_told) / sol_h;
+        vd x0 = ((t + h * WT_C0) - sol_told) * isolh;
+        vd x1 = ((t + h * WT_C1) - sol_told) * isolh;
+        vd x2 = ((t + h * 1.0) - sol_told) * isolh;
         WT_UNROLL
         for (int v = 0; v < 3; ++v) {
           vd z0 = (((Q[v][0] * x0 + Q[v][1] * (x0 * x0)) + Q[v][2] * ((x0 * x0) * x0)) + yold[v]) - y[v];
@@ -839,7 +870,7 @@ struct WtPlantStep {
         running = running & !over;
       }
       // (5) simplified Newton (radau.py:48-136)
-      const vd M_real = WT_MU_REAL / h, Mc_re = WT_MU_CRE / h, Mc_im = WT_MU_CIM / h;
+      const vd M_real = WT_MU_REAL * ih, Mc_re = WT_MU_CRE * ih, Mc_im = WT_MU_CIM * ih;
       vb converged = vbroadcast_b(false);
       vb active = running;
       vd dW_norm_old = vbroadcast(0.0), rate = vbroadcast(0.0);
@@ -890,17 +921,18 @@ struct WtPlantStep {
         vd q = vbroadcast(0.0);
         WT_UNROLL
         for (int v = 0; v < 3; ++v) {
-          vd a = fr[v] / scale[v], b = cr[v] / scale[v], d = ci[v] / scale[v];
+          vd a = fr[v] * scale[v], b = cr[v] * scale[v], d = ci[v] * scale[v];
           q = q + ((a * a + b * b) + d * d);
         }
-        vd dW_norm = vsqrt(wt_gsum(g, q)) / sqrt3N;
-        vd new_rate = dW_norm / dW_norm_old;
+        vd dW_norm = vsqrt(wt_gsum(g, q)) * g.inv_sqrt3N;
+        vd new_rate = wt_div(dW_norm, dW_norm_old);
         rate = sel(active & have_norm_old, new_rate, rate);
         have_rate = have_rate | (active & have_norm_old);
         // rate ** (NEWTON_MAXITER - k)
         vd rp = rate;
         for (int e = 1; e < WT_NEWTON_MAXITER - k; ++e) rp = rp * rate;
-        vb brk = active & have_rate & ((rate >= 1.0) | (rp / (1.0 - rate) * dW_norm > WT_NEWTON_TOL));
+        const vd i1r = wt_rcp(1.0 - rate);
+        vb brk = active & have_rate & ((rate >= 1.0) | (rp * i1r * dW_norm > WT_NEWTON_TOL));
         active = active & !brk;
         WT_UNROLL
         for (int v = 0; v < 3; ++v) {
@@ -908,7 +940,7 @@ struct WtPlantStep {
           W[1][v] = sel(active, W[1][v] + cr[v], W[1][v]);
           W[2][v] = sel(active, W[2][v] + ci[v], W[2][v]);
         }
-        vb cv = active & ((dW_norm == 0.0) | (have_rate & (rate / (1.0 - rate) * dW_norm < WT_NEWTON_TOL)));
+        vb cv = active & ((dW_norm == 0.0) | (have_rate & (rate * i1r * dW_norm < WT_NEWTON_TOL)));
         converged = converged | cv;
         active = active & !cv;
         dW_norm_old = dW_norm;
@@ -933,14 +965,14 @@ struct WtPlantStep {
       for (int v = 0; v < 3; ++v) {
         Z[0][v] = zrow(0, v); Z[1][v] = zrow(1, v); Z[2][v] = zrow(2, v);
         y_new[v] = y[v] + Z[2][v];
-        ZE[v] = ((Z[0][v] * WT_E0 + Z[1][v] * WT_E1) + Z[2][v] * WT_E2) / h;
+        ZE[v] = ((Z[0][v] * WT_E0 + Z[1][v] * WT_E1) + Z[2][v] * WT_E2) * ih;
         err[v] = f[v] + ZE[v];
       }
       solve_real(err);
       WT_UNROLL
-      for (int v = 0; v < 3; ++v) escale[v] = WT_ATOL + vmax(vabs(y[v]), vabs(y_new[v])) * WT_RTOL;
-      vd err_norm = rms3(err[0] / escale[0], err[1] / escale[1], err[2] / escale[2]);
-      vd safety = (0.9 * (2 * WT_NEWTON_MAXITER + 1)) / vfromint(n_iter + 2 * WT_NEWTON_MAXITER);
+      for (int v = 0; v < 3; ++v) escale[v] = wt_rcp(WT_ATOL + vmax(vabs(y[v]), vabs(y_new[v])) * WT_RTOL);
+      vd err_norm = rms3(err[0] * escale[0], err[1] * escale[1], err[2] * escale[2]);
+      vd safety = wt_div(vbroadcast(0.9 * (2 * WT_NEWTON_MAXITER + 1)), vfromint(n_iter + 2 * WT_NEWTON_MAXITER));
       {
         vb again = cv & rejected & (err_norm > 1.0);
         if (vany(again)) {  // radau.py:493-495
@@ -956,7 +988,7 @@ struct WtPlantStep {
           WT_UNROLL
           for (int v = 0; v < 3; ++v) e2[v] = fe[v] + ZE[v];
           solve_real(e2);
-          vd en2 = rms3(e2[0] / escale[0], e2[1] / escale[1], e2[2] / escale[2]);
+          vd en2 = rms3(e2[0] * escale[0], e2[1] * escale[1], e2[2] * escale[2]);
           err_norm = sel(again, en2, err_norm);
         }
       }
