@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libwt_b200.so")
+# WT_B200_LIB selects an alternative build of the SAME library (A/B tuning builds); never a CPU path
+LIB_PATH = os.environ.get("WT_B200_LIB") or os.path.join(_HERE, "csrc", "libwt_b200.so")
 
 NPAR = 12
 NBND = 10

@@ -33,9 +33,13 @@ static int cuda_err(cudaError_t e, const char *where) {
 // per-warp shared-memory store of the PCR factorizations
 // ---------------------------------------------------------------------------------------
 struct SmemLu {
-  double *p;  // &region[lane]; slot stride = 32 doubles
+  double *p;   // &lu_region[lane]; slot stride = 32 doubles
+  double *cp;  // constants of this lane's plant (one copy per plant, read as a broadcast)
   __device__ __forceinline__ void put(int slot, double x, bool mask) { if (mask) p[slot * 32] = x; }
   __device__ __forceinline__ double get(int slot) const { return p[slot * 32]; }
+  __device__ __forceinline__ void cput(int k, double x) { cp[k] = x; }
+  __device__ __forceinline__ double cget(int k) const { return cp[k]; }
+  __device__ __forceinline__ void csync() { __syncwarp(); }
 };
 
 __host__ __device__ inline int wt_lu_slots(int n) {
@@ -43,6 +47,8 @@ __host__ __device__ inline int wt_lu_slots(int n) {
   for (int s = 1; s < n; s <<= 1) ++L;
   return 3 * (2 * L + 1) + 3 * (4 * L + 2);
 }
+// doubles of shared memory per warp: LU slots for 32 lanes + constants for (32/n + 1) plants
+__host__ __device__ inline int wt_warp_smem_doubles(int n) { return wt_lu_slots(n) * 32 + (32 / n + 1) * CK_N; }
 
 struct StepArgs {
   int P, n, n_steps, bnd_stride, max_attempts;
@@ -53,8 +59,15 @@ struct StepArgs {
   int32_t *counters;
 };
 
+#ifndef WT_STEP_WARPS
+#define WT_STEP_WARPS 4
+#endif
+#ifndef WT_STEP_MINBLOCKS
+#define WT_STEP_MINBLOCKS 2
+#endif
+
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_kernel(StepArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = a.n, gpw = 32 / n;
@@ -71,7 +84,8 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
   if (!__any_sync(0xffffffffu, on)) return;
 
   SmemLu lu;
-  lu.p = smem + (size_t)warp * wt_lu_slots(n) * 32 + lane;
+  lu.p = smem + (size_t)warp * wt_warp_smem_doubles(n) + lane;
+  lu.cp = smem + (size_t)warp * wt_warp_smem_doubles(n) + wt_lu_slots(n) * 32 + (gi < gpw ? gi : gpw) * CK_N;
 
   WtPlantStep<SmemLu> ps;
   ps.g = wt_make_group(n);
@@ -82,7 +96,7 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
     for (int k = 0; k < WTP_NPAR; ++k) par[k] = a.par[(size_t)k * P + p];
 #pragma unroll
     for (int k = 0; k < WTB_NBND; ++k) bnd[k] = a.bnd[a.bnd_stride ? (size_t)k * P + p : (size_t)k];
-    ps.c = wt_make_const(par, bnd);
+    ps.c = wt_make_const(&lu, par, bnd);
   }
   double t = a.time[p];
 #pragma unroll
@@ -143,12 +157,16 @@ __global__ void wt_derivatives_kernel(int P, int n, const double *par_, const do
   const int p = in_plant ? (int)pl : 0;
   const int z = in_plant ? lane - gi * n : 0;
   WtGroup g = wt_make_group(n);
+  __shared__ double cs[4][17 * CK_N];
+  SmemLu st;
+  st.p = nullptr;
+  st.cp = &cs[threadIdx.x >> 5][(gi < gpw ? gi : gpw) * CK_N];
   double par[WTP_NPAR], bnd[WTB_NBND];
 #pragma unroll
   for (int k = 0; k < WTP_NPAR; ++k) par[k] = par_[(size_t)k * P + p];
 #pragma unroll
   for (int k = 0; k < WTB_NBND; ++k) bnd[k] = bnd_[bnd_stride ? (size_t)k * P + p : (size_t)k];
-  WtConst c = wt_make_const(par, bnd);
+  WtConstT<SmemLu> c = wt_make_const(&st, par, bnd);
   double yy[3], d[3];
 #pragma unroll
   for (int v = 0; v < 3; ++v) yy[v] = y[((size_t)v * n + z) * P + p];
@@ -238,13 +256,11 @@ static int check_common(int P, int n) {
   return 0;
 }
 
-#define WT_STEP_WARPS 4
-
 static int launch_step(StepArgs a, cudaStream_t s) {
   const int gpw = 32 / a.n;
   const long long warps = ((long long)a.P + gpw - 1) / gpw;
   const long long blocks = (warps + WT_STEP_WARPS - 1) / WT_STEP_WARPS;
-  const size_t smem = (size_t)WT_STEP_WARPS * wt_lu_slots(a.n) * 32 * sizeof(double);
+  const size_t smem = (size_t)WT_STEP_WARPS * wt_warp_smem_doubles(a.n) * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(wt_step_kernel<WT_STEP_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -48,6 +48,11 @@ enum {
   WTC_JAC_RETRY, WTC_NCNT
 };
 
+#ifdef WT_UNROLL_STAGES
+#define WT_STAGE_UNROLL WT_UNROLL
+#else
+#define WT_STAGE_UNROLL
+#endif
 #define WT_RTOL 1e-6  // reactor.py:482
 #define WT_ATOL 1e-8  // reactor.py:483
 #define WT_LN10 2.302585092994046
@@ -156,40 +161,64 @@ WT_DEV vb wt_gany(const WtGroup &g, vb c) { return vmask_any(vballot(c), g.gmask
 // ----------------------------------------------------------------------------------------
 // per-plant constants and boundary, replicated per lane
 // ----------------------------------------------------------------------------------------
-struct WtConst {
-  vd Kw, Ka1, Ka12, KaCl, CT2303, Kx, zh, v2;
-  vb strat, v_ok;
-  // boundary-derived (reactor.py:336, 349-368, 388-395, 420, 426-443)
-  vd QV, Hin, dHd, cl_dose, inCl, inT, hlA, amb, inv_hl_den, Ri_thr;
-  vb acid_on, cl_on, hl_on;
+// The 17 numeric constants live in the per-warp store (shared memory on the GPU: one copy
+// per plant, read as a broadcast) instead of 34 registers per lane; the flags stay in registers.
+enum {
+  CK_Kw = 0, CK_Ka1, CK_Ka12, CK_KaCl, CK_CT2303, CK_Kx, CK_zh, CK_Ri_thr, CK_QV, CK_Hin, CK_dHd,
+  CK_cl_dose, CK_inCl, CK_inT, CK_hlA, CK_amb, CK_inv_hl_den, CK_N
+};
+template <class Store>
+struct WtConstT {
+  Store *st;
+  vb strat, v_ok, acid_on, cl_on, hl_on;
+  WT_DEV vd Kw() const { return st->cget(CK_Kw); }
+  WT_DEV vd Ka1() const { return st->cget(CK_Ka1); }
+  WT_DEV vd Ka12() const { return st->cget(CK_Ka12); }
+  WT_DEV vd KaCl() const { return st->cget(CK_KaCl); }
+  WT_DEV vd CT2303() const { return st->cget(CK_CT2303); }
+  WT_DEV vd Kx() const { return st->cget(CK_Kx); }
+  WT_DEV vd zh() const { return st->cget(CK_zh); }
+  WT_DEV vd Ri_thr() const { return st->cget(CK_Ri_thr); }
+  WT_DEV vd QV() const { return st->cget(CK_QV); }
+  WT_DEV vd Hin() const { return st->cget(CK_Hin); }
+  WT_DEV vd dHd() const { return st->cget(CK_dHd); }
+  WT_DEV vd cl_dose() const { return st->cget(CK_cl_dose); }
+  WT_DEV vd inCl() const { return st->cget(CK_inCl); }
+  WT_DEV vd inT() const { return st->cget(CK_inT); }
+  WT_DEV vd hlA() const { return st->cget(CK_hlA); }
+  WT_DEV vd amb() const { return st->cget(CK_amb); }
+  WT_DEV vd inv_hl_den() const { return st->cget(CK_inv_hl_den); }
 };
 
-// par / bnd hold this lane's plant values (already loaded)
-WT_DEV WtConst wt_make_const(const vd *par, const vd *bnd) {
-  WtConst c;
-  c.Kw = par[WTP_KW];
-  c.Ka1 = par[WTP_KA1];
-  c.Ka12 = par[WTP_KA1] * par[WTP_KA2];
-  c.KaCl = par[WTP_KACL];
-  c.CT2303 = 2.303 * par[WTP_CT];
-  c.Kx = par[WTP_KX];
-  c.zh = par[WTP_ZH];
-  c.v2 = par[WTP_V] * par[WTP_V];
+// par / bnd hold this lane's plant values (already loaded); boundary-derived terms follow
+// reactor.py:336, 349-368, 388-395, 420, 426-443
+template <class Store>
+WT_DEV WtConstT<Store> wt_make_const(Store *st, const vd *par, const vd *bnd) {
+  WtConstT<Store> c;
+  c.st = st;
+  st->cput(CK_Kw, par[WTP_KW]);
+  st->cput(CK_Ka1, par[WTP_KA1]);
+  st->cput(CK_Ka12, par[WTP_KA1] * par[WTP_KA2]);
+  st->cput(CK_KaCl, par[WTP_KACL]);
+  st->cput(CK_CT2303, 2.303 * par[WTP_CT]);
+  st->cput(CK_Kx, par[WTP_KX]);
+  st->cput(CK_zh, par[WTP_ZH]);
+  st->cput(CK_Ri_thr, 0.25 * (par[WTP_V] * par[WTP_V]));
   c.v_ok = par[WTP_V] > 1e-6;
   c.strat = par[WTP_STRAT] != 0.0;
-  c.QV = wt_div(bnd[WTB_INLET_FLOW] / 60.0, par[WTP_VOLUME]);
-  c.Hin = vexp10(-bnd[WTB_INLET_PH]);
+  st->cput(CK_QV, wt_div(bnd[WTB_INLET_FLOW] / 60.0, par[WTP_VOLUME]));
+  st->cput(CK_Hin, vexp10(-bnd[WTB_INLET_PH]));
   c.acid_on = bnd[WTB_ACID_FLOW] > 0.0;
-  c.dHd = wt_div((bnd[WTB_ACID_FLOW] / 60.0) * bnd[WTB_ACID_CONC], par[WTP_VZL]);
+  st->cput(CK_dHd, wt_div((bnd[WTB_ACID_FLOW] / 60.0) * bnd[WTB_ACID_CONC], par[WTP_VZL]));
   c.cl_on = bnd[WTB_CL_FLOW] > 0.0;
-  c.cl_dose = wt_div((bnd[WTB_CL_FLOW] / 60.0) * bnd[WTB_CL_CONC], par[WTP_VZL]);
-  c.inCl = bnd[WTB_INLET_CL];
-  c.inT = bnd[WTB_INLET_T];
+  st->cput(CK_cl_dose, wt_div((bnd[WTB_CL_FLOW] / 60.0) * bnd[WTB_CL_CONC], par[WTP_VZL]));
+  st->cput(CK_inCl, bnd[WTB_INLET_CL]);
+  st->cput(CK_inT, bnd[WTB_INLET_T]);
   c.hl_on = bnd[WTB_HEAT_LOSS] > 0.0;
-  c.hlA = bnd[WTB_HEAT_LOSS] * par[WTP_AT];
-  c.amb = bnd[WTB_AMBIENT_T];
-  c.inv_hl_den = wt_rcp((998.2 * 4184.0) * (par[WTP_VOLUME] / 1000.0));
-  c.Ri_thr = 0.25 * c.v2;
+  st->cput(CK_hlA, bnd[WTB_HEAT_LOSS] * par[WTP_AT]);
+  st->cput(CK_amb, bnd[WTB_AMBIENT_T]);
+  st->cput(CK_inv_hl_den, wt_rcp((998.2 * 4184.0) * (par[WTP_VOLUME] / 1000.0)));
+  st->csync();
   return c;
 }
 
@@ -207,12 +236,13 @@ WT_DEV vd wt_density(vd T) {
 
 // spatial.py:266-275, 293, 313-316: exchange multiplier of the interface between a zone
 // (rho_lo) and the zone above it (rho_hi)
-WT_DEV vd wt_suppression(const WtConst &c, vd rho_lo, vd rho_hi) {
+template <class Store>
+WT_DEV vd wt_suppression(const WtConstT<Store> &c, vd rho_lo, vd rho_hi) {
   vd drho = rho_hi - rho_lo;
   vd ravg = 0.5 * (rho_lo + rho_hi);
   // Ri = (g drho zh)/(ravg v^2) > 0.25, cross-multiplied (ravg v^2 > 0): same decision except
   // within an ulp of the threshold; v <= 1e-6 -> Ri = +inf
-  vb stable = (!c.v_ok) | (((9.81 * drho) * c.zh) > ravg * c.Ri_thr);
+  vb stable = (!c.v_ok) | (((9.81 * drho) * c.zh()) > ravg * c.Ri_thr());
   return sel(c.strat & stable, 0.5, 1.0);
 }
 
@@ -225,69 +255,73 @@ WT_DEV vd wt_arrhenius(vd T) {
 WT_DEV vb wt_t_out_of_range(vd T) { return (T < 0.0) | (T > 100.0); }  // thermodynamics.py:146-157
 
 // chemistry.py:422-437 (+ :181-191): beta(pH) * ln(10)
-WT_DEV vd wt_beta_ln10(const WtConst &c, vd H, vb &bpos) {
-  vd bw = 2.303 * (H + c.Kw * wt_rcp(H));
+template <class Store>
+WT_DEV vd wt_beta_ln10(const WtConstT<Store> &c, vd H, vb &bpos) {
+  vd bw = 2.303 * (H + c.Kw() * wt_rcp(H));
   vd HH = H * H;
-  vd D = HH + c.Ka1 * H + c.Ka12;
+  vd D = HH + c.Ka1() * H + c.Ka12();
   vd iD = wt_rcp(D);  // the three alphas share one reciprocal (<= 1 ulp from three divisions)
   vd a0 = HH * iD;
-  vd a1 = (c.Ka1 * H) * iD;
-  vd a2 = c.Ka12 * iD;
-  vd bc = c.CT2303 * (a0 * a1 + (4.0 * a1) * a2 + a0 * a2);
+  vd a1 = (c.Ka1() * H) * iD;
+  vd a2 = c.Ka12() * iD;
+  vd bc = c.CT2303() * (a0 * a1 + (4.0 * a1) * a2 + a0 * a2);
   vd beta = bw + bc;
   bpos = beta > 0.0;
   return beta * WT_LN10;
 }
 
 // chemistry.py:510-523
-WT_DEV vd wt_decay_factor(const WtConst &c, vd H) {
-  vd iden = wt_rcp(H + c.KaCl);
-  return (H * iden) * 1.0 + (c.KaCl * iden) * 0.02;
+template <class Store>
+WT_DEV vd wt_decay_factor(const WtConstT<Store> &c, vd H) {
+  vd iden = wt_rcp(H + c.KaCl());
+  return (H * iden) * 1.0 + (c.KaCl() * iden) * 0.02;
 }
 
 struct WtMix { vd off_dn, off_up, diag; };
 
 // reactor.py:318-337: row z of the stratification-scaled exchange matrix
-WT_DEV WtMix wt_mix_row(const WtGroup &g, const WtConst &c, vd s_dn, vd s_up) {
+template <class Store>
+WT_DEV WtMix wt_mix_row(const WtGroup &g, const WtConstT<Store> &c, vd s_dn, vd s_up) {
   WtMix m;
-  m.off_up = sel(g.last, 0.0, c.Kx * s_up);
-  m.off_dn = sel(g.first, 0.0, c.Kx * s_dn);
+  m.off_up = sel(g.last, 0.0, c.Kx() * s_up);
+  m.off_dn = sel(g.first, 0.0, c.Kx() * s_dn);
   vd d = -(m.off_dn + m.off_up);
-  m.diag = sel(g.last, d - c.QV, d);
+  m.diag = sel(g.last, d - c.QV(), d);
   return m;
 }
 WT_DEV vd wt_mix(const WtMix &m, vd xdn, vd x, vd xup) { return (m.off_dn * xdn + m.diag * x) + m.off_up * xup; }
 
 // reactor.py:349-368: the zone-0-only acid dosing + inlet terms of dpH (0 elsewhere)
 // (ibl = 1 / (beta ln10): the up-to-three quotients of zone 0 share one reciprocal)
-WT_DEV vd wt_dph_inlet(const WtGroup &g, const WtConst &c, vd H, vd ibl, vb bpos) {
-  vd t1 = sel(g.first & c.acid_on & bpos, -c.dHd * ibl, 0.0);
-  vd dHin = c.QV * (c.Hin - H);
+template <class Store>
+WT_DEV vd wt_dph_inlet(const WtGroup &g, const WtConstT<Store> &c, vd H, vd ibl, vb bpos) {
+  vd t1 = sel(g.first & c.acid_on & bpos, -c.dHd() * ibl, 0.0);
+  vd dHin = c.QV() * (c.Hin() - H);
   vd t2 = sel(g.first & bpos, -dHin * ibl, 0.0);
   return (0.0 + t1) + t2;
 }
 // reactor.py:371-376
 WT_DEV vd wt_dph(vd t12, vd mixH, vd ibl, vb bpos) { return t12 + sel(bpos, -mixH * ibl, 0.0); }
 // reactor.py:388-411
-WT_DEV vd wt_dcl(const WtGroup &g, const WtConst &c, vd Cl, vd mixCl, vd kf) {
-  vd r = sel(g.first & c.cl_on, c.cl_dose, 0.0);
-  r = r + sel(g.first, c.QV * (c.inCl - Cl), 0.0);
+template <class Store>
+WT_DEV vd wt_dcl(const WtGroup &g, const WtConstT<Store> &c, vd Cl, vd mixCl, vd kf) {
+  vd r = sel(g.first & c.cl_on, c.cl_dose(), 0.0);
+  r = r + sel(g.first, c.QV() * (c.inCl() - Cl), 0.0);
   r = r + mixCl;
   return r - kf * Cl;
 }
 // reactor.py:420-443
-WT_DEV vd wt_dt(const WtGroup &g, const WtConst &c, vd T, vd mixT) {
-  vd r = sel(g.first, c.QV * (c.inT - T), 0.0);
+template <class Store>
+WT_DEV vd wt_dt(const WtGroup &g, const WtConstT<Store> &c, vd T, vd mixT) {
+  vd r = sel(g.first, c.QV() * (c.inT() - T), 0.0);
   r = r + mixT;
-  if (vany(c.hl_on)) {  // warp-uniform: adiabatic ensembles skip the term entirely
-    vd loss = (c.hlA * (T - c.amb)) * c.inv_hl_den;
-    r = sel(c.hl_on, r - loss, r);
-  }
-  return r;
+  vd loss = (c.hlA() * (T - c.amb())) * c.inv_hl_den();
+  return sel(c.hl_on, r - loss, r);
 }
 
 // Full RHS for this lane's zone.  `bad` is set where the reference would raise ValueError.
-WT_DEV void wt_rhs(const WtGroup &g, const WtConst &c, vd pH, vd Cl, vd T, vd &dpH, vd &dCl, vd &dT,
+template <class Store>
+WT_DEV void wt_rhs(const WtGroup &g, const WtConstT<Store> &c, vd pH, vd Cl, vd T, vd &dpH, vd &dCl, vd &dT,
                    vb &bad) {
   vd rho = wt_density(T);
   vd s_up = wt_suppression(c, rho, shfl_down(rho, 1));
@@ -408,7 +442,7 @@ struct WtJac {
 template <class LuStore>
 struct WtPlantStep {
   WtGroup g;
-  WtConst c;
+  WtConstT<LuStore> c;
   LuStore *lu;
   // state vector of this zone: 0 pH, 1 Cl, 2 T  (and f = dy/dt)
   vd y[3], f[3];
@@ -431,34 +465,117 @@ struct WtPlantStep {
   // -------------------------------------------------------------------------------------
   // linear algebra on the block-triangular structure.  System order: 0 = T, 1 = pH, 2 = Cl.
   // -------------------------------------------------------------------------------------
+  // All six factorizations (real + complex of T, pH, Cl) share one sweep over the PCR levels:
+  // six independent dependency chains per level instead of six sweeps back to back.
   WT_DEV void factor(vd h, vb mask) {
-    vd ih = wt_rcp(h);
-    vd mr = WT_MU_REAL * ih;
-    vd cr = WT_MU_CRE * ih, ci = WT_MU_CIM * ih;
-    wt_pcr_factor_real(g, *lu, slot_real(0), -J.tt[0], mr - J.tt[1], -J.tt[2], mask);
-    wt_pcr_factor_real(g, *lu, slot_real(1), -J.pp[0], mr - J.pp[1], -J.pp[2], mask);
-    wt_pcr_factor_real(g, *lu, slot_real(2), -J.cc[0], mr - J.cc[1], -J.cc[2], mask);
-    wt_pcr_factor_cplx(g, *lu, slot_cplx(0), -J.tt[0], cr - J.tt[1], ci, -J.tt[2], mask);
-    wt_pcr_factor_cplx(g, *lu, slot_cplx(1), -J.pp[0], cr - J.pp[1], ci, -J.pp[2], mask);
-    wt_pcr_factor_cplx(g, *lu, slot_cplx(2), -J.cc[0], cr - J.cc[1], ci, -J.cc[2], mask);
+    const vd ih = wt_rcp(h);
+    const vd mr = WT_MU_REAL * ih, gr = WT_MU_CRE * ih, gi = WT_MU_CIM * ih;
+    vd a[3], b[3], c_[3];                         // real rows
+    vd ar[3], ai[3], br[3], bi[3], cr[3], ci[3];  // complex rows
+    a[0] = -J.tt[0]; b[0] = mr - J.tt[1]; c_[0] = -J.tt[2];
+    a[1] = -J.pp[0]; b[1] = mr - J.pp[1]; c_[1] = -J.pp[2];
+    a[2] = -J.cc[0]; b[2] = mr - J.cc[1]; c_[2] = -J.cc[2];
+    WT_UNROLL
+    for (int q = 0; q < 3; ++q) {
+      ar[q] = a[q]; ai[q] = vbroadcast(0.0);
+      br[q] = b[q] - mr + gr; bi[q] = gi;
+      cr[q] = c_[q]; ci[q] = vbroadcast(0.0);
+    }
+    br[0] = gr - J.tt[1]; br[1] = gr - J.pp[1]; br[2] = gr - J.cc[1];
+    int l = 0;
+    for (int s = 1; s < g.n; s <<= 1, ++l) {
+      const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
+      WT_UNROLL
+      for (int q = 0; q < 3; ++q) {
+        {  // real
+          const int s0 = slot_real(q);
+          vd r = wt_rcp(b[q]);
+          vd k1 = a[q] * shfl_idx(r, sd);
+          vd k2 = c_[q] * shfl_idx(r, su);
+          vd a_dn = shfl_idx(a[q], sd), c_dn = shfl_idx(c_[q], sd);
+          vd a_up = shfl_idx(a[q], su), c_up = shfl_idx(c_[q], su);
+          b[q] = b[q] - c_dn * k1 - a_up * k2;
+          a[q] = -(a_dn * k1);
+          c_[q] = -(c_up * k2);
+          lu->put(s0 + 2 * l, k1, mask);
+          lu->put(s0 + 2 * l + 1, k2, mask);
+        }
+        {  // complex
+          const int s0 = slot_cplx(q);
+          vd iden = wt_rcp(br[q] * br[q] + bi[q] * bi[q]);
+          vd rr = br[q] * iden, ri = -(bi[q] * iden);  // 1 / b
+          vd rdr = shfl_idx(rr, sd), rdi = shfl_idx(ri, sd);
+          vd rur = shfl_idx(rr, su), rui = shfl_idx(ri, su);
+          vd k1r = ar[q] * rdr - ai[q] * rdi, k1i = ar[q] * rdi + ai[q] * rdr;
+          vd k2r = cr[q] * rur - ci[q] * rui, k2i = cr[q] * rui + ci[q] * rur;
+          vd adr = shfl_idx(ar[q], sd), adi = shfl_idx(ai[q], sd), cdr = shfl_idx(cr[q], sd), cdi = shfl_idx(ci[q], sd);
+          vd aur = shfl_idx(ar[q], su), aui = shfl_idx(ai[q], su), cur = shfl_idx(cr[q], su), cui = shfl_idx(ci[q], su);
+          br[q] = br[q] - (cdr * k1r - cdi * k1i) - (aur * k2r - aui * k2i);
+          bi[q] = bi[q] - (cdr * k1i + cdi * k1r) - (aur * k2i + aui * k2r);
+          ar[q] = -(adr * k1r - adi * k1i);
+          ai[q] = -(adr * k1i + adi * k1r);
+          cr[q] = -(cur * k2r - cui * k2i);
+          ci[q] = -(cur * k2i + cui * k2r);
+          lu->put(s0 + 4 * l + 0, k1r, mask);
+          lu->put(s0 + 4 * l + 1, k1i, mask);
+          lu->put(s0 + 4 * l + 2, k2r, mask);
+          lu->put(s0 + 4 * l + 3, k2i, mask);
+        }
+      }
+    }
+    WT_UNROLL
+    for (int q = 0; q < 3; ++q) {
+      lu->put(slot_real(q) + 2 * l, wt_rcp(b[q]), mask);
+      vd iden = wt_rcp(br[q] * br[q] + bi[q] * bi[q]);
+      lu->put(slot_cplx(q) + 4 * l + 0, br[q] * iden, mask);
+      lu->put(slot_cplx(q) + 4 * l + 1, -(bi[q] * iden), mask);
+    }
   }
-  WT_DEV vd tri_mv(const vd *row, vd x) const {
-    return (row[0] * wt_dn(g, x, 0.0) + row[1] * x) + row[2] * wt_up(g, x, 0.0);
-  }
+  WT_DEV vd tri_mv(const vd *row, vd xdn, vd x, vd xup) const { return (row[0] * xdn + row[1] * x) + row[2] * xup; }
   // (mu/h I - J) x = b, b and x indexed [0 pH, 1 Cl, 2 T]
   WT_DEV void solve_real(vd *b) {
     vd xT = wt_pcr_solve_real(g, *lu, slot_real(0), b[2]);
-    vd xp = wt_pcr_solve_real(g, *lu, slot_real(1), b[0] + tri_mv(J.pt, xT));
-    vd xc = wt_pcr_solve_real(g, *lu, slot_real(2), b[1] + tri_mv(J.ct, xT) + J.cp * xp);
+    vd xTd = wt_dn(g, xT, 0.0), xTu = wt_up(g, xT, 0.0);
+    vd xp = wt_pcr_solve_real(g, *lu, slot_real(1), b[0] + tri_mv(J.pt, xTd, xT, xTu));
+    vd xc = wt_pcr_solve_real(g, *lu, slot_real(2), b[1] + tri_mv(J.ct, xTd, xT, xTu) + J.cp * xp);
     b[0] = xp; b[1] = xc; b[2] = xT;
   }
-  WT_DEV void solve_cplx(vd *br, vd *bi) {
-    vd tr = br[2], ti = bi[2];
-    wt_pcr_solve_cplx(g, *lu, slot_cplx(0), tr, ti);
-    vd pr = br[0] + tri_mv(J.pt, tr), pi = bi[0] + tri_mv(J.pt, ti);
-    wt_pcr_solve_cplx(g, *lu, slot_cplx(1), pr, pi);
-    vd qr = br[1] + tri_mv(J.ct, tr) + J.cp * pr, qi = bi[1] + tri_mv(J.ct, ti) + J.cp * pi;
-    wt_pcr_solve_cplx(g, *lu, slot_cplx(2), qr, qi);
+  // one system, real and complex right-hand sides in the same sweep (three independent chains)
+  WT_DEV void solve_sys3(int q, vd &d, vd &dr, vd &di) {
+    const int sr = slot_real(q), sc = slot_cplx(q);
+    int l = 0;
+    for (int s = 1; s < g.n; s <<= 1, ++l) {
+      const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
+      vd k1 = lu->get(sr + 2 * l), k2 = lu->get(sr + 2 * l + 1);
+      vd k1r = lu->get(sc + 4 * l + 0), k1i = lu->get(sc + 4 * l + 1);
+      vd k2r = lu->get(sc + 4 * l + 2), k2i = lu->get(sc + 4 * l + 3);
+      vd dd = shfl_idx(d, sd), du = shfl_idx(d, su);
+      vd ddr = shfl_idx(dr, sd), ddi = shfl_idx(di, sd), dur = shfl_idx(dr, su), dui = shfl_idx(di, su);
+      d = d - dd * k1 - du * k2;
+      vd nr = dr - (ddr * k1r - ddi * k1i) - (dur * k2r - dui * k2i);
+      vd ni = di - (ddr * k1i + ddi * k1r) - (dur * k2i + dui * k2r);
+      dr = nr;
+      di = ni;
+    }
+    d = d * lu->get(sr + 2 * l);
+    vd rr = lu->get(sc + 4 * l + 0), ri = lu->get(sc + 4 * l + 1);
+    vd xr = dr * rr - di * ri, xi = dr * ri + di * rr;
+    dr = xr;
+    di = xi;
+  }
+  // the real and the complex collocation systems of one Newton iteration together
+  WT_DEV void solve_newton(vd *b, vd *br, vd *bi) {
+    vd xT = b[2], tr = br[2], ti = bi[2];
+    solve_sys3(0, xT, tr, ti);
+    vd xTd = wt_dn(g, xT, 0.0), xTu = wt_up(g, xT, 0.0);
+    vd trd = wt_dn(g, tr, 0.0), tru = wt_up(g, tr, 0.0), tid = wt_dn(g, ti, 0.0), tiu = wt_up(g, ti, 0.0);
+    vd xp = b[0] + tri_mv(J.pt, xTd, xT, xTu);
+    vd pr = br[0] + tri_mv(J.pt, trd, tr, tru), pi = bi[0] + tri_mv(J.pt, tid, ti, tiu);
+    solve_sys3(1, xp, pr, pi);
+    vd xc = b[1] + tri_mv(J.ct, xTd, xT, xTu) + J.cp * xp;
+    vd qr = br[1] + tri_mv(J.ct, trd, tr, tru) + J.cp * pr, qi = bi[1] + tri_mv(J.ct, tid, ti, tiu) + J.cp * pi;
+    solve_sys3(2, xc, qr, qi);
+    b[0] = xp; b[1] = xc; b[2] = xT;
     br[0] = pr; bi[0] = pi; br[1] = qr; bi[1] = qi; br[2] = tr; bi[2] = ti;
   }
 
@@ -884,7 +1001,8 @@ struct WtPlantStep {
         WT_UNROLL
         for (int v = 0; v < 3; ++v) { fr[v] = vbroadcast(0.0); cr[v] = vbroadcast(0.0); ci[v] = vbroadcast(0.0); }
         vb finite = vbroadcast_b(true), bad_any = vbroadcast_b(false);
-        for (int i = 0; i < 3; ++i) {
+        WT_STAGE_UNROLL
+        for (int i = 0; i < 3; ++i) {  // three independent stage evaluations
           vd F[3];
           vb bad;
           wt_rhs(g, c, y[0] + zrow(i, 0), y[1] + zrow(i, 1), y[2] + zrow(i, 2), F[0], F[1], F[2], bad);
@@ -916,8 +1034,7 @@ struct WtPlantStep {
           cr[v] = re;
           ci[v] = im;
         }
-        solve_real(fr);
-        solve_cplx(cr, ci);
+        solve_newton(fr, cr, ci);
         vd q = vbroadcast(0.0);
         WT_UNROLL
         for (int v = 0; v < 3; ++v) {

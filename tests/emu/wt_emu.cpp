@@ -13,6 +13,10 @@ struct EmuLu {
   vd slot[128];
   void put(int s, const vd &x, const vb &m) { for (int l = 0; l < 32; ++l) if (m.v[l]) slot[s].v[l] = x.v[l]; }
   vd get(int s) const { return slot[s]; }
+  vd cst[CK_N];
+  void cput(int k, const vd &x) { cst[k] = x; }
+  vd cget(int k) const { return cst[k]; }
+  void csync() {}
 };
 
 extern "C" {
@@ -43,7 +47,7 @@ void wt_emu_step_batch(int P, int n, int nsteps, double dt, const double *par, c
         t0.v[l] = t[pp];
         for (int v = 0; v < 3; ++v) yin[v].v[l] = y[(size_t)pp * 3 * n + v * n + z];
       }
-      ps.c = wt_make_const(vpar, vbnd);
+      ps.c = wt_make_const(&lu, vpar, vbnd);
       for (int v = 0; v < 3; ++v) ps.y[v] = yin[v];
       ps.integrate(t0, vdt, on, max_attempts);
       vd der[3];
@@ -82,7 +86,8 @@ void wt_emu_rhs(const double *par, const double *bnd, int n, const double *y, do
     for (int k = 0; k < WTB_NBND; ++k) vbnd[k].v[l] = bnd[k];
     for (int v = 0; v < 3; ++v) yy[v].v[l] = y[v * n + z];
   }
-  WtConst c = wt_make_const(vpar, vbnd);
+  static EmuLu st;
+  WtConstT<EmuLu> c = wt_make_const(&st, vpar, vbnd);
   vb bad;
   wt_rhs(g, c, yy[0], yy[1], yy[2], d[0], d[1], d[2], bad);
   int b = 0;
