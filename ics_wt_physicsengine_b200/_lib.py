@@ -31,7 +31,7 @@ CNT_NAMES = ("nfev", "njev", "nlu", "nsteps", "nnewton", "nreject", "nnewton_fai
 
 EXPORTS = (
     "wt_abi_version", "wt_device_count", "wt_last_error", "wt_step", "wt_advance", "wt_derivatives",
-    "wt_step_host", "wt_calc_ph", "wt_measure_fp64_peak",
+    "wt_step_host", "wt_calc_ph", "wt_measure_fp64_peak", "wt_stats", "wt_stats_size", "wt_stats_scratch_doubles",
 )
 
 
@@ -67,6 +67,12 @@ def lib() -> C.CDLL:
     L.wt_step_host.restype = C.c_int
     L.wt_calc_ph.argtypes = [C.c_int, dp, dp, dp, dp, dp, ip, ip, vp]
     L.wt_calc_ph.restype = C.c_int
+    L.wt_stats_size.argtypes = [C.c_int]
+    L.wt_stats_size.restype = C.c_int
+    L.wt_stats_scratch_doubles.argtypes = [C.c_int]
+    L.wt_stats_scratch_doubles.restype = C.c_int
+    L.wt_stats.argtypes = [C.c_int, C.c_int, dp, up, dp, dp, dp, C.c_int, vp]
+    L.wt_stats.restype = C.c_int
     L.wt_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.c_int]
     L.wt_measure_fp64_peak.restype = C.c_int
     _lib = L

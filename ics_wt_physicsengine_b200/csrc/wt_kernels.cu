@@ -225,6 +225,79 @@ __global__ void wt_calc_ph_kernel(int P, const double *alk, const double *ct, co
   status[i] = st;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// K4: ensemble statistics (the payload of the one collective).
+// Stage 1: each block reduces a slab of plants to per-block partials (coalesced rows of the
+// zone-major state).  Stage 2: one block sums the partials in a fixed order -> deterministic.
+//   out[0] live plants, out[1] halted plants, out[2] outlet Cl < thr[0],
+//   out[3] outlet pH outside [thr[1], thr[2]], out[4] outlet T > thr[3], out[5..7] reserved,
+//   out[8 + 2*(v*n+z)] = sum (x - shift[v]), out[9 + 2*(v*n+z)] = sum (x - shift[v])^2   (live plants)
+// ---------------------------------------------------------------------------------------
+#define WT_STATS_HDR 8
+#define WT_STATS_TPB 256
+
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WT_STATS_TPB / 32; ++i) r += sh[i];
+  }
+  __syncthreads();
+  return r;  // valid on thread 0
+}
+
+__global__ void __launch_bounds__(WT_STATS_TPB) wt_stats_partial_kernel(int P, int n, const double *y, const uint32_t *status,
+                                                                          const double *shift_thr, double *partial) {
+  __shared__ double sh[WT_STATS_TPB / 32];
+  const int nstat = WT_STATS_HDR + 6 * n;
+  double *out = partial + (size_t)blockIdx.x * nstat;
+  const int per_block = (P + gridDim.x - 1) / gridDim.x;
+  const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
+  const double c0 = shift_thr[0], c1 = shift_thr[1], c2 = shift_thr[2];
+  const double t_cl = shift_thr[3], t_ph_lo = shift_thr[4], t_ph_hi = shift_thr[5], t_T = shift_thr[6];
+  double live = 0, halted = 0, e0 = 0, e1 = 0, e2 = 0;
+  for (int p = lo + threadIdx.x; p < hi; p += WT_STATS_TPB) {
+    const bool h = (status[p] & WTS_HALT_MASK) != 0;
+    if (h) { halted += 1.0; continue; }
+    live += 1.0;
+    const double ph = y[((size_t)0 * n + (n - 1)) * P + p], cl = y[((size_t)1 * n + (n - 1)) * P + p],
+                 T = y[((size_t)2 * n + (n - 1)) * P + p];
+    e0 += cl < t_cl ? 1.0 : 0.0;
+    e1 += (ph < t_ph_lo || ph > t_ph_hi) ? 1.0 : 0.0;
+    e2 += T > t_T ? 1.0 : 0.0;
+  }
+  double r;
+  r = block_sum(live, sh); if (threadIdx.x == 0) out[0] = r;
+  r = block_sum(halted, sh); if (threadIdx.x == 0) out[1] = r;
+  r = block_sum(e0, sh); if (threadIdx.x == 0) out[2] = r;
+  r = block_sum(e1, sh); if (threadIdx.x == 0) out[3] = r;
+  r = block_sum(e2, sh); if (threadIdx.x == 0) { out[4] = r; out[5] = 0; out[6] = 0; out[7] = 0; }
+  for (int row = 0; row < 3 * n; ++row) {
+    const double c = row < n ? c0 : (row < 2 * n ? c1 : c2);
+    double s1 = 0, s2 = 0;
+    for (int p = lo + threadIdx.x; p < hi; p += WT_STATS_TPB) {
+      if (status[p] & WTS_HALT_MASK) continue;
+      const double d = y[(size_t)row * P + p] - c;
+      s1 += d;
+      s2 += d * d;
+    }
+    r = block_sum(s1, sh); if (threadIdx.x == 0) out[WT_STATS_HDR + 2 * row] = r;
+    r = block_sum(s2, sh); if (threadIdx.x == 0) out[WT_STATS_HDR + 2 * row + 1] = r;
+  }
+}
+
+__global__ void wt_stats_final_kernel(int nblocks, int nstat, const double *partial, double *out, int accumulate) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nstat) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * nstat + k];
+  out[k] = accumulate ? out[k] + s : s;
+}
+
 // 8 independent DFMA chains per thread: saturates the FP64 pipe without memory traffic
 __global__ void wt_dfma_peak_kernel(double *out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -314,6 +387,24 @@ int wt_calc_ph(int P, const double *alk, const double *ct, const double *temp, c
   const int tpb = 128;
   wt_calc_ph_kernel<<<(P + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(P, alk, ct, temp, guess, ph, iters, status);
   return cuda_err(cudaGetLastError(), "wt_calc_ph_kernel launch");
+}
+
+
+int wt_stats_size(int n) { return WT_STATS_HDR + 6 * n; }
+int wt_stats_scratch_doubles(int n) { return 1024 * (WT_STATS_HDR + 6 * n); }
+
+int wt_stats(int P, int n, const double *y, const uint32_t *status, const double *shift_thr, double *out,
+             double *scratch, int accumulate, void *stream) {
+  int rc = check_common(P, n);
+  if (rc) return rc;
+  if (!y || !status || !shift_thr || !out || !scratch) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  int blocks = (P + 4 * WT_STATS_TPB - 1) / (4 * WT_STATS_TPB);
+  if (blocks > 1024) blocks = 1024;
+  if (blocks < 1) blocks = 1;
+  const int nstat = wt_stats_size(n);
+  wt_stats_partial_kernel<<<blocks, WT_STATS_TPB, 0, (cudaStream_t)stream>>>(P, n, y, status, shift_thr, scratch);
+  wt_stats_final_kernel<<<(nstat + 127) / 128, 128, 0, (cudaStream_t)stream>>>(blocks, nstat, scratch, out, accumulate);
+  return cuda_err(cudaGetLastError(), "wt_stats launch");
 }
 
 // Host-buffer path: one workspace per process, grown on demand.

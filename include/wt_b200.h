@@ -122,6 +122,24 @@ int wt_calc_ph(int P, const double *alk_dev, const double *ct_dev, const double 
                const double *guess_dev, double *ph_dev, int32_t *iters_dev, int32_t *status_dev,
                void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Ensemble statistics: the payload of the ONE collective of the multi-GPU path.  The reference
+ * has no counterpart (one plant, logging only: __main__.py:426-448, base_sensor.py:809-856);
+ * BASELINE.json north_star asks for mean / variance / exceedance counts all-reduced over NCCL.
+ *   shift_thr[7] = {shift_pH, shift_Cl, shift_T,  Cl_min, pH_lo, pH_hi, T_max}   (device)
+ *   out[wt_stats_size(n)]:
+ *     [0] live plants  [1] halted plants  [2] #outlet Cl < Cl_min  [3] #outlet pH outside [pH_lo,pH_hi]
+ *     [4] #outlet T > T_max  [5..7] reserved
+ *     [8 + 2*(var*n+zone)] = sum(x - shift[var]),  [9 + 2*(var*n+zone)] = sum (x - shift[var])^2   over live plants
+ *   scratch: wt_stats_scratch_doubles(n) doubles of device workspace.  Deterministic (fixed
+ *   summation order).  accumulate != 0 adds to `out` instead of overwriting it.
+ * ------------------------------------------------------------------------------------- */
+int wt_stats_size(int n_zones);
+int wt_stats_scratch_doubles(int n_zones);
+int wt_stats(int P, int n_zones, const double *y_dev, const uint32_t *status_dev,
+             const double *shift_thr_dev, double *out_dev, double *scratch_dev, int accumulate,
+             void *stream);
+
 /* Measured-peak helper for the roofline denominator: runs a dependent-chain-free DFMA loop on
  * every SM and returns the sustained FP64 rate in TFLOP/s (2 flops per DFMA). */
 int wt_measure_fp64_peak(double *tflops_out, int iters);

@@ -270,3 +270,22 @@ def test_calculate_ph_262144_histogram(oracle):
     # default buffer: 8.39839641036611 in 6 iterations from the grid guess 7.0 (chemistry.py:546-550)
     k = alk.size - 29 + 14
     assert it[k] == 6 and abs(ph[k] - 8.39839641036611) < 1e-12
+
+
+# ---- ensemble statistics kernel (payload of the NCCL all-reduce) -------------------------------
+def test_stats_kernel_matches_numpy_and_is_deterministic():
+    from ics_wt_physicsengine_b200.partition import EnsembleStatistics, StatsSpec, finalize_stats
+    from tests.test_partition_gloo import local_stats_numpy
+    e = ens.config5(200003, 10)  # odd size: ragged last block
+    eng = PlantEnsemble(e)
+    eng.advance(3, 1.0, e.bnd)
+    st = EnsembleStatistics(eng, StatsSpec())
+    a = st.local().cpu().numpy().copy()
+    b = st.local().cpu().numpy().copy()
+    assert np.array_equal(a, b), "fixed summation order: bitwise reproducible"
+    want = local_stats_numpy(eng.state_numpy(), eng.status.cpu().numpy().astype(np.uint32), 10, StatsSpec())
+    assert np.array_equal(a[:5], want[:5])
+    assert np.allclose(a[8:], want[8:], rtol=1e-11, atol=1e-7)
+    r = finalize_stats(a, 10, StatsSpec())
+    assert r["live"] + r["halted"] == 200003
+    assert np.all(r["var_pH"] >= 0) and np.all((r["mean_temperature"] > 0) & (r["mean_temperature"] < 45))

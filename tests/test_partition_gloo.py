@@ -1,0 +1,93 @@
+"""Multi-process path on CPU: world_size-2 gloo all-reduce of the ensemble statistics vector and the
+plant partitioner.  The per-shard vectors come from a numpy restatement of the wt_stats kernel
+layout (include/wt_b200.h) -- the GPU tests check the kernel against the same function."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ics_wt_physicsengine_b200 import ensembles as ens
+from ics_wt_physicsengine_b200.partition import (StatsSpec, finalize_stats, shard_bounds, shard_ensemble, stats_size)
+
+
+def local_stats_numpy(y_pn, status, n, spec: StatsSpec) -> np.ndarray:
+    """y_pn: [P, 3n] species-major.  Same layout as the wt_stats kernel."""
+    live = (status & (2 | 128)) == 0
+    v = np.zeros(stats_size(n))
+    v[0], v[1] = live.sum(), (~live).sum()
+    yl = y_pn[live]
+    ph, cl, T = yl[:, n - 1], yl[:, 2 * n - 1], yl[:, 3 * n - 1]
+    v[2] = (cl < spec.chlorine_min).sum()
+    v[3] = ((ph < spec.pH_low) | (ph > spec.pH_high)).sum()
+    v[4] = (T > spec.temperature_max).sum()
+    sh = np.repeat([spec.shift_pH, spec.shift_chlorine, spec.shift_temperature], n)
+    d = yl - sh[None, :]
+    v[8::2] = d.sum(axis=0)
+    v[9::2] = (d * d).sum(axis=0)
+    return v
+
+
+def test_shard_bounds_cover_the_ensemble_exactly():
+    for total in (1, 7, 64, 1000, 1048576):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                lo, hi = shard_bounds(total, r, world)
+                assert 0 <= lo <= hi <= total
+                seen.extend(range(lo, hi)) if total <= 1000 else seen.append((lo, hi))
+            if total <= 1000:
+                assert seen == list(range(total))
+            else:
+                assert seen[0][0] == 0 and seen[-1][1] == total
+                assert all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = ens.config2(257, 10)
+    e = shard_ensemble(full, rank, world)
+    spec = StatsSpec()
+    y = np.concatenate([e.pH0, e.Cl0, e.T0], axis=1)
+    status = np.zeros(e.n_plants, dtype=np.uint32)
+    if rank == 0:
+        status[3] = 2    # a halted plant is excluded from the moments and counted as halted
+    v = torch.from_numpy(local_stats_numpy(y, status, 10, spec))
+    dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        q.put(v.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_allreduce_of_statistics_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = 29500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    full = ens.config2(257, 10)
+    y = np.concatenate([full.pH0, full.Cl0, full.T0], axis=1)
+    status = np.zeros(257, dtype=np.uint32)
+    status[3] = 2
+    spec = StatsSpec()
+    want = local_stats_numpy(y, status, 10, spec)
+    assert np.allclose(got, want, rtol=1e-13, atol=1e-9)
+    r = finalize_stats(got, 10, spec)
+    live = status == 0
+    assert r["live"] == 256 and r["halted"] == 1
+    assert np.allclose(r["mean_pH"], full.pH0[live].mean(axis=0), rtol=1e-12)
+    assert np.allclose(r["var_temperature"], full.T0[live].var(axis=0), rtol=1e-9)
+    assert 0 <= r["frac_outlet_chlorine_low"] <= 1
