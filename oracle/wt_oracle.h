@@ -142,6 +142,9 @@ int wt_oracle_calc_ph(double alkalinity, double total_carbonate, double temperat
                       double initial_guess, double tolerance, int max_iter,
                       double *ph_out, int32_t *iters_out);
 
+/* test knob: perturb H by (1 +- eps) inside calculate_pH (stability probe) */
+void wt_oracle_set_ph_h_eps(double eps);
+
 void wt_oracle_calc_ph_batch(int P, const double *alk, const double *ct, const double *temp,
                              const double *guess, double *ph, int32_t *iters, int32_t *status,
                              int nthreads);

@@ -73,6 +73,8 @@ def lib():
         L.wt_oracle_step_batch.restype = None
         L.wt_oracle_set_max_attempts.argtypes = [C.c_int]
         L.wt_oracle_set_max_attempts.restype = None
+        L.wt_oracle_set_ph_h_eps.argtypes = [C.c_double]
+        L.wt_oracle_set_ph_h_eps.restype = None
         L.wt_oracle_calc_ph.argtypes = [C.c_double] * 5 + [C.c_int, dp, ip]
         L.wt_oracle_calc_ph.restype = C.c_int
         L.wt_oracle_calc_ph_batch.argtypes = [C.c_int, dp, dp, dp, dp, dp, ip, ip, C.c_int]
@@ -83,6 +85,10 @@ def lib():
 
 def set_max_attempts(m: int) -> None:
     lib().wt_oracle_set_max_attempts(int(m))
+
+
+def set_ph_h_eps(eps: float) -> None:
+    lib().wt_oracle_set_ph_h_eps(float(eps))
 
 
 def _dp(a):
