@@ -32,6 +32,7 @@ CNT_NAMES = ("nfev", "njev", "nlu", "nsteps", "nnewton", "nreject", "nnewton_fai
 EXPORTS = (
     "wt_abi_version", "wt_device_count", "wt_last_error", "wt_step", "wt_advance", "wt_derivatives",
     "wt_step_host", "wt_calc_ph", "wt_measure_fp64_peak", "wt_stats", "wt_stats_size", "wt_stats_scratch_doubles",
+    "wt_sensors_init", "wt_sensors_calibrate", "wt_sensors_read",
 )
 
 
@@ -73,6 +74,13 @@ def lib() -> C.CDLL:
     L.wt_stats_scratch_doubles.restype = C.c_int
     L.wt_stats.argtypes = [C.c_int, C.c_int, dp, up, dp, dp, dp, C.c_int, vp]
     L.wt_stats.restype = C.c_int
+    L.wt_sensors_init.argtypes = [C.c_int, C.c_double, dp, dp, dp, dp, ip, ip, vp]
+    L.wt_sensors_init.restype = C.c_int
+    L.wt_sensors_calibrate.argtypes = [C.c_int, C.c_int, C.c_double, dp, C.c_double, dp, ip, vp]
+    L.wt_sensors_calibrate.restype = C.c_int
+    L.wt_sensors_read.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_uint, C.c_double, C.c_double, dp, dp, dp, dp, dp, dp, ip,
+                                  dp, ip, dp, ip, ip, C.POINTER(C.c_double), C.c_uint64, vp]
+    L.wt_sensors_read.restype = C.c_int
     L.wt_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.c_int]
     L.wt_measure_fp64_peak.restype = C.c_int
     _lib = L

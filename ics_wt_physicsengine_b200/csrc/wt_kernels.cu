@@ -13,6 +13,7 @@
 
 #include "../../include/wt_b200.h"
 #include "wt_step_core.h"
+#include "wt_sensors.cuh"
 
 static_assert((int)WT_NPAR == (int)WTP_NPAR && (int)WT_NBND == (int)WTB_NBND && (int)WT_NCNT == (int)WTC_NCNT,
               "ABI enums out of sync with the core");
@@ -405,6 +406,61 @@ int wt_stats(int P, int n, const double *y, const uint32_t *status, const double
   wt_stats_partial_kernel<<<blocks, WT_STATS_TPB, 0, (cudaStream_t)stream>>>(P, n, y, status, shift_thr, scratch);
   wt_stats_final_kernel<<<(nstat + 127) / 128, 128, 0, (cudaStream_t)stream>>>(blocks, nstat, scratch, out, accumulate);
   return cuda_err(cudaGetLastError(), "wt_stats launch");
+}
+
+
+// ---- K3: sensor suite ---------------------------------------------------------------------------
+__global__ void wt_sensors_calibrate_kernel(int P, int sensor, double t, const double *ref, double ref_scalar,
+                                            double *sens, int *sens_i) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const size_t Pz = (size_t)P;
+  double *S = sens + (size_t)sensor * Pz + p;
+  const double r = ref ? ref[p] : ref_scalar;
+  // BaseSensor.calibrate (base_sensor.py:701-755): offset = reference - current_value, timers reset
+  S[(size_t)WT_SF_CALOFF * WT_NSENS * Pz] = r - S[(size_t)WT_SF_CUR * WT_NSENS * Pz];
+  S[(size_t)WT_SF_TCAL * WT_NSENS * Pz] = t;
+  sens_i[(size_t)sensor * Pz + p] = SS_NORMAL;
+  sens_i[((size_t)WT_NSENS + sensor) * Pz + p] = SFLT_NONE;
+}
+
+int wt_sensors_init(int P, double t0, const double *cfg_flow, const double *cfg_cl, const double *cfg_T, double *sens,
+                    int32_t *sens_i, int32_t *ring_i, void *stream) {
+  if (P <= 0) return set_err(WT_ERR_BAD_ARG, "P must be positive");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (!cfg_flow || !cfg_cl || !cfg_T || !sens || !sens_i || !ring_i) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  wt_sensors_init_kernel<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, t0, cfg_flow, cfg_cl, cfg_T, sens, sens_i, ring_i);
+  return cuda_err(cudaGetLastError(), "wt_sensors_init_kernel launch");
+}
+
+int wt_sensors_calibrate(int P, int sensor, double t, const double *ref_dev, double ref_scalar, double *sens,
+                         int32_t *sens_i, void *stream) {
+  if (P <= 0 || sensor < 0 || sensor >= WT_NSENS) return set_err(WT_ERR_BAD_ARG, "bad P or sensor index");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (!sens || !sens_i) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  wt_sensors_calibrate_kernel<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, sensor, t, ref_dev, ref_scalar, sens, sens_i);
+  return cuda_err(cudaGetLastError(), "wt_sensors_calibrate_kernel launch");
+}
+
+int wt_sensors_read(int P, int n, long long plant0, unsigned read_index, double t, double t_prev, const double *y,
+                    const double *flow, const double *cfg_flow, const double *cfg_cl, const double *cfg_T, double *sens,
+                    int32_t *sens_i, double *ring, int32_t *ring_i, double *out, int32_t *out_status, int32_t *out_fault,
+                    const double *suite6, uint64_t seed, void *stream) {
+  int rc = check_common(P, n);
+  if (rc) return rc;
+  if (!y || !flow || !cfg_flow || !cfg_cl || !cfg_T || !sens || !sens_i || !ring || !ring_i || !out || !out_status ||
+      !out_fault || !suite6)
+    return set_err(WT_ERR_BAD_ARG, "null pointer");
+  SensorArgs a;
+  a.P = P; a.n = n; a.plant0 = plant0; a.read_index = read_index; a.t = t; a.t_prev = t_prev;
+  a.y = y; a.flow = flow; a.cfg_flow = cfg_flow; a.cfg_cl = cfg_cl; a.cfg_T = cfg_T;
+  a.sens = sens; a.sens_i = sens_i; a.ring = ring; a.ring_i = ring_i; a.out = out; a.out_status = out_status;
+  a.out_fault = out_fault;
+  a.s.flow_velocity = suite6[0]; a.s.bubble_per_min = suite6[1]; a.s.grounding = suite6[2]; a.s.vibration_g = suite6[3];
+  a.s.ambient_temp = suite6[4]; a.s.line_delay_s = suite6[5];
+  a.s.seed_lo = (uint32_t)seed; a.s.seed_hi = (uint32_t)(seed >> 32);
+  wt_sensors_read_kernel<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+  return cuda_err(cudaGetLastError(), "wt_sensors_read_kernel launch");
 }
 
 // Host-buffer path: one workspace per process, grown on demand.

@@ -1,0 +1,197 @@
+"""Host-side mirror of ``wt_simulator.sensors`` for the batched sensor suite.
+
+``create_realistic_sensor_suite(ensemble)`` builds, for every plant of a ``PlantEnsemble``, the 7
+sensors of the reference factory (sensors/__init__.py:41-120) and ``SensorSuite.read(state, t)`` is
+one kernel launch doing ``<Sensor>.read(reactor_state, current_time)`` for all of them in the
+reference's dict order (base_sensor.py:509-699 + the four subclasses).  Enum values, reading
+fields, calibration semantics (``calibrate(reference, t)`` -> offset = reference - current_value)
+and the monotonic-time ``ValueError`` are the reference's.  Randomness is a counter-based Philox
+stream keyed by (seed, global plant id, read index): outputs match the reference in
+distribution, not draw for draw (the reference seeds from ``secrets``, base_sensor.py:331).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from enum import Enum
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ensembles import CFG_FIELDS
+
+
+class SensorStatus(Enum):  # base_sensor.py:49-63
+    NORMAL = "normal"
+    CALIBRATING = "calibrating"
+    WARMING_UP = "warming_up"
+    FAILED = "failed"
+    SATURATED = "saturated"
+    DRIFT_WARNING = "drift_warning"
+    CALIBRATION_EXPIRED = "calibration_expired"
+    OPEN_CIRCUIT = "open_circuit"
+    SHORT_CIRCUIT = "short_circuit"
+    OUT_OF_RANGE = "out_of_range"
+    POWER_FAULT = "power_fault"
+    RATE_OF_CHANGE_FAULT = "rate_of_change_fault"
+
+
+class SensorFault(Enum):  # base_sensor.py:66-75
+    NONE = "none"
+    OPEN_CIRCUIT = "open_circuit"
+    SHORT_CIRCUIT = "short_circuit"
+    OUT_OF_RANGE = "out_of_range"
+    RATE_FAULT = "rate_fault"
+    POWER_LOW = "power_low"
+    POWER_HIGH = "power_high"
+
+
+STATUS_BY_CODE = tuple(SensorStatus)   # device codes are the enum declaration order
+FAULT_BY_CODE = tuple(SensorFault)
+SENSOR_NAMES = ("pH_inlet", "pH_outlet", "chlorine_inlet", "chlorine_outlet", "flow_main", "temp_inlet", "temp_outlet")
+
+
+@dataclass
+class InstallationQuality:  # base_sensor.py:124-145; defaults = the suite's "good_installation"
+    flow_velocity: float = 0.5
+    air_bubble_frequency: float = 0.0
+    grounding_quality: float = 0.9
+    pipe_vibration_g: float = 0.1
+    ambient_temperature: float = 30.0
+
+    def validate(self):
+        if not 0.0 <= self.flow_velocity <= 5.0:
+            raise ValueError(f"Flow velocity {self.flow_velocity} m/s out of range")
+        if not 0.0 <= self.grounding_quality <= 1.0:
+            raise ValueError("Grounding quality must be 0-1")
+        if self.pipe_vibration_g < 0:
+            raise ValueError("Vibration must be non-negative")
+
+
+@dataclass
+class SampleLine:  # base_sensor.py:148-175; defaults = the suite's sample lines
+    volume_mL: float = 250.0
+    flow_rate_mL_min: float = 500.0
+    ambient_temp: float = 25.0
+
+    @property
+    def transport_delay_s(self) -> float:
+        volume_L = self.volume_mL / 1000.0
+        flow_rate_L_s = self.flow_rate_mL_min / 1000.0 / 60.0
+        return volume_L / flow_rate_L_s if flow_rate_L_s > 0 else 0.0
+
+
+@dataclass
+class BatchReading:
+    """SensorReading (base_sensor.py:78-103) for P plants: device tensors of length P."""
+
+    timestamp: float
+    value: torch.Tensor
+    raw_value: torch.Tensor
+    noise: torch.Tensor
+    drift: torch.Tensor
+    status: torch.Tensor       # int32 codes, see STATUS_BY_CODE
+    uncertainty: torch.Tensor
+    fault: torch.Tensor        # int32 codes, see FAULT_BY_CODE
+
+    def status_of(self, p: int) -> SensorStatus:
+        return STATUS_BY_CODE[int(self.status[p])]
+
+    def fault_of(self, p: int) -> SensorFault:
+        return FAULT_BY_CODE[int(self.fault[p])]
+
+
+class SensorSuite:
+    """The 7-sensor suite of every plant of one ensemble shard, state resident in HBM."""
+
+    def __init__(self, ensemble, seed: int = 0, plant0: int = 0, installation: Optional[InstallationQuality] = None,
+                 sample_line: Optional[SampleLine] = None):
+        _lib.require_device()
+        self.ens = ensemble
+        self.seed, self.plant0 = int(seed) & (2 ** 64 - 1), int(plant0)
+        self.installation = installation or InstallationQuality()
+        self.installation.validate()
+        line = sample_line or SampleLine()
+        if int(line.transport_delay_s) + 10 > 100:
+            raise ValueError("sample-line delay needs a deque longer than the 100 slots the engine keeps")
+        i = self.installation
+        self._suite6 = np.array([i.flow_velocity, i.air_bubble_frequency, i.grounding_quality, i.pipe_vibration_g,
+                                 i.ambient_temperature, line.transport_delay_s], dtype=np.float64)
+        P, dev = ensemble.n_plants, ensemble.device
+        cfg = ensemble.cfg
+        col = lambda k: torch.from_numpy(np.ascontiguousarray(cfg[:, CFG_FIELDS.index(k)])).to(dev)
+        self._cfg_flow, self._cfg_cl, self._cfg_T = col("flow_rate"), col("initial_chlorine"), col("temperature")
+        f64, i32 = torch.float64, torch.int32
+        self._sens = torch.zeros((8, 7, P), dtype=f64, device=dev)
+        self._sens_i = torch.zeros((2, 7, P), dtype=i32, device=dev)
+        self._ring = torch.zeros((2, 100, 2, P), dtype=f64, device=dev)
+        self._ring_i = torch.zeros((2, 2, P), dtype=i32, device=dev)
+        self._out = torch.zeros((5, 7, P), dtype=f64, device=dev)
+        self._out_status = torch.zeros((7, P), dtype=i32, device=dev)
+        self._out_fault = torch.zeros((7, P), dtype=i32, device=dev)
+        self.read_index = 0
+        self.last_time: Optional[float] = None
+        self._initialized = False
+
+    def keys(self):
+        return SENSOR_NAMES
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def initialize(self, t0: float) -> None:
+        """Constructors + __main__.initialize_sensors: calibrate every sensor at t0 with references
+        7.0 (pH), config.initial_chlorine, config.temperature, config.flow_rate (__main__.py:96-105)."""
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.ens.device):
+            rc = _lib.lib().wt_sensors_init(self.ens.n_plants, float(t0), p(self._cfg_flow), p(self._cfg_cl), p(self._cfg_T),
+                                            p(self._sens), p(self._sens_i), p(self._ring_i), self._stream())
+        _lib.check(rc, "wt_sensors_init")
+        self.read_index, self.last_time, self._initialized = 0, None, True
+        self._t0 = float(t0)
+
+    def calibrate(self, name: str, reference, current_time: float) -> None:
+        """BaseSensor.calibrate(reference, t) for sensor `name` of every plant (base_sensor.py:701-755)."""
+        s = SENSOR_NAMES.index(name)
+        ref_t, ref_s = None, 0.0
+        if np.ndim(reference) == 0 and not torch.is_tensor(reference):
+            ref_s = float(reference)
+        else:
+            ref_t = torch.as_tensor(reference, dtype=torch.float64).reshape(self.ens.n_plants).to(self.ens.device).contiguous()
+        with torch.cuda.device(self.ens.device):
+            rc = _lib.lib().wt_sensors_calibrate(self.ens.n_plants, s, float(current_time),
+                                                 C.c_void_p(0 if ref_t is None else ref_t.data_ptr()), ref_s,
+                                                 C.c_void_p(self._sens.data_ptr()), C.c_void_p(self._sens_i.data_ptr()),
+                                                 self._stream())
+        _lib.check(rc, "wt_sensors_calibrate")
+
+    def read(self, reactor_state=None, current_time: Optional[float] = None) -> Dict[str, BatchReading]:
+        """All 7 sensors of every plant read the ensemble state at `current_time`."""
+        if not self._initialized:
+            raise RuntimeError("call initialize(t0) first (the reference calibrates its sensors at start-up)")
+        if current_time is None:
+            raise ValueError("current_time is required (the ensemble runs on simulated time)")
+        if self.last_time is not None and current_time < self.last_time:
+            raise ValueError(f"Non-monotonic time: {current_time} < {self.last_time}")  # base_sensor.py:543-549
+        e = self.ens
+        p = lambda t: C.c_void_p(t.data_ptr())
+        t_prev = self.last_time if self.last_time is not None else float(current_time)
+        with torch.cuda.device(e.device):
+            rc = _lib.lib().wt_sensors_read(
+                e.n_plants, e.n_zones, self.plant0, self.read_index, float(current_time), float(t_prev), p(e._y), p(e._flow),
+                p(self._cfg_flow), p(self._cfg_cl), p(self._cfg_T), p(self._sens), p(self._sens_i), p(self._ring),
+                p(self._ring_i), p(self._out), p(self._out_status), p(self._out_fault),
+                self._suite6.ctypes.data_as(C.POINTER(C.c_double)), C.c_uint64(self.seed), self._stream())
+        _lib.check(rc, "wt_sensors_read")
+        self.read_index += 1
+        self.last_time = float(current_time)
+        o = self._out
+        return {name: BatchReading(float(current_time), o[0, s], o[1, s], o[2, s], o[3, s], self._out_status[s], o[4, s],
+                                   self._out_fault[s]) for s, name in enumerate(SENSOR_NAMES)}
+
+
+def create_realistic_sensor_suite(ensemble, seed: int = 0, plant0: int = 0) -> SensorSuite:
+    """Batched counterpart of sensors/__init__.py:41-120 for a PlantEnsemble (same 7 keys)."""
+    return SensorSuite(ensemble, seed=seed, plant0=plant0)

@@ -140,6 +140,46 @@ int wt_stats(int P, int n_zones, const double *y_dev, const uint32_t *status_dev
              const double *shift_thr_dev, double *out_dev, double *scratch_dev, int accumulate,
              void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Sensor suite of create_realistic_sensor_suite (sensors/__init__.py:41-120): 7 sensors per plant in
+ * the reference's dict order 0 pH_inlet, 1 pH_outlet, 2 chlorine_inlet (amperometric),
+ * 3 chlorine_outlet (DPD), 4 flow_main (magnetic), 5 temp_inlet (RTD), 6 temp_outlet (RTD);
+ * pH_x and temp_x share one SampleLine, as in the reference.
+ *
+ * Device buffers (plant index fastest; shapes in elements):
+ *   sens     double [8][7][P]      per-sensor state (WT_SF_*: current_value, supply_voltage,
+ *                                  calibration_offset, calibration time, last history value, 3 aux)
+ *   sens_i   int32  [2][7][P]      sticky SensorStatus, SensorFault (enum order of base_sensor.py:49-75)
+ *   ring     double [2][100][2][P] delay lines: (timestamp, value) per slot
+ *   ring_i   int32  [2][2][P]      per line: head, count
+ *   out      double [5][7][P]      SensorReading.value, raw_value, noise, drift, uncertainty
+ *   out_status, out_fault  int32 [7][P]
+ *
+ * wt_sensors_init     = constructors + __main__.initialize_sensors (calibrate(reference, t0) with
+ *                       reference 7.0 / initial_chlorine / temperature / flow_rate; __main__.py:96-105)
+ * wt_sensors_calibrate = BaseSensor.calibrate(reference, t) for one sensor of every plant
+ *                       (base_sensor.py:701-755); ref_dev NULL -> ref_scalar for all plants
+ * wt_sensors_read     = <Sensor>.read(reactor_state, current_time) for the whole suite
+ *                       (base_sensor.py:509-699 + ph_sensor.py:216-336, chlorine_sensor.py:345-484,
+ *                       temperature_sensor.py:110-171, flow_sensor.py:125-219).  t must not decrease
+ *                       (base_sensor.py:543-549 raises; the Python facade checks it).
+ *     plant0      global id of the shard's first plant; read_index = number of earlier suite reads
+ *                 (both only feed the counter-based Philox4x32-10 RNG: results are independent of sharding)
+ *     suite6      HOST array {flow_velocity, air_bubble_frequency, grounding_quality, pipe_vibration_g,
+ *                 ambient_temperature, sample-line transport delay [s]}
+ * ------------------------------------------------------------------------------------- */
+int wt_sensors_init(int P, double t0, const double *cfg_flow_dev, const double *cfg_chlorine_dev,
+                    const double *cfg_temperature_dev, double *sens_dev, int32_t *sens_i_dev,
+                    int32_t *ring_i_dev, void *stream);
+int wt_sensors_calibrate(int P, int sensor, double t, const double *ref_dev, double ref_scalar,
+                         double *sens_dev, int32_t *sens_i_dev, void *stream);
+int wt_sensors_read(int P, int n_zones, long long plant0, unsigned read_index, double t, double t_prev,
+                    const double *y_dev, const double *flow_rate_dev, const double *cfg_flow_dev,
+                    const double *cfg_chlorine_dev, const double *cfg_temperature_dev, double *sens_dev,
+                    int32_t *sens_i_dev, double *ring_dev, int32_t *ring_i_dev, double *out_dev,
+                    int32_t *out_status_dev, int32_t *out_fault_dev, const double *suite6,
+                    uint64_t seed, void *stream);
+
 /* Measured-peak helper for the roofline denominator: runs a dependent-chain-free DFMA loop on
  * every SM and returns the sustained FP64 rate in TFLOP/s (2 flops per DFMA). */
 int wt_measure_fp64_peak(double *tflops_out, int iters);

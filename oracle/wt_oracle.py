@@ -45,8 +45,8 @@ ST_HALT_MASK = ST_T_RANGE | ST_WORK_LIMIT
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc only)."""
-    src = os.path.join(_HERE, "wt_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("wt_oracle.c", "wt_sensors_oracle.c", "wt_oracle.h")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libwt_oracle.so"])
     return _LIB_PATH
 
@@ -79,6 +79,14 @@ def lib():
         L.wt_oracle_calc_ph.restype = C.c_int
         L.wt_oracle_calc_ph_batch.argtypes = [C.c_int, dp, dp, dp, dp, dp, ip, ip, C.c_int]
         L.wt_oracle_calc_ph_batch.restype = None
+        L.wt_oracle_suite_bytes.restype = C.c_int
+        L.wt_oracle_sensors_init.argtypes = [C.c_int, C.c_double, dp, dp, dp, C.c_void_p]
+        L.wt_oracle_sensors_init.restype = None
+        L.wt_oracle_sensors_calibrate.argtypes = [C.c_int, C.c_int, C.c_double, dp, C.c_void_p]
+        L.wt_oracle_sensors_calibrate.restype = None
+        L.wt_oracle_sensors_read.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_uint, C.c_double, C.c_double, dp, dp,
+                                             C.c_void_p, dp, ip, ip, dp, C.c_uint64, C.c_int]
+        L.wt_oracle_sensors_read.restype = None
         _lib = L
     return _lib
 
@@ -154,3 +162,40 @@ def calc_ph_batch(alk, ct, temp, guess, nthreads=1):
     lib().wt_oracle_calc_ph_batch(P, _dp(alk), _dp(ct), _dp(temp), _dp(guess), _dp(ph), _ip(iters),
                                   _ip(status), nthreads)
     return ph, iters, status
+
+
+SENSOR_NAMES = ("pH_inlet", "pH_outlet", "chlorine_inlet", "chlorine_outlet", "flow_main", "temp_inlet", "temp_outlet")
+# InstallationQuality of create_realistic_sensor_suite (sensors/__init__.py:53-59) + SampleLine delay (:62-67)
+STANDARD_SUITE6 = np.array([0.5, 0.0, 0.9, 0.1, 30.0, (250 / 1000.0) / (500 / 1000.0 / 60.0)])
+
+
+class SensorSuiteOracle:
+    """P instances of the reference sensor suite (CPU port), calibrated at t0 as __main__.initialize_sensors does."""
+
+    def __init__(self, cfg_flow, cfg_cl, cfg_T, t0, seed=0, plant0=0, suite6=None, nthreads=1):
+        self.P = len(cfg_flow)
+        self.t0, self.seed, self.plant0, self.nthreads = float(t0), int(seed), int(plant0), nthreads
+        self.suite6 = np.ascontiguousarray(STANDARD_SUITE6 if suite6 is None else suite6, dtype=np.float64)
+        self._buf = np.zeros(self.P * lib().wt_oracle_suite_bytes(), dtype=np.uint8)
+        f, c, t = (np.ascontiguousarray(a, dtype=np.float64) for a in (cfg_flow, cfg_cl, cfg_T))
+        lib().wt_oracle_sensors_init(self.P, self.t0, _dp(f), _dp(c), _dp(t), self._buf.ctypes.data)
+        self.k = 0
+        self.t_prev = self.t0
+
+    def calibrate(self, sensor: int, reference, t: float):
+        ref = np.ascontiguousarray(np.broadcast_to(np.asarray(reference, dtype=np.float64), (self.P,)))
+        lib().wt_oracle_sensors_calibrate(self.P, sensor, float(t), _dp(ref), self._buf.ctypes.data)
+
+    def read(self, y_pn, flow, t, n):
+        """y_pn [P,3n] species-major, flow [P] -> (out [P,7,5] value/raw/noise/drift/uncertainty, status [P,7], fault [P,7])."""
+        y = np.ascontiguousarray(y_pn, dtype=np.float64)
+        fl = np.ascontiguousarray(flow, dtype=np.float64)
+        out = np.zeros((self.P, 7, 5))
+        st = np.zeros((self.P, 7), dtype=np.int32)
+        ft = np.zeros((self.P, 7), dtype=np.int32)
+        lib().wt_oracle_sensors_read(self.P, n, self.plant0, self.k, float(t), float(self.t_prev), _dp(y), _dp(fl),
+                                     self._buf.ctypes.data, _dp(out), _ip(st), _ip(ft), _dp(self.suite6), self.seed,
+                                     self.nthreads)
+        self.k += 1
+        self.t_prev = float(t)
+        return out, st, ft

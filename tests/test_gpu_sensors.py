@@ -1,0 +1,151 @@
+"""Sensor-suite kernel (K3) through the facade / C ABI: value-for-value against the CPU port (both
+draw from the same counter-based Philox stream), in distribution against the committed samples of
+the unmodified reference, plus the API behaviour of the reference (calibrate, monotonic time)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from ics_wt_physicsengine_b200 import PlantEnsemble, ensembles as ens  # noqa: E402
+from ics_wt_physicsengine_b200.sensors import SENSOR_NAMES, SensorStatus, create_realistic_sensor_suite  # noqa: E402
+from tests.test_sensors_oracle import compare_distributions  # noqa: E402
+
+
+def _gpu_read(suite, t):
+    r = suite.read(None, t)
+    val = torch.stack([r[k].value for k in SENSOR_NAMES]).cpu().numpy()
+    raw = torch.stack([r[k].raw_value for k in SENSOR_NAMES]).cpu().numpy()
+    noise = torch.stack([r[k].noise for k in SENSOR_NAMES]).cpu().numpy()
+    drift = torch.stack([r[k].drift for k in SENSOR_NAMES]).cpu().numpy()
+    unc = torch.stack([r[k].uncertainty for k in SENSOR_NAMES]).cpu().numpy()
+    st = torch.stack([r[k].status for k in SENSOR_NAMES]).cpu().numpy()
+    ft = torch.stack([r[k].fault for k in SENSOR_NAMES]).cpu().numpy()
+    return np.stack([val, raw, noise, drift, unc], axis=2), st, ft   # [7, P, 5]
+
+
+def _close(a, b, tol=1e-9):
+    both_nan = np.isnan(a) & np.isnan(b)
+    d = np.abs(a - b) / np.maximum(np.abs(b), 1e-6)
+    d[both_nan] = 0.0
+    return np.nan_to_num(d, nan=np.inf).max() <= tol
+
+
+def test_default_plant_1900_reads_value_for_value(oracle, golden_dir):
+    """All warm-ups (10/30/60/300/1800 s), the shared 30 s delay lines and the absorbing faults, on the
+    golden default-plant trajectory, 2,048 suites: every field of every reading equals the CPU port."""
+    g = np.load(os.path.join(golden_dir, "sensors_default_plant.npz"))
+    P, n, t0 = 2048, 5, float(g["t0"])
+    e = ens.config1(5)
+    e = ens.Ensemble(5, np.repeat(e.cfg, P, 0), np.repeat(e.bnd, P, 0), np.repeat(e.pH0, P, 0), np.repeat(e.Cl0, P, 0), np.repeat(e.T0, P, 0))
+    eng = PlantEnsemble(e)
+    suite = create_realistic_sensor_suite(eng, seed=777)
+    suite.initialize(t0)
+    osu = oracle.SensorSuiteOracle(e.cfg[:, 3], e.cfg[:, 12], e.cfg[:, 13], t0, seed=777, nthreads=8)
+    mism = 0
+    for k in range(1901):
+        y = np.concatenate([g["traj_pH"][k], g["traj_Cl"][k], g["traj_T"][k]])
+        Y = np.broadcast_to(y, (P, 15))
+        eng.set_state(Y[:, :5], Y[:, 5:10], Y[:, 10:])
+        eng._flow.fill_(float(g["traj_flow"][k]))
+        out_g, st_g, ft_g = _gpu_read(suite, t0 + k)
+        out_o, st_o, ft_o = osu.read(Y, np.full(P, float(g["traj_flow"][k])), t0 + k, n)
+        same = (st_g.T == st_o) & (ft_g.T == ft_o)
+        mism += int((~same).sum())
+        if k % 50 == 0 or k in (1800, 1801, 1805, 1830, 1840):
+            assert _close(np.transpose(out_g, (1, 0, 2)), out_o), k
+    assert mism == 0
+
+
+def test_random_plants_with_stepping_value_for_value(oracle):
+    """Sensors reading an ensemble that is actually being stepped (config-2 plants, n = 10)."""
+    P, n, t0 = 1536, 10, 50.0
+    e = ens.config2(P, n, seed=99)
+    eng = PlantEnsemble(e)
+    suite = create_realistic_sensor_suite(eng, seed=5, plant0=1000)
+    suite.initialize(t0)
+    osu = oracle.SensorSuiteOracle(e.cfg[:, 3], e.cfg[:, 12], e.cfg[:, 13], t0, seed=5, plant0=1000, nthreads=8)
+    for k in range(340):
+        eng.step(1.0, e.bnd)
+        out_g, st_g, ft_g = _gpu_read(suite, t0 + k)
+        out_o, st_o, ft_o = osu.read(eng.state_numpy(), eng.state.flow_rate.cpu().numpy(), t0 + k, n)
+        assert np.array_equal(st_g.T, st_o) and np.array_equal(ft_g.T, ft_o), k
+        if k % 20 == 0 or k > 300:
+            assert _close(np.transpose(out_g, (1, 0, 2)), out_o), k
+
+
+def test_distribution_against_reference_samples(golden_dir):
+    """10,240 engine suites vs 10,240 reference suites at the recorded check times (moments + KS)."""
+    g = np.load(os.path.join(golden_dir, "sensors_default_plant.npz"))
+    checks = list(g["checks"])
+    P, t0 = 10240, float(g["t0"])
+    e = ens.config1(5)
+    e = ens.Ensemble(5, np.repeat(e.cfg, P, 0), np.repeat(e.bnd, P, 0), np.repeat(e.pH0, P, 0), np.repeat(e.Cl0, P, 0), np.repeat(e.T0, P, 0))
+    eng = PlantEnsemble(e)
+    suite = create_realistic_sensor_suite(eng, seed=20260004)
+    suite.initialize(t0)
+    n_tested, ci = 0, 0
+    for k in range(max(checks) + 1):
+        y = np.concatenate([g["traj_pH"][k], g["traj_Cl"][k], g["traj_T"][k]])
+        Y = np.broadcast_to(y, (P, 15))
+        eng.set_state(Y[:, :5], Y[:, 5:10], Y[:, 10:])
+        eng._flow.fill_(float(g["traj_flow"][k]))
+        r = suite.read(None, t0 + k)
+        if ci < len(checks) and k == checks[ci]:
+            for s, name in enumerate(SENSOR_NAMES):
+                b = r[name].value.cpu().numpy()
+                a = g["values"][ci, s]
+                pa, pb = np.isnan(a).mean(), np.isnan(b).mean()
+                assert abs(pa - pb) < 5 * np.sqrt(max(pa * (1 - pa), 1e-4) * 2 / P) + 1e-3, (k, name, pa, pb)
+                ha = np.bincount(g["status"][ci, s].astype(int), minlength=12) / a.size
+                hb = np.bincount(r[name].status.cpu().numpy(), minlength=12) / P
+                assert np.abs(ha - hb).max() < 0.02, (k, name)
+                a, b = a[np.isfinite(a)], b[np.isfinite(b)]
+                if a.size >= 500:
+                    n_tested += bool(compare_distributions(a, b, (k, name)))
+            ci += 1
+    assert n_tested >= 20
+
+
+def test_results_do_not_depend_on_sharding():
+    """Counter-based RNG keyed by the GLOBAL plant id: a shard reproduces its slice of the full run."""
+    P, n, t0 = 512, 10, 0.0
+    e = ens.config2(P, n, seed=3)
+    full = PlantEnsemble(e)
+    sf = create_realistic_sensor_suite(full, seed=42)
+    sf.initialize(t0)
+    lo, hi = 200, 456
+    part = PlantEnsemble(e.slice(slice(lo, hi)))
+    sp = create_realistic_sensor_suite(part, seed=42, plant0=lo)
+    sp.initialize(t0)
+    for k in range(70):
+        full.step(1.0, e.bnd)
+        part.step(1.0, e.bnd[lo:hi])
+        a, sa, fa = _gpu_read(sf, t0 + k)
+        b, sb, fb = _gpu_read(sp, t0 + k)
+        assert np.array_equal(np.nan_to_num(a[:, lo:hi], nan=-1e300), np.nan_to_num(b, nan=-1e300))
+        assert np.array_equal(sa[:, lo:hi], sb) and np.array_equal(fa[:, lo:hi], fb)
+
+
+def test_calibrate_and_time_semantics():
+    e = ens.config2(64, 10, seed=4)
+    eng = PlantEnsemble(e)
+    suite = create_realistic_sensor_suite(eng)
+    with pytest.raises(RuntimeError):
+        suite.read(None, 0.0)
+    suite.initialize(0.0)
+    for k in range(15):
+        eng.step(1.0, e.bnd)
+        r = suite.read(eng.state, float(k))
+    assert r["flow_main"].status_of(0) in (SensorStatus.DRIFT_WARNING, SensorStatus.POWER_FAULT, SensorStatus.SATURATED)
+    with pytest.raises(ValueError, match="Non-monotonic"):
+        suite.read(eng.state, 3.0)                           # base_sensor.py:543-549
+    # calibrate(reference, t): offset = reference - current_value and the warm-up timer restarts
+    cur = suite._sens[0, 4].clone()
+    suite.calibrate("flow_main", 5.0, 15.0)
+    assert torch.allclose(suite._sens[2, 4], 5.0 - cur)
+    r = suite.read(eng.state, 16.0)
+    assert (r["flow_main"].status.cpu().numpy() == 2).mean() > 0.9    # WARMING_UP again for 10 s
+    assert set(suite.keys()) == set(SENSOR_NAMES)
