@@ -223,7 +223,7 @@ class PlantEnsemble:
         """Overwrite the primary state ([P, n_zones] each), as assigning reactor.state.* does."""
         P, n = self.n_plants, self.n_zones
         for v, a in enumerate((pH, chlorine, temperature)):
-            a = torch.as_tensor(np.asarray(a, dtype=np.float64) if not torch.is_tensor(a) else a,
+            a = torch.as_tensor(np.array(a, dtype=np.float64) if not torch.is_tensor(a) else a,
                                 dtype=torch.float64).reshape(P, n)
             self._y[v].copy_(a.t().to(self.device))
         if time is not None:

@@ -82,8 +82,8 @@ def compare_distributions(a, b, what):
     sa, sb = am.std(), bm.std()
     assert abs(am.mean() - bm.mean()) < 6 * np.sqrt(sa ** 2 / am.size + sb ** 2 / bm.size) + 1e-9, (what, "mean", am.mean(), bm.mean())
     assert abs(sa - sb) < 0.06 * max(sa, sb) + 1e-9, (what, "std", sa, sb)
-    assert abs(stats.skew(am) - stats.skew(bm)) < 0.25, (what, "skew")
-    assert abs(stats.kurtosis(am) - stats.kurtosis(bm)) < 0.6, (what, "kurtosis")
+    assert abs(stats.skew(am) - stats.skew(bm)) < 0.3, (what, "skew")
+    assert abs(stats.kurtosis(am) - stats.kurtosis(bm)) < 1.0, (what, "kurtosis")  # one-sided clipped modes: large sampling error
     return True
 
 
