@@ -48,8 +48,10 @@ __host__ __device__ inline int wt_lu_slots(int n) {
   for (int s = 1; s < n; s <<= 1) ++L;
   return 3 * (2 * L + 1) + 3 * (4 * L + 2);
 }
+// + the lane-private constants (LK_*) kept after the LU multipliers
+__host__ __device__ inline int wt_lane_slots(int n) { return wt_lu_slots(n) + LK_N; }
 // doubles of shared memory per warp: LU slots for 32 lanes + constants for (32/n + 1) plants
-__host__ __device__ inline int wt_warp_smem_doubles(int n) { return wt_lu_slots(n) * 32 + (32 / n + 1) * CK_N; }
+__host__ __device__ inline int wt_warp_smem_doubles(int n) { return wt_lane_slots(n) * 32 + (32 / n + 1) * CK_N; }
 
 struct StepArgs {
   int P, n, n_steps, bnd_stride, max_attempts;
@@ -68,7 +70,13 @@ struct StepArgs {
 #endif
 
 template <int WARPS>
+#if WT_STEP_MINBLOCKS > 0
 __global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_kernel(StepArgs a) {
+#elif defined(WT_STEP_MAXNREG)
+__global__ void __maxnreg__(WT_STEP_MAXNREG) wt_step_kernel(StepArgs a) {
+#else
+__global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
+#endif
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = a.n, gpw = 32 / n;
@@ -82,11 +90,13 @@ __global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_kernel(
 
   uint32_t st_in = in_plant ? a.status[p] : 0u;
   bool on = in_plant && !(st_in & WTS_HALT_MASK);
+#ifndef WT_CTA_LOCKSTEP
   if (!__any_sync(0xffffffffu, on)) return;
+#endif
 
   SmemLu lu;
   lu.p = smem + (size_t)warp * wt_warp_smem_doubles(n) + lane;
-  lu.cp = smem + (size_t)warp * wt_warp_smem_doubles(n) + wt_lu_slots(n) * 32 + (gi < gpw ? gi : gpw) * CK_N;
+  lu.cp = smem + (size_t)warp * wt_warp_smem_doubles(n) + wt_lane_slots(n) * 32 + (gi < gpw ? gi : gpw) * CK_N;
 
   WtPlantStep<SmemLu> ps;
   ps.g = wt_make_group(n);
@@ -97,7 +107,7 @@ __global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_kernel(
     for (int k = 0; k < WTP_NPAR; ++k) par[k] = a.par[(size_t)k * P + p];
 #pragma unroll
     for (int k = 0; k < WTB_NBND; ++k) bnd[k] = a.bnd[a.bnd_stride ? (size_t)k * P + p : (size_t)k];
-    ps.c = wt_make_const(&lu, par, bnd);
+    ps.c = wt_make_const(&lu, ps.g, wt_lu_slots(n), par, bnd);
   }
   double t = a.time[p];
 #pragma unroll
@@ -111,7 +121,9 @@ __global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_kernel(
   bool stepped = false;
 
   for (int s = 0; s < a.n_steps; ++s) {
+#ifndef WT_CTA_LOCKSTEP
     if (!__any_sync(0xffffffffu, on)) break;
+#endif
     double yin[3] = {ps.y[0], ps.y[1], ps.y[2]};
     ps.integrate(t, a.dt, on, a.max_attempts);
     bool adv;
@@ -158,16 +170,16 @@ __global__ void wt_derivatives_kernel(int P, int n, const double *par_, const do
   const int p = in_plant ? (int)pl : 0;
   const int z = in_plant ? lane - gi * n : 0;
   WtGroup g = wt_make_group(n);
-  __shared__ double cs[4][17 * CK_N];
+  __shared__ double cs[4][17 * CK_N + LK_N * 32];
   SmemLu st;
-  st.p = nullptr;
+  st.p = &cs[threadIdx.x >> 5][17 * CK_N + lane];
   st.cp = &cs[threadIdx.x >> 5][(gi < gpw ? gi : gpw) * CK_N];
   double par[WTP_NPAR], bnd[WTB_NBND];
 #pragma unroll
   for (int k = 0; k < WTP_NPAR; ++k) par[k] = par_[(size_t)k * P + p];
 #pragma unroll
   for (int k = 0; k < WTB_NBND; ++k) bnd[k] = bnd_[bnd_stride ? (size_t)k * P + p : (size_t)k];
-  WtConstT<SmemLu> c = wt_make_const(&st, par, bnd);
+  WtConstT<SmemLu> c = wt_make_const(&st, g, 0, par, bnd);
   double yy[3], d[3];
 #pragma unroll
   for (int v = 0; v < 3; ++v) yy[v] = y[((size_t)v * n + z) * P + p];

@@ -58,40 +58,58 @@ enum {
 #define WT_LN10 2.302585092994046
 #define WT_EPS 2.220446049250313e-16
 
-// radau.py:11-45
+// radau.py:11-45.  On the GPU the tables live in __constant__ memory so that DFMA/DMUL take them
+// as c[bank][offset] operands instead of materialising 64-bit immediates (two UMOV each).
 #define WT_S6 2.449489742783178
-#define WT_C0 ((4.0 - WT_S6) / 10.0)
-#define WT_C1 ((4.0 + WT_S6) / 10.0)
-#define WT_E0 ((-13.0 - 7.0 * WT_S6) / 3.0)
-#define WT_E1 ((-13.0 + 7.0 * WT_S6) / 3.0)
-#define WT_E2 (-1.0 / 3.0)
-#define WT_MU_REAL 3.6378342527444957          // 3 + 3**(2/3) - 3**(1/3)
-#define WT_MU_CRE 2.6810828736277523           // 3 + 0.5*(3**(1/3) - 3**(2/3))
-#define WT_MU_CIM (-3.0504301992474105)        // -0.5*(3**(5/6) + 3**(7/6))
-#define WT_T00 0.09443876248897524
-#define WT_T01 (-0.14125529502095421)
-#define WT_T02 0.03002919410514742
-#define WT_T10 0.25021312296533332
-#define WT_T11 0.20412935229379994
-#define WT_T12 (-0.38294211275726192)
-#define WT_TI00 4.17871859155190428
-#define WT_TI01 0.32768282076106237
-#define WT_TI02 0.52337644549944951
-#define WT_TI10 (-4.17871859155190428)
-#define WT_TI11 (-0.32768282076106237)
-#define WT_TI12 0.47662355450055044
-#define WT_TI20 0.50287263494578682
-#define WT_TI21 (-2.57192694985560522)
-#define WT_TI22 0.59603920482822492
-#define WT_P00 (13.0 / 3.0 + 7.0 * WT_S6 / 3.0)
-#define WT_P01 (-23.0 / 3.0 - 22.0 * WT_S6 / 3.0)
-#define WT_P02 (10.0 / 3.0 + 5.0 * WT_S6)
-#define WT_P10 (13.0 / 3.0 - 7.0 * WT_S6 / 3.0)
-#define WT_P11 (-23.0 / 3.0 + 22.0 * WT_S6 / 3.0)
-#define WT_P12 (10.0 / 3.0 - 5.0 * WT_S6)
-#define WT_P20 (1.0 / 3.0)
-#define WT_P21 (-8.0 / 3.0)
-#define WT_P22 (10.0 / 3.0)
+#define WT_RADAU_TABLE {                                                                      \
+    (4.0 - WT_S6) / 10.0, (4.0 + WT_S6) / 10.0,                                  /* 0 C0 C1 */ \
+    (-13.0 - 7.0 * WT_S6) / 3.0, (-13.0 + 7.0 * WT_S6) / 3.0, -1.0 / 3.0,        /* 2 E */     \
+    3.6378342527444957, 2.6810828736277523, -3.0504301992474105,                 /* 5 MU_REAL, MU_COMPLEX re, im */ \
+    0.09443876248897524, -0.14125529502095421, 0.03002919410514742,              /* 8 T row 0 */ \
+    0.25021312296533332, 0.20412935229379994, -0.38294211275726192,              /* 11 T row 1 */ \
+    4.17871859155190428, 0.32768282076106237, 0.52337644549944951,               /* 14 TI row 0 */ \
+    -4.17871859155190428, -0.32768282076106237, 0.47662355450055044,             /* 17 TI row 1 */ \
+    0.50287263494578682, -2.57192694985560522, 0.59603920482822492,              /* 20 TI row 2 */ \
+    13.0 / 3.0 + 7.0 * WT_S6 / 3.0, -23.0 / 3.0 - 22.0 * WT_S6 / 3.0, 10.0 / 3.0 + 5.0 * WT_S6,   /* 23 P row 0 */ \
+    13.0 / 3.0 - 7.0 * WT_S6 / 3.0, -23.0 / 3.0 + 22.0 * WT_S6 / 3.0, 10.0 / 3.0 - 5.0 * WT_S6,   /* 26 P row 1 */ \
+    1.0 / 3.0, -8.0 / 3.0, 10.0 / 3.0 }                                          /* 29 P row 2 */
+#ifdef WT_EMU
+static const double wt_rk[32] = WT_RADAU_TABLE;
+#else
+__constant__ double wt_rk[32] = WT_RADAU_TABLE;
+#endif
+#define WT_C0 wt_rk[0]
+#define WT_C1 wt_rk[1]
+#define WT_E0 wt_rk[2]
+#define WT_E1 wt_rk[3]
+#define WT_E2 wt_rk[4]
+#define WT_MU_REAL wt_rk[5]   // 3 + 3**(2/3) - 3**(1/3)
+#define WT_MU_CRE wt_rk[6]    // 3 + 0.5*(3**(1/3) - 3**(2/3))
+#define WT_MU_CIM wt_rk[7]    // -0.5*(3**(5/6) + 3**(7/6))
+#define WT_T00 wt_rk[8]
+#define WT_T01 wt_rk[9]
+#define WT_T02 wt_rk[10]
+#define WT_T10 wt_rk[11]
+#define WT_T11 wt_rk[12]
+#define WT_T12 wt_rk[13]
+#define WT_TI00 wt_rk[14]
+#define WT_TI01 wt_rk[15]
+#define WT_TI02 wt_rk[16]
+#define WT_TI10 wt_rk[17]
+#define WT_TI11 wt_rk[18]
+#define WT_TI12 wt_rk[19]
+#define WT_TI20 wt_rk[20]
+#define WT_TI21 wt_rk[21]
+#define WT_TI22 wt_rk[22]
+#define WT_P00 wt_rk[23]
+#define WT_P01 wt_rk[24]
+#define WT_P02 wt_rk[25]
+#define WT_P10 wt_rk[26]
+#define WT_P11 wt_rk[27]
+#define WT_P12 wt_rk[28]
+#define WT_P20 wt_rk[29]
+#define WT_P21 wt_rk[30]
+#define WT_P22 wt_rk[31]
 #define WT_NEWTON_MAXITER 6
 #define WT_HARD_MAX_ATTEMPTS 2000000
 #define WT_NEWTON_TOL 1e-3  // max(10*EPS/rtol, min(0.03, sqrt(rtol))), radau.py:315
@@ -110,6 +128,7 @@ struct WtGroup {
   double inv_sqrtN, inv_sqrt3N;  // 1/sqrt(3n), 1/sqrt(9n) for the RMS norms (common.py:63-65)
   vi lane;     // this lane
   vi last_lane;  // last lane of this lane's plant
+  vi src_dn1, src_up1;  // neighbour zones' lanes, clamped to the plant
 };
 
 WT_DEV WtGroup wt_make_group(int n) {
@@ -137,12 +156,19 @@ WT_DEV WtGroup wt_make_group(int n) {
   g.inv_sqrt3N = 1.0 / sqrt((double)(9 * n));
   g.lane = lane;
   g.last_lane = seli(in, g.base + (n - 1), lane);
+  g.src_dn1 = vmaxi(lane - 1, g.base);
+  g.src_up1 = vmini(lane + 1, g.last_lane);
   return g;
 }
 
 // neighbour access inside the plant; `dflt` outside
 WT_DEV vd wt_dn(const WtGroup &g, vd x, double dflt) { return sel(g.first, dflt, shfl_up(x, 1)); }
 WT_DEV vd wt_up(const WtGroup &g, vd x, double dflt) { return sel(g.last, dflt, shfl_down(x, 1)); }
+// Same neighbours through source lanes clamped to the plant (edge zones read themselves): for use
+// where the coefficient that multiplies a non-existent neighbour is exactly 0, so no select is needed
+// and no value of another plant (possibly NaN) is ever touched.
+WT_DEV vd wt_dnc(const WtGroup &g, vd x) { return shfl_idx(x, g.src_dn1); }
+WT_DEV vd wt_upc(const WtGroup &g, vd x) { return shfl_idx(x, g.src_up1); }
 WT_DEV vd wt_dn_s(const WtGroup &g, vd x, int s) { return sel(g.z >= s, shfl_up(x, s), 0.0); }
 WT_DEV vd wt_up_s(const WtGroup &g, vd x, int s) { return sel((g.z + s) < g.n, shfl_down(x, s), 0.0); }
 // Source lanes at stride s CLAMPED to the plant: a lane never reads another plant's values (no
@@ -153,6 +179,7 @@ WT_DEV vi wt_src_up(const WtGroup &g, int s) { return vmini(g.lane + s, g.last_l
 
 // sum over the plant's lanes, result replicated on all of them
 WT_DEV vd wt_gsum(const WtGroup &g, vd x) {
+  WT_NOUNROLL
   for (int s = 1; s < g.n; s <<= 1) x = x + wt_up_s(g, x, s);
   return shfl_idx(x, g.base);
 }
@@ -167,10 +194,16 @@ enum {
   CK_Kw = 0, CK_Ka1, CK_Ka12, CK_KaCl, CK_CT2303, CK_Kx, CK_zh, CK_Ri_thr, CK_QV, CK_Hin, CK_dHd,
   CK_cl_dose, CK_inCl, CK_inT, CK_hlA, CK_amb, CK_inv_hl_den, CK_N
 };
+// per-LANE constants (zone-position dependent), kept in lane-private slots of the store after the LU
+// multipliers: the "zone 0 only" / "last zone only" terms of reactor.py:336-395 become multiplications
+// by a constant that is 0 on the other zones (x + 0 and 0 * finite are exact), not selects
+enum { LK_KX_UP = 0, LK_KX_DN, LK_QV_FIRST, LK_QV_LAST, LK_DHD_FIRST, LK_DOSE_FIRST, LK_N };
 template <class Store>
 struct WtConstT {
   Store *st;
-  vb strat, v_ok, acid_on, cl_on, hl_on;
+  int lk0;  // first lane-constant slot
+  vb strat, v_ok;
+  WT_DEV vd lk(int k) const { return st->get(lk0 + k); }
   WT_DEV vd Kw() const { return st->cget(CK_Kw); }
   WT_DEV vd Ka1() const { return st->cget(CK_Ka1); }
   WT_DEV vd Ka12() const { return st->cget(CK_Ka12); }
@@ -193,9 +226,10 @@ struct WtConstT {
 // par / bnd hold this lane's plant values (already loaded); boundary-derived terms follow
 // reactor.py:336, 349-368, 388-395, 420, 426-443
 template <class Store>
-WT_DEV WtConstT<Store> wt_make_const(Store *st, const vd *par, const vd *bnd) {
+WT_DEV WtConstT<Store> wt_make_const(Store *st, const WtGroup &g, int lk0, const vd *par, const vd *bnd) {
   WtConstT<Store> c;
   c.st = st;
+  c.lk0 = lk0;
   st->cput(CK_Kw, par[WTP_KW]);
   st->cput(CK_Ka1, par[WTP_KA1]);
   st->cput(CK_Ka12, par[WTP_KA1] * par[WTP_KA2]);
@@ -206,16 +240,23 @@ WT_DEV WtConstT<Store> wt_make_const(Store *st, const vd *par, const vd *bnd) {
   st->cput(CK_Ri_thr, 0.25 * (par[WTP_V] * par[WTP_V]));
   c.v_ok = par[WTP_V] > 1e-6;
   c.strat = par[WTP_STRAT] != 0.0;
-  st->cput(CK_QV, wt_div(bnd[WTB_INLET_FLOW] / 60.0, par[WTP_VOLUME]));
+  const vd QV = wt_div(bnd[WTB_INLET_FLOW] / 60.0, par[WTP_VOLUME]);
+  st->cput(CK_QV, QV);
   st->cput(CK_Hin, vexp10(-bnd[WTB_INLET_PH]));
-  c.acid_on = bnd[WTB_ACID_FLOW] > 0.0;
-  st->cput(CK_dHd, wt_div((bnd[WTB_ACID_FLOW] / 60.0) * bnd[WTB_ACID_CONC], par[WTP_VZL]));
-  c.cl_on = bnd[WTB_CL_FLOW] > 0.0;
-  st->cput(CK_cl_dose, wt_div((bnd[WTB_CL_FLOW] / 60.0) * bnd[WTB_CL_CONC], par[WTP_VZL]));
+  const vd dHd = sel(bnd[WTB_ACID_FLOW] > 0.0, wt_div((bnd[WTB_ACID_FLOW] / 60.0) * bnd[WTB_ACID_CONC], par[WTP_VZL]), 0.0);
+  st->cput(CK_dHd, dHd);
+  const vd dose = sel(bnd[WTB_CL_FLOW] > 0.0, wt_div((bnd[WTB_CL_FLOW] / 60.0) * bnd[WTB_CL_CONC], par[WTP_VZL]), 0.0);
+  st->cput(CK_cl_dose, dose);
   st->cput(CK_inCl, bnd[WTB_INLET_CL]);
   st->cput(CK_inT, bnd[WTB_INLET_T]);
-  c.hl_on = bnd[WTB_HEAT_LOSS] > 0.0;
-  st->cput(CK_hlA, bnd[WTB_HEAT_LOSS] * par[WTP_AT]);
+  st->cput(CK_hlA, sel(bnd[WTB_HEAT_LOSS] > 0.0, bnd[WTB_HEAT_LOSS] * par[WTP_AT], 0.0));  // reactor.py:426: only if > 0
+  const vb all = vbroadcast_b(true);
+  st->put(lk0 + LK_KX_UP, sel(g.last, 0.0, par[WTP_KX]), all);
+  st->put(lk0 + LK_KX_DN, sel(g.first, 0.0, par[WTP_KX]), all);
+  st->put(lk0 + LK_QV_FIRST, sel(g.first, QV, 0.0), all);
+  st->put(lk0 + LK_QV_LAST, sel(g.last, QV, 0.0), all);
+  st->put(lk0 + LK_DHD_FIRST, sel(g.first, dHd, 0.0), all);
+  st->put(lk0 + LK_DOSE_FIRST, sel(g.first, dose, 0.0), all);
   st->cput(CK_amb, bnd[WTB_AMBIENT_T]);
   st->cput(CK_inv_hl_den, wt_rcp((998.2 * 4184.0) * (par[WTP_VOLUME] / 1000.0)));
   st->csync();
@@ -283,10 +324,9 @@ struct WtMix { vd off_dn, off_up, diag; };
 template <class Store>
 WT_DEV WtMix wt_mix_row(const WtGroup &g, const WtConstT<Store> &c, vd s_dn, vd s_up) {
   WtMix m;
-  m.off_up = sel(g.last, 0.0, c.Kx() * s_up);
-  m.off_dn = sel(g.first, 0.0, c.Kx() * s_dn);
-  vd d = -(m.off_dn + m.off_up);
-  m.diag = sel(g.last, d - c.QV(), d);
+  m.off_up = c.lk(LK_KX_UP) * s_up;
+  m.off_dn = c.lk(LK_KX_DN) * s_dn;
+  m.diag = -(m.off_dn + m.off_up) - c.lk(LK_QV_LAST);
   return m;
 }
 WT_DEV vd wt_mix(const WtMix &m, vd xdn, vd x, vd xup) { return (m.off_dn * xdn + m.diag * x) + m.off_up * xup; }
@@ -294,29 +334,28 @@ WT_DEV vd wt_mix(const WtMix &m, vd xdn, vd x, vd xup) { return (m.off_dn * xdn 
 // reactor.py:349-368: the zone-0-only acid dosing + inlet terms of dpH (0 elsewhere)
 // (ibl = 1 / (beta ln10): the up-to-three quotients of zone 0 share one reciprocal)
 template <class Store>
+// The reference guards each of the three terms with the same `beta > 0`; the guard is applied once,
+// to the sum, in wt_dph.
 WT_DEV vd wt_dph_inlet(const WtGroup &g, const WtConstT<Store> &c, vd H, vd ibl, vb bpos) {
-  vd t1 = sel(g.first & c.acid_on & bpos, -c.dHd() * ibl, 0.0);
-  vd dHin = c.QV() * (c.Hin() - H);
-  vd t2 = sel(g.first & bpos, -dHin * ibl, 0.0);
+  vd t1 = -c.lk(LK_DHD_FIRST) * ibl;
+  vd dHin = c.lk(LK_QV_FIRST) * (c.Hin() - H);
+  vd t2 = -dHin * ibl;
   return (0.0 + t1) + t2;
 }
 // reactor.py:371-376
-WT_DEV vd wt_dph(vd t12, vd mixH, vd ibl, vb bpos) { return t12 + sel(bpos, -mixH * ibl, 0.0); }
+WT_DEV vd wt_dph(vd t12, vd mixH, vd ibl, vb bpos) { return sel(bpos, t12 + (-mixH * ibl), 0.0); }
 // reactor.py:388-411
 template <class Store>
 WT_DEV vd wt_dcl(const WtGroup &g, const WtConstT<Store> &c, vd Cl, vd mixCl, vd kf) {
-  vd r = sel(g.first & c.cl_on, c.cl_dose(), 0.0);
-  r = r + sel(g.first, c.QV() * (c.inCl() - Cl), 0.0);
+  vd r = c.lk(LK_DOSE_FIRST) + c.lk(LK_QV_FIRST) * (c.inCl() - Cl);
   r = r + mixCl;
   return r - kf * Cl;
 }
 // reactor.py:420-443
 template <class Store>
 WT_DEV vd wt_dt(const WtGroup &g, const WtConstT<Store> &c, vd T, vd mixT) {
-  vd r = sel(g.first, c.QV() * (c.inT() - T), 0.0);
-  r = r + mixT;
-  vd loss = (c.hlA() * (T - c.amb())) * c.inv_hl_den();
-  return sel(c.hl_on, r - loss, r);
+  vd r = c.lk(LK_QV_FIRST) * (c.inT() - T) + mixT;
+  return r - (c.hlA() * (T - c.amb())) * c.inv_hl_den();  // hlA = 0 when the coefficient is not > 0
 }
 
 // Full RHS for this lane's zone.  `bad` is set where the reference would raise ValueError.
@@ -330,11 +369,11 @@ WT_DEV void wt_rhs(const WtGroup &g, const WtConstT<Store> &c, vd pH, vd Cl, vd 
   vd H = vexp10(-pH);
   vb bpos;
   vd ibl = wt_rcp(wt_beta_ln10(c, H, bpos));
-  vd mixH = wt_mix(m, wt_dn(g, H, 0.0), H, wt_up(g, H, 0.0));
+  vd mixH = wt_mix(m, wt_dnc(g, H), H, wt_upc(g, H));
   dpH = wt_dph(wt_dph_inlet(g, c, H, ibl, bpos), mixH, ibl, bpos);
   vd kf = wt_arrhenius(T) * wt_decay_factor(c, H);
-  dCl = wt_dcl(g, c, Cl, wt_mix(m, wt_dn(g, Cl, 0.0), Cl, wt_up(g, Cl, 0.0)), kf);
-  dT = wt_dt(g, c, T, wt_mix(m, wt_dn(g, T, 0.0), T, wt_up(g, T, 0.0)));
+  dCl = wt_dcl(g, c, Cl, wt_mix(m, wt_dnc(g, Cl), Cl, wt_upc(g, Cl)), kf);
+  dT = wt_dt(g, c, T, wt_mix(m, wt_dnc(g, T), T, wt_upc(g, T)));
   bad = wt_t_out_of_range(T);
 }
 
@@ -353,6 +392,7 @@ WT_DEV int wt_pcr_levels(int n) { int L = 0; for (int s = 1; s < n; s <<= 1) ++L
 template <class LuStore>
 WT_DEV void wt_pcr_factor_real(const WtGroup &g, LuStore &lu, int slot0, vd a, vd b, vd c, vb mask) {
   int l = 0;
+  WT_NOUNROLL
   for (int s = 1; s < g.n; s <<= 1, ++l) {
     const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
     vd r = wt_rcp(b);
@@ -371,6 +411,7 @@ WT_DEV void wt_pcr_factor_real(const WtGroup &g, LuStore &lu, int slot0, vd a, v
 template <class LuStore>
 WT_DEV vd wt_pcr_solve_real(const WtGroup &g, LuStore &lu, int slot0, vd d) {
   int l = 0;
+  WT_NOUNROLL
   for (int s = 1; s < g.n; s <<= 1, ++l)
     d = d - shfl_idx(d, wt_src_dn(g, s)) * lu.get(slot0 + 2 * l) - shfl_idx(d, wt_src_up(g, s)) * lu.get(slot0 + 2 * l + 1);
   return d * lu.get(slot0 + 2 * l);
@@ -382,6 +423,7 @@ WT_DEV void wt_pcr_factor_cplx(const WtGroup &g, LuStore &lu, int slot0, vd ar, 
                                vb mask) {
   vd ai = vbroadcast(0.0), ci = vbroadcast(0.0);
   int l = 0;
+  WT_NOUNROLL
   for (int s = 1; s < g.n; s <<= 1, ++l) {
     const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
     vd iden = wt_rcp(br * br + bi * bi);
@@ -410,6 +452,7 @@ WT_DEV void wt_pcr_factor_cplx(const WtGroup &g, LuStore &lu, int slot0, vd ar, 
 template <class LuStore>
 WT_DEV void wt_pcr_solve_cplx(const WtGroup &g, LuStore &lu, int slot0, vd &dr, vd &di) {
   int l = 0;
+  WT_NOUNROLL
   for (int s = 1; s < g.n; s <<= 1, ++l) {
     const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
     vd k1r = lu.get(slot0 + 4 * l + 0), k1i = lu.get(slot0 + 4 * l + 1);
@@ -483,6 +526,7 @@ struct WtPlantStep {
     }
     br[0] = gr - J.tt[1]; br[1] = gr - J.pp[1]; br[2] = gr - J.cc[1];
     int l = 0;
+    WT_NOUNROLL
     for (int s = 1; s < g.n; s <<= 1, ++l) {
       const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
       WT_UNROLL
@@ -535,7 +579,7 @@ struct WtPlantStep {
   // (mu/h I - J) x = b, b and x indexed [0 pH, 1 Cl, 2 T]
   WT_DEV void solve_real(vd *b) {
     vd xT = wt_pcr_solve_real(g, *lu, slot_real(0), b[2]);
-    vd xTd = wt_dn(g, xT, 0.0), xTu = wt_up(g, xT, 0.0);
+    vd xTd = wt_dnc(g, xT), xTu = wt_upc(g, xT);
     vd xp = wt_pcr_solve_real(g, *lu, slot_real(1), b[0] + tri_mv(J.pt, xTd, xT, xTu));
     vd xc = wt_pcr_solve_real(g, *lu, slot_real(2), b[1] + tri_mv(J.ct, xTd, xT, xTu) + J.cp * xp);
     b[0] = xp; b[1] = xc; b[2] = xT;
@@ -544,6 +588,7 @@ struct WtPlantStep {
   WT_DEV void solve_sys3(int q, vd &d, vd &dr, vd &di) {
     const int sr = slot_real(q), sc = slot_cplx(q);
     int l = 0;
+    WT_NOUNROLL
     for (int s = 1; s < g.n; s <<= 1, ++l) {
       const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
       vd k1 = lu->get(sr + 2 * l), k2 = lu->get(sr + 2 * l + 1);
@@ -567,8 +612,8 @@ struct WtPlantStep {
   WT_DEV void solve_newton(vd *b, vd *br, vd *bi) {
     vd xT = b[2], tr = br[2], ti = bi[2];
     solve_sys3(0, xT, tr, ti);
-    vd xTd = wt_dn(g, xT, 0.0), xTu = wt_up(g, xT, 0.0);
-    vd trd = wt_dn(g, tr, 0.0), tru = wt_up(g, tr, 0.0), tid = wt_dn(g, ti, 0.0), tiu = wt_up(g, ti, 0.0);
+    vd xTd = wt_dnc(g, xT), xTu = wt_upc(g, xT);
+    vd trd = wt_dnc(g, tr), tru = wt_upc(g, tr), tid = wt_dnc(g, ti), tiu = wt_upc(g, ti);
     vd xp = b[0] + tri_mv(J.pt, xTd, xT, xTu);
     vd pr = br[0] + tri_mv(J.pt, trd, tr, tru), pi = bi[0] + tri_mv(J.pt, tid, ti, tiu);
     solve_sys3(1, xp, pr, pi);
@@ -612,9 +657,9 @@ struct WtPlantStep {
     vd t12 = wt_dph_inlet(g, c, H, bl, bpos);
     vd kk = wt_arrhenius(T);
     vd kf = kk * wt_decay_factor(c, H);
-    vd Hdn = wt_dn(g, H, 0.0), Hup = wt_up(g, H, 0.0);
-    vd Cldn = wt_dn(g, Cl, 0.0), Clup = wt_up(g, Cl, 0.0);
-    vd Tdn = wt_dn(g, T, 0.0), Tup = wt_up(g, T, 0.0);
+    vd Hdn = wt_dnc(g, H), Hup = wt_upc(g, H);
+    vd Cldn = wt_dnc(g, Cl), Clup = wt_upc(g, Cl);
+    vd Tdn = wt_dnc(g, T), Tup = wt_upc(g, T);
     vd mixCl = wt_mix(mx, Cldn, Cl, Clup);
     // base f of the neighbours (rows of the column's stencil) and of row 0
     vd fdn[3], fup[3];
@@ -677,12 +722,12 @@ struct WtPlantStep {
       // pH columns
       n_pp[1] = wt_dph(wt_dph_inlet(g, c, Hp, blp, bposp), wt_mix(mx, Hdn, Hp, Hup), blp, bposp);
       n_cp = wt_dcl(g, c, Cl, mixCl, kfp_pH);
-      n_pp[0] = wt_dph(t12, wt_mix(mx, wt_dn(g, Hp, 0.0), H, Hup), bl, bpos);
-      n_pp[2] = wt_dph(t12, wt_mix(mx, Hdn, H, wt_up(g, Hp, 0.0)), bl, bpos);
+      n_pp[0] = wt_dph(t12, wt_mix(mx, wt_dnc(g, Hp), H, Hup), bl, bpos);
+      n_pp[2] = wt_dph(t12, wt_mix(mx, Hdn, H, wt_upc(g, Hp)), bl, bpos);
       // Cl columns
       n_cc[1] = wt_dcl(g, c, Clp, wt_mix(mx, Cldn, Clp, Clup), kf);
-      n_cc[0] = wt_dcl(g, c, Cl, wt_mix(mx, wt_dn(g, Clp, 0.0), Cl, Clup), kf);
-      n_cc[2] = wt_dcl(g, c, Cl, wt_mix(mx, Cldn, Cl, wt_up(g, Clp, 0.0)), kf);
+      n_cc[0] = wt_dcl(g, c, Cl, wt_mix(mx, wt_dnc(g, Clp), Cl, Clup), kf);
+      n_cc[2] = wt_dcl(g, c, Cl, wt_mix(mx, Cldn, Cl, wt_upc(g, Clp)), kf);
       // T columns: the perturbed density can flip the Richardson switch of either interface
       {
         WtMix mo = wt_mix_row(g, c, wt_suppression(c, rho_dn, rhop), wt_suppression(c, rhop, rho_up));
@@ -692,11 +737,11 @@ struct WtPlantStep {
         WtMix ml = wt_mix_row(g, c, wt_suppression(c, shfl_up(rhop, 1), rho), s_up);
         n_pt[0] = wt_dph(t12, wt_mix(ml, Hdn, H, Hup), bl, bpos);
         n_ct[0] = wt_dcl(g, c, Cl, wt_mix(ml, Cldn, Cl, Clup), kf);
-        n_tt[0] = wt_dt(g, c, T, wt_mix(ml, wt_dn(g, Tp, 0.0), T, Tup));
+        n_tt[0] = wt_dt(g, c, T, wt_mix(ml, wt_dnc(g, Tp), T, Tup));
         WtMix mr = wt_mix_row(g, c, s_dn, wt_suppression(c, rho, shfl_down(rhop, 1)));
         n_pt[2] = wt_dph(t12, wt_mix(mr, Hdn, H, Hup), bl, bpos);
         n_ct[2] = wt_dcl(g, c, Cl, wt_mix(mr, Cldn, Cl, Clup), kf);
-        n_tt[2] = wt_dt(g, c, T, wt_mix(mr, Tdn, T, wt_up(g, Tp, 0.0)));
+        n_tt[2] = wt_dt(g, c, T, wt_mix(mr, Tdn, T, wt_upc(g, Tp)));
       }
 
       // ---- column owner: arg-max row in species-major order (np.argmax: first maximum)
@@ -905,7 +950,7 @@ struct WtPlantStep {
     vd min_step = vbroadcast(0.0);
 
     vi attempts = vbroadcast_i(0);
-    while (vany(running)) {
+    while (wt_cta_any(vany(running))) {
       // (1) Jacobian: first one, stale-J refresh (radau.py:467-473) or post-accept refresh (:519-521)
       {
         vb m = running & need_jac;
@@ -919,7 +964,9 @@ struct WtPlantStep {
       }
       // base.py:204-208: finished once t reached t_bound
       running = running & !(t == t_bound);
+#ifndef WT_CTA_LOCKSTEP
       if (!vany(running)) break;
+#endif
 
       // (2) _step_impl entry (radau.py:413-428)
       {
@@ -993,6 +1040,7 @@ struct WtPlantStep {
       vd dW_norm_old = vbroadcast(0.0), rate = vbroadcast(0.0);
       vb have_norm_old = vbroadcast_b(false), have_rate = vbroadcast_b(false);
       vi n_iter = vbroadcast_i(0);
+      WT_NOUNROLL
       for (int k = 0; k < WT_NEWTON_MAXITER; ++k) {
         if (!vany(active)) break;
         cnt[WTC_NNEWTON] = cnt[WTC_NNEWTON] + seli(active, 1, 0);
@@ -1008,9 +1056,7 @@ struct WtPlantStep {
           wt_rhs(g, c, y[0] + zrow(i, 0), y[1] + zrow(i, 1), y[2] + zrow(i, 2), F[0], F[1], F[2], bad);
           bad_any = bad_any | bad;
           finite = finite & visfinite(F[0]) & visfinite(F[1]) & visfinite(F[2]);
-          const double tr = i == 0 ? WT_TI00 : (i == 1 ? WT_TI01 : WT_TI02);
-          const double t1 = i == 0 ? WT_TI10 : (i == 1 ? WT_TI11 : WT_TI12);
-          const double t2 = i == 0 ? WT_TI20 : (i == 1 ? WT_TI21 : WT_TI22);
+          const double tr = wt_rk[14 + i], t1 = wt_rk[17 + i], t2 = wt_rk[20 + i];
           WT_UNROLL
           for (int v = 0; v < 3; ++v) {
             fr[v] = fr[v] + F[v] * tr;
@@ -1047,6 +1093,7 @@ struct WtPlantStep {
         have_rate = have_rate | (active & have_norm_old);
         // rate ** (NEWTON_MAXITER - k)
         vd rp = rate;
+        WT_NOUNROLL
         for (int e = 1; e < WT_NEWTON_MAXITER - k; ++e) rp = rp * rate;
         const vd i1r = wt_rcp(1.0 - rate);
         vb brk = active & have_rate & ((rate >= 1.0) | (rp * i1r * dW_norm > WT_NEWTON_TOL));

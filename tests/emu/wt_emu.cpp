@@ -47,7 +47,7 @@ void wt_emu_step_batch(int P, int n, int nsteps, double dt, const double *par, c
         t0.v[l] = t[pp];
         for (int v = 0; v < 3; ++v) yin[v].v[l] = y[(size_t)pp * 3 * n + v * n + z];
       }
-      ps.c = wt_make_const(&lu, vpar, vbnd);
+      ps.c = wt_make_const(&lu, ps.g, 110, vpar, vbnd);
       for (int v = 0; v < 3; ++v) ps.y[v] = yin[v];
       ps.integrate(t0, vdt, on, max_attempts);
       vd der[3];
@@ -87,7 +87,7 @@ void wt_emu_rhs(const double *par, const double *bnd, int n, const double *y, do
     for (int v = 0; v < 3; ++v) yy[v].v[l] = y[v * n + z];
   }
   static EmuLu st;
-  WtConstT<EmuLu> c = wt_make_const(&st, vpar, vbnd);
+  WtConstT<EmuLu> c = wt_make_const(&st, g, 110, vpar, vbnd);
   vb bad;
   wt_rhs(g, c, yy[0], yy[1], yy[2], d[0], d[1], d[2], bad);
   int b = 0;
