@@ -145,11 +145,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--plants", type=int, default=TOTAL_PLANTS)
-    ap.add_argument("--max-attempts", type=int, default=256)
+    ap.add_argument("--max-attempts", type=int, default=64)
     ap.add_argument("--cpu-plants", type=int, default=16384)
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused", action="store_true", help="time one fused wt_advance(K) launch instead of K launches")
+    ap.add_argument("--sort-every", type=int, default=2, help="re-order plants by last-step work every k launches (scheduling only)")
     ap.add_argument("--no-sensors", action="store_true", help="physics only (BASELINE configs[1]-style step)")
     args = ap.parse_args()
 
@@ -178,7 +179,7 @@ def main():
     full = ensembles.config5(P_total, N_ZONES)
     e = full.slice(slice(lo, hi))
     P = e.n_plants
-    eng = PlantEnsemble(e, device=dev, max_attempts=args.max_attempts)
+    eng = PlantEnsemble(e, device=dev, max_attempts=args.max_attempts, sort_every=args.sort_every)
     bnd_dev = torch.from_numpy(np.ascontiguousarray(e.bnd.T)).to(dev)  # SoA, resident: no per-step H2D
     fp64_peak = _lib.measure_fp64_peak() if rank == 0 else 0.0
 
@@ -281,7 +282,7 @@ def main():
                         f"IntegratedCSTR.step(dt=1s) + 7-sensor suite read per plant per step, sharded over {world} GPU(s)",
             "launch_mode": "fused wt_advance(K)" if args.fused else "one wt_step launch per step",
             "l2": "state+params per GPU >> 126 MB L2 at N<=4; inputs larger than L2 (no flush needed)",
-            "sensor_suite": suite is not None,
+            "sensor_suite": suite is not None, "sort_every": args.sort_every,
             "max_attempts": args.max_attempts, "plants_halted_at_end_rank0": halted_after,
             "stats_allreduce_every": 10,
         },

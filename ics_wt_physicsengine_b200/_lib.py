@@ -60,7 +60,7 @@ def lib() -> C.CDLL:
     L.wt_step.argtypes = [C.c_int, C.c_int, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, up, ip, C.c_int, vp]
     L.wt_step.restype = C.c_int
     L.wt_advance.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, up, ip,
-                             C.c_int, vp]
+                             C.c_int, ip, ip, vp]
     L.wt_advance.restype = C.c_int
     L.wt_derivatives.argtypes = [C.c_int, C.c_int, dp, dp, C.c_int, dp, dp, ip, vp]
     L.wt_derivatives.restype = C.c_int

@@ -60,6 +60,8 @@ struct StepArgs {
   double *time, *y, *flow, *derived;
   uint32_t *status;
   int32_t *counters;
+  const int32_t *order;  // optional: slot -> plant (e.g. plants sorted by the cost of their last step)
+  int32_t *cost;         // optional: per-plant work of this launch (collocation solves + Newton iterations)
 };
 
 #ifndef WT_STEP_WARPS
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
   const int gi = lane / n;
   const long long pl = wg * gpw + gi;
   const bool in_plant = gi < gpw && pl < a.P;
-  const int p = in_plant ? (int)pl : 0;
+  const int p = in_plant ? (a.order ? a.order[pl] : (int)pl) : 0;
   const int z = in_plant ? lane - gi * n : 0;
   const size_t P = (size_t)a.P;
 
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
 #pragma unroll
         for (int k = 0; k < WTC_NCNT; ++k) a.counters[(size_t)k * P + p] += acc[k];
       }
+      if (a.cost) a.cost[p] = acc[WTC_NSTEPS] + acc[WTC_NREJECT] + acc[WTC_NNEWTON_FAIL] + acc[WTC_NNEWTON];
     }
   }
 }
@@ -359,7 +362,7 @@ static int launch_step(StepArgs a, cudaStream_t s) {
 
 int wt_advance(int P, int n, int n_steps, double dt, const double *par, const double *bnd, int bnd_stride,
                double *time, double *y, double *flow, double *derived, uint32_t *status, int32_t *counters,
-               int max_attempts, void *stream) {
+               int max_attempts, const int32_t *order, int32_t *cost, void *stream) {
   int rc = check_common(P, n);
   if (rc) return rc;
   if (!(dt > 0.0)) return set_err(WT_ERR_BAD_ARG, "dt must be positive");
@@ -369,14 +372,15 @@ int wt_advance(int P, int n, int n_steps, double dt, const double *par, const do
   StepArgs a;
   a.P = P; a.n = n; a.n_steps = n_steps; a.bnd_stride = bnd_stride; a.max_attempts = max_attempts;
   a.dt = dt; a.par = par; a.bnd = bnd; a.time = time; a.y = y; a.flow = flow; a.derived = derived;
-  a.status = status; a.counters = counters;
+  a.status = status; a.counters = counters; a.order = order; a.cost = cost;
   return launch_step(a, (cudaStream_t)stream);
 }
 
 int wt_step(int P, int n, double dt, const double *par, const double *bnd, int bnd_stride, double *time,
             double *y, double *flow, double *derived, uint32_t *status, int32_t *counters, int max_attempts,
             void *stream) {
-  return wt_advance(P, n, 1, dt, par, bnd, bnd_stride, time, y, flow, derived, status, counters, max_attempts, stream);
+  return wt_advance(P, n, 1, dt, par, bnd, bnd_stride, time, y, flow, derived, status, counters, max_attempts, nullptr,
+                    nullptr, stream);
 }
 
 int wt_derivatives(int P, int n, const double *par, const double *bnd, int bnd_stride, const double *y,

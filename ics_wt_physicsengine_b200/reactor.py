@@ -170,11 +170,11 @@ class PlantEnsemble:
     "straggler policy"); 0 means unlimited, which is the reference's behaviour.
     """
 
-    DEFAULT_MAX_ATTEMPTS = 256
+    DEFAULT_MAX_ATTEMPTS = 64
 
     def __init__(self, cfg: Union[np.ndarray, Sequence[ReactorConfiguration], Ensemble], n_zones: Optional[int] = None,
                  device: Union[str, torch.device, None] = None, max_attempts: int = DEFAULT_MAX_ATTEMPTS,
-                 validate: bool = True):
+                 validate: bool = True, sort_every: int = 0):
         _lib.require_device()
         init = None
         if isinstance(cfg, Ensemble):
@@ -195,6 +195,10 @@ class PlantEnsemble:
         self.n_plants = int(cfg.shape[0])
         self.cfg = cfg
         self.max_attempts = int(max_attempts)
+        # scheduling only (results do not depend on it): every `sort_every` launches the plants are
+        # re-ordered by the work of their last step, most expensive first (0 = natural order)
+        self.sort_every = int(sort_every)
+        self._launches = 0
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         P, n = self.n_plants, self.n_zones
         par = derive_params(cfg, n)
@@ -209,6 +213,8 @@ class PlantEnsemble:
             self._counters = torch.zeros((_lib.NCNT, P), dtype=torch.int32, device=self.device)
             self._bnd_bcast = torch.zeros(NBND, dtype=torch.float64, device=self.device)
             self._bnd_batch = None
+            self._order = None
+            self._cost = torch.zeros(P, dtype=torch.int32, device=self.device) if self.sort_every > 0 else None
         self.state = EnsembleState(self._y, self._derived, self._time, self._flow)
         if init is not None:
             self.set_state(init.pH0, init.Cl0, init.T0)
@@ -288,12 +294,15 @@ class PlantEnsemble:
         """``n_steps`` consecutive ``step(dt, boundary)`` calls fused into one kernel launch."""
         bnd, stride = self._boundary(boundary)
         with torch.cuda.device(self.device):
+            if self.sort_every > 0 and self._launches > 0 and self._launches % self.sort_every == 0:
+                self._order = torch.argsort(self._cost, descending=True).to(torch.int32)
             stream = torch.cuda.current_stream().cuda_stream
             rc = _lib.lib().wt_advance(self.n_plants, self.n_zones, int(n_steps), float(dt), _ptr(self._par),
                                        _ptr(bnd), stride, _ptr(self._time), _ptr(self._y), _ptr(self._flow),
                                        _ptr(self._derived), _ptr(self._status), _ptr(self._counters),
-                                       self.max_attempts, C.c_void_p(stream))
+                                       self.max_attempts, _ptr(self._order), _ptr(self._cost), C.c_void_p(stream))
         _lib.check(rc, "wt_advance")
+        self._launches += 1
         return self.state
 
     def derivatives(self, boundary: BoundaryLike, y: Optional[torch.Tensor] = None):

@@ -94,11 +94,18 @@ int wt_step(int P, int n_zones, double dt, const double *par_dev, const double *
 
 /* Same, `n_steps` consecutive step(dt) calls fused in one launch (state stays in registers
  * between steps; plants are independent so no grid-wide synchronisation is needed).
- * Equivalent to calling wt_step n_steps times with unchanged boundary conditions. */
+ * Equivalent to calling wt_step n_steps times with unchanged boundary conditions.
+ *   order_dev  optional int32 [P]: permutation slot -> plant.  Results do not depend on it (plants
+ *              are independent); it only decides which plants share a warp and which start first,
+ *              e.g. plants sorted by the cost of their previous step (stragglers first, similar
+ *              solver paths together).  NULL = identity.
+ *   cost_dev   optional int32 [P]: work of this launch per plant (collocation solves + Newton
+ *              iterations), the sort key for the next launch. */
 int wt_advance(int P, int n_zones, int n_steps, double dt, const double *par_dev,
                const double *bnd_dev, int bnd_stride, double *time_dev, double *y_dev,
                double *flow_rate_dev, double *derived_dev, uint32_t *status_dev,
-               int32_t *counters_dev, int max_attempts, void *stream);
+               int32_t *counters_dev, int max_attempts, const int32_t *order_dev,
+               int32_t *cost_dev, void *stream);
 
 /* IntegratedCSTR.derivatives(t, y, boundary) for P plants (reactor.py:272-448).
  * dy has the layout of y; bad[p] != 0 where the reference would raise ValueError. */

@@ -8,7 +8,7 @@ import pytest
 from ics_wt_physicsengine_b200 import ensembles as ens
 from tests._util import HALT, check_step_parity, relerr, species_major
 
-CAP = 256
+CAP = 64
 
 
 def _run(oracle, emu, e, steps, dt=1.0, cap=CAP):

@@ -19,10 +19,11 @@ ap.add_argument("--zones", type=int, default=10)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--config", default="config5")
-ap.add_argument("--max-attempts", type=int, default=256)
+ap.add_argument("--max-attempts", type=int, default=64)
+ap.add_argument("--sort-every", type=int, default=0)
 a = ap.parse_args()
 e = getattr(ensembles, a.config)(a.plants, a.zones)
-eng = PlantEnsemble(e, max_attempts=a.max_attempts)
+eng = PlantEnsemble(e, max_attempts=a.max_attempts, sort_every=a.sort_every)
 bnd = torch.from_numpy(np.ascontiguousarray(e.bnd.T)).to(eng.device)
 for _ in range(a.warmup):
     eng.step(1.0, bnd)
