@@ -47,35 +47,47 @@ def bytes_alg(n_plant_steps: float, n_zones: int) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md): one streaming
+    nvidia-smi process (-lms 100), started before and killed after the region."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.stop = index, [], threading.Event()
-        self.th = threading.Thread(target=self._run, daemon=True)
+        self.index, self.rows, self.proc, self.th = index, [], None, None
 
-    def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
+    def _pump(self):
+        try:
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.strip().split(",")]
                 if len(f) >= 7:
                     self.rows.append(f)
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+        except Exception:
+            pass
 
     def __enter__(self):
-        self.th.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+            time.sleep(0.35)  # let the first sample arrive before the region starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
-        self.th.join(timeout=6)
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except Exception:
+                self.proc.kill()
+            if self.th is not None:
+                self.th.join(timeout=3)
 
     def summary(self):
         if not self.rows:
@@ -85,8 +97,9 @@ class ClockSampler:
         for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
             if any(r[3 + i].lower().startswith("active") for r in self.rows):
                 reasons.append(name)
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "", 1).isdigit()]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "power_w_max": max(pw) if pw else None}
 
 
 def run_reference(args, rank, world):
@@ -248,6 +261,21 @@ def main():
     halted_after = P - int(((eng.status & _lib.ST_HALT_MASK) == 0).sum())
     value = timed_plant_steps * N_ZONES / (ms * 1e-3)
 
+    # ---- e2e: the C-ABI host-buffer call (H2D + step + D2H inside the timed region) on EVERY rank's
+    # shard at the same time; whole-job value = all plants / slowest rank
+    if world > 1:
+        dist.barrier()
+    live_e2e, el_e2e, k_e2e, h2d, d2h = e2e_measure(e, eng, args)
+    e2e_agg = torch.tensor([float(live_e2e), el_e2e, float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+    e2e_max = e2e_agg.clone()
+    if world > 1:
+        dist.all_reduce(e2e_agg)
+        dist.all_reduce(e2e_max, op=dist.ReduceOp.MAX)
+    e2e = {"value": float(e2e_agg[0]) * N_ZONES * k_e2e / float(e2e_max[1]), "unit": UNIT,
+           "h2d_bytes_per_step": int(e2e_agg[2]), "d2h_bytes_per_step": int(e2e_agg[3]), "steps": k_e2e,
+           "api": "wt_step_host (C ABI, pinned host buffers: H2D of state+boundary, step, D2H of state+time+flow+status per call; "
+                  "per-plant constants resident after the first call)", "n_gpus": world}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -266,11 +294,10 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_ach = bytes_alg(timed_plant_steps, N_ZONES) / world / (step_ms * 1e-3) / 1e9
 
-    # ---- e2e: the C-ABI host-buffer call (H2D + kernel + D2H inside the timed region), N=1 shard
-    e2e = e2e_measure(e, eng, args)
+    pass
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # rank 0 at N=1 only
         cpu = cpu_baseline(args)
 
     line = {
@@ -312,9 +339,9 @@ def main():
 
 
 def e2e_measure(e, eng, args):
-    """Same metric through the C-ABI host-buffer entry point wt_step_host: state, boundary and
-    parameters start in pinned HOST memory every step; the call copies them in, steps, and copies
-    state + status back."""
+    """Same metric through the C-ABI host-buffer entry point wt_step_host: state and boundary start in
+    pinned HOST memory every step; the call copies them in, steps, and copies state, time, flow and
+    status back.  Returns (live plants, seconds, steps, h2d bytes/step, d2h bytes/step) of this shard."""
     import ctypes as C
 
     import torch
@@ -332,18 +359,17 @@ def e2e_measure(e, eng, args):
     p = lambda x: C.c_void_p(x.data_ptr())
     L = _lib.lib()
     k = max(3, min(args.steps, 10))
-    for _ in range(2):
-        _lib.check(L.wt_step_host(P, n, DT, p(par), p(bnd), P, p(t), p(y), p(flow), p(st), args.max_attempts), "wt_step_host")
+    for i in range(3):
+        _lib.check(L.wt_step_host(P, n, DT, p(par), p(bnd), P, p(t), p(y), p(flow), p(st), args.max_attempts, 1 if i else 0),
+                   "wt_step_host")
     t0 = time.perf_counter()
     for _ in range(k):
-        _lib.check(L.wt_step_host(P, n, DT, p(par), p(bnd), P, p(t), p(y), p(flow), p(st), args.max_attempts), "wt_step_host")
+        _lib.check(L.wt_step_host(P, n, DT, p(par), p(bnd), P, p(t), p(y), p(flow), p(st), args.max_attempts, 1), "wt_step_host")
     el = time.perf_counter() - t0
     live = int(((st & _lib.ST_HALT_MASK) == 0).sum())
-    h2d = (12 + 10 + 1 + 3 * n + 1) * P * 8 + P * 4
+    h2d = (10 + 1 + 3 * n + 1) * P * 8 + P * 4
     d2h = (1 + 3 * n + 1) * P * 8 + P * 4
-    return {"value": live * n * k / el, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "steps": k, "api": "wt_step_host (C ABI, pinned host buffers, H2D + step + D2H per call)",
-            "n_gpus": 1, "plants": P}
+    return live, el, k, h2d, d2h
 
 
 def cpu_baseline(args):

@@ -64,7 +64,7 @@ def lib() -> C.CDLL:
     L.wt_advance.restype = C.c_int
     L.wt_derivatives.argtypes = [C.c_int, C.c_int, dp, dp, C.c_int, dp, dp, ip, vp]
     L.wt_derivatives.restype = C.c_int
-    L.wt_step_host.argtypes = [C.c_int, C.c_int, C.c_double, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int]
+    L.wt_step_host.argtypes = [C.c_int, C.c_int, C.c_double, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int]
     L.wt_step_host.restype = C.c_int
     L.wt_calc_ph.argtypes = [C.c_int, dp, dp, dp, dp, dp, ip, ip, vp]
     L.wt_calc_ph.restype = C.c_int

@@ -486,7 +486,7 @@ static struct {
 } g_ws = {0, nullptr};
 
 int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, int bnd_stride, double *time,
-                 double *y, double *flow, uint32_t *status, int max_attempts) {
+                 double *y, double *flow, uint32_t *status, int max_attempts, int flags) {
   int rc = check_common(P, n);
   if (rc) return rc;
   if (!par || !bnd || !time || !y || !status) return set_err(WT_ERR_BAD_ARG, "null host pointer");
@@ -496,6 +496,7 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
                b_y = 3 * (size_t)n * Pz * 8, b_f = Pz * 8, b_s = Pz * 4;
   const size_t total = b_par + b_bnd + b_t + b_y + b_f + b_s + 256 * 6;
   if (total > g_ws.cap_bytes) {
+    flags &= ~1;
     if (g_ws.dev) cudaFree(g_ws.dev);
     g_ws.dev = nullptr;
     g_ws.cap_bytes = 0;
@@ -512,7 +513,10 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
   double *d_f = (double *)q; q += al(b_f);
   uint32_t *d_s = (uint32_t *)q;
   cudaStream_t s = 0;
-  cudaMemcpyAsync(d_par, par, b_par, cudaMemcpyHostToDevice, s);
+  // WT_HOST_PARAMS_RESIDENT: the derived constants uploaded by the previous call (same P, n) are reused
+  static int res_P = 0, res_n = 0;
+  if (!(flags & 1) || res_P != P || res_n != n) cudaMemcpyAsync(d_par, par, b_par, cudaMemcpyHostToDevice, s);
+  res_P = P; res_n = n;
   cudaMemcpyAsync(d_bnd, bnd, b_bnd, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(d_t, time, b_t, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(d_y, y, b_y, cudaMemcpyHostToDevice, s);

@@ -113,12 +113,15 @@ int wt_derivatives(int P, int n_zones, const double *par_dev, const double *bnd_
                    int bnd_stride, const double *y_dev, double *dy_dev, int32_t *bad_dev,
                    void *stream);
 
-/* Host-buffer convenience used for end-to-end timing: copies state / boundary in, runs
- * wt_step, copies state / status back, all on `stream`, and waits for completion.
- * All pointers are HOST pointers with the SoA layouts above; bnd_stride is P or 0. */
+/* Host-buffer entry point (the call a host-only caller makes; used for end-to-end timing): copies
+ * state / boundary (and the constants) in, runs wt_step, copies state / time / flow / status back,
+ * and waits for completion.  All pointers are HOST pointers with the SoA layouts above;
+ * bnd_stride is P or 0.  flags: WT_HOST_PARAMS_RESIDENT = the per-plant constants `par` are
+ * unchanged since the previous call with the same (P, n_zones) and are not uploaded again. */
+#define WT_HOST_PARAMS_RESIDENT 1
 int wt_step_host(int P, int n_zones, double dt, const double *par, const double *bnd,
                  int bnd_stride, double *time, double *y, double *flow_rate, uint32_t *status,
-                 int max_attempts);
+                 int max_attempts, int flags);
 
 /* ---------------------------------------------------------------------------------------
  * AqueousChemistry.calculate_pH(initial_guess) for P buffer systems   (chemistry.py:271-330)
