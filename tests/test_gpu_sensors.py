@@ -149,3 +149,26 @@ def test_calibrate_and_time_semantics():
     r = suite.read(eng.state, 16.0)
     assert (r["flow_main"].status.cpu().numpy() == 2).mean() > 0.9    # WARMING_UP again for 10 s
     assert set(suite.keys()) == set(SENSOR_NAMES)
+
+
+def test_orchestrator_closed_loop_on_device():
+    """step -> sensors -> controller -> clamps -> boundary, no host round trip of the state."""
+    from ics_wt_physicsengine_b200.orchestrator import EnsembleOrchestrator
+    P, n = 4096, 10
+    e = ens.config2(P, n, seed=21)
+    eng = PlantEnsemble(e)
+    suite = create_realistic_sensor_suite(eng, seed=1)
+    bnd = torch.from_numpy(np.ascontiguousarray(e.bnd.T)).to(eng.device)
+    orch = EnsembleOrchestrator(eng, suite, bnd, t0=0.0)
+
+    def controller(readings, state, k):
+        # dose chlorine where the outlet reading (once the sensor is warm) is below 1 mg/L; garbage on purpose elsewhere
+        cl = readings["chlorine_outlet"].value
+        want = torch.where(torch.isnan(cl), torch.full_like(cl, float("nan")), (1.0 - cl) * 5.0)
+        return torch.zeros_like(cl), want, torch.full_like(cl, 25.0)   # inlet command above the 20 L/min clamp
+
+    orch.run(80, 1.0, controller)
+    assert float(bnd[0].max()) == 20.0 and float(bnd[0].min()) == 20.0          # inlet clamped to 20
+    assert float(bnd[6].min()) >= 0.0 and float(bnd[6].max()) <= 1.0            # chlorine dosing in [0, 1]
+    assert not torch.isnan(bnd).any()
+    assert np.all(eng.state.time.cpu().numpy()[(eng.status.cpu().numpy() & 130) == 0] == 80.0)
