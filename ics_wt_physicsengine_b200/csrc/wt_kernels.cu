@@ -9,6 +9,7 @@
 // bound by the FP64 FMA pipe and touches HBM only at entry and exit.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/wt_b200.h"
@@ -349,7 +350,8 @@ static int launch_step(StepArgs a, cudaStream_t s) {
   const int gpw = 32 / a.n;
   const long long warps = ((long long)a.P + gpw - 1) / gpw;
   const long long blocks = (warps + WT_STEP_WARPS - 1) / WT_STEP_WARPS;
-  const size_t smem = (size_t)WT_STEP_WARPS * wt_warp_smem_doubles(a.n) * sizeof(double);
+  size_t smem = (size_t)WT_STEP_WARPS * wt_warp_smem_doubles(a.n) * sizeof(double);
+  if (const char *pad = getenv("WT_B200_SMEM_PAD_KB")) smem += (size_t)atoi(pad) * 1024;  // occupancy experiments only
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(wt_step_kernel<WT_STEP_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
