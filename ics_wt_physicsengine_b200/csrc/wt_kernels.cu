@@ -37,7 +37,12 @@ static int cuda_err(cudaError_t e, const char *where) {
 struct SmemLu {
   double *p;   // &lu_region[lane]; slot stride = 32 doubles
   double *cp;  // constants of this lane's plant (one copy per plant, read as a broadcast)
-  __device__ __forceinline__ void put(int slot, double x, bool mask) { if (mask) p[slot * 32] = x; }
+  // predicated store: an `if (mask)` here becomes a branch around each group of stores, and a branch ends
+  // the basic block ptxas schedules in (the six factorizations of a PCR level then run one after the other)
+  __device__ __forceinline__ void put(int slot, double x, bool mask) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q st.shared.f64 [%0], %1;\n\t}"
+                 :: "r"((unsigned)__cvta_generic_to_shared(p + slot * 32)), "d"(x), "r"((int)mask) : "memory");
+  }
   __device__ __forceinline__ double get(int slot) const { return p[slot * 32]; }
   __device__ __forceinline__ void cput(int k, double x) { cp[k] = x; }
   __device__ __forceinline__ double cget(int k) const { return cp[k]; }
@@ -91,7 +96,19 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
   const int z = in_plant ? lane - gi * n : 0;
   const size_t P = (size_t)a.P;
 
-  uint32_t st_in = in_plant ? a.status[p] : 0u;
+  // Every global load of the launch is issued here, back to back and before the first use: the prologue
+  // then waits for ONE round trip to HBM instead of one per dependent group (status -> params -> state).
+  const uint32_t st_in = a.status[p];
+  double par[WTP_NPAR], bnd[WTB_NBND];
+#pragma unroll
+  for (int k = 0; k < WTP_NPAR; ++k) par[k] = a.par[(size_t)k * P + p];
+#pragma unroll
+  for (int k = 0; k < WTB_NBND; ++k) bnd[k] = a.bnd[a.bnd_stride ? (size_t)k * P + p : (size_t)k];
+  double t = a.time[p];
+  double y0[3];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) y0[v] = a.y[((size_t)v * n + z) * P + p];
+
   bool on = in_plant && !(st_in & WTS_HALT_MASK);
 #ifndef WT_CTA_LOCKSTEP
   if (!__any_sync(0xffffffffu, on)) return;
@@ -104,17 +121,11 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
   WtPlantStep<SmemLu> ps;
   ps.g = wt_make_group(n);
   ps.lu = &lu;
-  {
-    double par[WTP_NPAR], bnd[WTB_NBND];
+  // reactor.py:500: flow_rate = inlet + acid + chlorine flow, parked with the plant's constants until the epilogue
+  lu.cput(CK_flow, bnd[WTB_INLET_FLOW] + bnd[WTB_ACID_FLOW] + bnd[WTB_CL_FLOW]);
+  ps.c = wt_make_const(&lu, ps.g, wt_lu_slots(n), par, bnd);
 #pragma unroll
-    for (int k = 0; k < WTP_NPAR; ++k) par[k] = a.par[(size_t)k * P + p];
-#pragma unroll
-    for (int k = 0; k < WTB_NBND; ++k) bnd[k] = a.bnd[a.bnd_stride ? (size_t)k * P + p : (size_t)k];
-    ps.c = wt_make_const(&lu, ps.g, wt_lu_slots(n), par, bnd);
-  }
-  double t = a.time[p];
-#pragma unroll
-  for (int v = 0; v < 3; ++v) ps.y[v] = a.y[((size_t)v * n + z) * P + p];
+  for (int v = 0; v < 3; ++v) ps.y[v] = y0[v];
 
   int32_t acc[WTC_NCNT];
 #pragma unroll
@@ -150,13 +161,11 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
     if (z == 0) {
       a.time[p] = t;
       a.status[p] = st;
-      if (stepped && a.flow) {
-        const size_t bs = a.bnd_stride ? P : 1, bp = a.bnd_stride ? p : 0;
-        a.flow[p] = a.bnd[WTB_INLET_FLOW * bs + bp] + a.bnd[WTB_ACID_FLOW * bs + bp] + a.bnd[WTB_CL_FLOW * bs + bp];
-      }
+      if (stepped && a.flow) a.flow[p] = lu.cget(CK_flow);
       if (a.counters) {
+        // fire-and-forget reductions: a load-add-store here made the whole warp wait for eight loads
 #pragma unroll
-        for (int k = 0; k < WTC_NCNT; ++k) a.counters[(size_t)k * P + p] += acc[k];
+        for (int k = 0; k < WTC_NCNT; ++k) atomicAdd(&a.counters[(size_t)k * P + p], acc[k]);
       }
       if (a.cost) a.cost[p] = acc[WTC_NSTEPS] + acc[WTC_NREJECT] + acc[WTC_NNEWTON_FAIL] + acc[WTC_NNEWTON];
     }

@@ -48,10 +48,13 @@ enum {
   WTC_JAC_RETRY, WTC_NCNT
 };
 
+// The three stage evaluations of a Newton iteration stay a ROLLED loop: the kernel is bound by instruction
+// fetch (SM instruction-cache hit rate ~80 %, GPC-level cache at 92 % of its request rate), so one copy of the
+// RHS in the hot loop beats three (measured); -DWT_UNROLL_STAGES unrolls for experiments.
 #ifdef WT_UNROLL_STAGES
 #define WT_STAGE_UNROLL WT_UNROLL
 #else
-#define WT_STAGE_UNROLL
+#define WT_STAGE_UNROLL WT_NOUNROLL
 #endif
 #define WT_RTOL 1e-6  // reactor.py:482
 #define WT_ATOL 1e-8  // reactor.py:483
@@ -72,11 +75,12 @@ enum {
     0.50287263494578682, -2.57192694985560522, 0.59603920482822492,              /* 20 TI row 2 */ \
     13.0 / 3.0 + 7.0 * WT_S6 / 3.0, -23.0 / 3.0 - 22.0 * WT_S6 / 3.0, 10.0 / 3.0 + 5.0 * WT_S6,   /* 23 P row 0 */ \
     13.0 / 3.0 - 7.0 * WT_S6 / 3.0, -23.0 / 3.0 + 22.0 * WT_S6 / 3.0, 10.0 / 3.0 - 5.0 * WT_S6,   /* 26 P row 1 */ \
-    1.0 / 3.0, -8.0 / 3.0, 10.0 / 3.0 }                                          /* 29 P row 2 */
+    1.0 / 3.0, -8.0 / 3.0, 10.0 / 3.0,                                           /* 29 P row 2 */ \
+    1.0, 1.0, 0.0 }                                                              /* 32 T row 2 (stage-indexed reads of T: 8 + 3 i for i < 2, 32 for i = 2) */
 #ifdef WT_EMU
-static const double wt_rk[32] = WT_RADAU_TABLE;
+static const double wt_rk[35] = WT_RADAU_TABLE;
 #else
-__constant__ double wt_rk[32] = WT_RADAU_TABLE;
+__constant__ double wt_rk[35] = WT_RADAU_TABLE;
 #endif
 #define WT_C0 wt_rk[0]
 #define WT_C1 wt_rk[1]
@@ -145,9 +149,7 @@ WT_DEV WtGroup wt_make_group(int n) {
   uint32_t full = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
   vi m = vbroadcast_i(0);
   for (int k = 0; k < gpw; ++k) m = seli(in & (q == k), (int)(full << (k * n)), m);
-  vi one = vbroadcast_i(0);
-  for (int k = 0; k < WT_WARP; ++k) one = seli(lane == k, (int)(1u << k), one);
-  g.gmask = seli(in, m, one);
+  g.gmask = seli(in, m, vlanebit());
   g.first = g.z == 0;
   g.last = selb(in, g.z == (n - 1), vbroadcast_b(true));
   g.L = 0;
@@ -192,7 +194,7 @@ WT_DEV vb wt_gany(const WtGroup &g, vb c) { return vmask_any(vballot(c), g.gmask
 // per plant, read as a broadcast) instead of 34 registers per lane; the flags stay in registers.
 enum {
   CK_Kw = 0, CK_Ka1, CK_Ka12, CK_KaCl, CK_CT2303, CK_Kx, CK_zh, CK_Ri_thr, CK_QV, CK_Hin, CK_dHd,
-  CK_cl_dose, CK_inCl, CK_inT, CK_hlA, CK_amb, CK_inv_hl_den, CK_N
+  CK_cl_dose, CK_inCl, CK_inT, CK_hlA, CK_amb, CK_inv_hl_den, CK_flow, CK_N
 };
 // per-LANE constants (zone-position dependent), kept in lane-private slots of the store after the LU
 // multipliers: the "zone 0 only" / "last zone only" terms of reactor.py:336-395 become multiplications
@@ -694,6 +696,7 @@ struct WtPlantStep {
     WT_UNROLL
     for (int v = 0; v < 3; ++v) { retry[v] = vbroadcast_b(false); maxd[v] = vbroadcast(0.0); scl[v] = vbroadcast(0.0); }
 
+    WT_NOUNROLL  // the retry pass is rare: one copy of the column evaluation (instruction-fetch bound kernel)
     for (int pass = 0; pass < 2; ++pass) {
       vd hc[3];
       if (pass == 1) {
@@ -875,10 +878,10 @@ struct WtPlantStep {
   }
 
   // Z_i[var] = sum_k T[i][k] W[k][var]   (radau.py:126)
+  // (table-driven: with the stage loop rolled, an if-chain on i would be a branch inside the loop body)
   WT_DEV vd zrow(int i, int v) const {
-    if (i == 0) return (WT_T00 * W[0][v] + WT_T01 * W[1][v]) + WT_T02 * W[2][v];
-    if (i == 1) return (WT_T10 * W[0][v] + WT_T11 * W[1][v]) + WT_T12 * W[2][v];
-    return (1.0 * W[0][v] + 1.0 * W[1][v]) + 0.0 * W[2][v];
+    const int r = i < 2 ? 8 + 3 * i : 32;
+    return (wt_rk[r] * W[0][v] + wt_rk[r + 1] * W[1][v]) + wt_rk[r + 2] * W[2][v];
   }
 
   // -------------------------------------------------------------------------------------
