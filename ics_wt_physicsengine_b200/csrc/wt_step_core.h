@@ -242,12 +242,12 @@ WT_DEV WtConstT<Store> wt_make_const(Store *st, const WtGroup &g, int lk0, const
   st->cput(CK_Ri_thr, 0.25 * (par[WTP_V] * par[WTP_V]));
   c.v_ok = par[WTP_V] > 1e-6;
   c.strat = par[WTP_STRAT] != 0.0;
-  const vd QV = wt_div(bnd[WTB_INLET_FLOW] / 60.0, par[WTP_VOLUME]);
+  const vd QV = wt_div(wt_div(bnd[WTB_INLET_FLOW], 60.0), par[WTP_VOLUME]);
   st->cput(CK_QV, QV);
   st->cput(CK_Hin, vexp10(-bnd[WTB_INLET_PH]));
-  const vd dHd = sel(bnd[WTB_ACID_FLOW] > 0.0, wt_div((bnd[WTB_ACID_FLOW] / 60.0) * bnd[WTB_ACID_CONC], par[WTP_VZL]), 0.0);
+  const vd dHd = sel(bnd[WTB_ACID_FLOW] > 0.0, wt_div(wt_div(bnd[WTB_ACID_FLOW], 60.0) * bnd[WTB_ACID_CONC], par[WTP_VZL]), 0.0);
   st->cput(CK_dHd, dHd);
-  const vd dose = sel(bnd[WTB_CL_FLOW] > 0.0, wt_div((bnd[WTB_CL_FLOW] / 60.0) * bnd[WTB_CL_CONC], par[WTP_VZL]), 0.0);
+  const vd dose = sel(bnd[WTB_CL_FLOW] > 0.0, wt_div(wt_div(bnd[WTB_CL_FLOW], 60.0) * bnd[WTB_CL_CONC], par[WTP_VZL]), 0.0);
   st->cput(CK_cl_dose, dose);
   st->cput(CK_inCl, bnd[WTB_INLET_CL]);
   st->cput(CK_inT, bnd[WTB_INLET_T]);
@@ -260,7 +260,7 @@ WT_DEV WtConstT<Store> wt_make_const(Store *st, const WtGroup &g, int lk0, const
   st->put(lk0 + LK_DHD_FIRST, sel(g.first, dHd, 0.0), all);
   st->put(lk0 + LK_DOSE_FIRST, sel(g.first, dose, 0.0), all);
   st->cput(CK_amb, bnd[WTB_AMBIENT_T]);
-  st->cput(CK_inv_hl_den, wt_rcp((998.2 * 4184.0) * (par[WTP_VOLUME] / 1000.0)));
+  st->cput(CK_inv_hl_den, wt_rcp((998.2 * 4184.0) * wt_div(par[WTP_VOLUME], 1000.0)));
   st->csync();
   return c;
 }
@@ -919,23 +919,30 @@ struct WtPlantStep {
     // ---- Radau.__init__: f0 and select_initial_step (radau.py:303-311, common.py:68-134)
     vd self_h_abs;
     {
-      vb bad;
-      wt_rhs(g, c, y[0], y[1], y[2], f[0], f[1], f[2], bad);
-      cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(running, 1, 0);
-      trange = trange | (running & wt_gany(g, bad));
-      vd sc[3];  // 1 / scale
+      // f0 = f(y) and f1 = f(y + h0 f0) go through ONE rolled copy of the RHS (instruction-fetch bound kernel)
+      vd sc[3], yy[3], fo[3];  // sc = 1 / scale
+      vd d1 = vbroadcast(0.0), h0 = vbroadcast(0.0);
+      const vd interval = vabs(t_bound - t0);
       WT_UNROLL
-      for (int v = 0; v < 3; ++v) sc[v] = wt_rcp(WT_ATOL + vabs(y[v]) * WT_RTOL);
-      vd d0 = rms3(y[0] * sc[0], y[1] * sc[1], y[2] * sc[2]);
-      vd d1 = rms3(f[0] * sc[0], f[1] * sc[1], f[2] * sc[2]);
-      vd h0 = sel((d0 < 1e-5) | (d1 < 1e-5), 1e-6, wt_div(0.01 * d0, d1));
-      vd interval = vabs(t_bound - t0);
-      h0 = vmin(h0, interval);
-      vd f1[3];
-      wt_rhs(g, c, y[0] + h0 * f[0], y[1] + h0 * f[1], y[2] + h0 * f[2], f1[0], f1[1], f1[2], bad);
-      cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(running, 1, 0);
-      trange = trange | (running & wt_gany(g, bad));
-      vd d2 = wt_div(rms3((f1[0] - f[0]) * sc[0], (f1[1] - f[1]) * sc[1], (f1[2] - f[2]) * sc[2]), h0);
+      for (int v = 0; v < 3; ++v) { yy[v] = y[v]; sc[v] = wt_rcp(WT_ATOL + vabs(y[v]) * WT_RTOL); }
+      WT_NOUNROLL
+      for (int it = 0; it < 2; ++it) {
+        vb bad;
+        wt_rhs(g, c, yy[0], yy[1], yy[2], fo[0], fo[1], fo[2], bad);
+        cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(running, 1, 0);
+        trange = trange | (running & wt_gany(g, bad));
+        if (it == 0) {
+          WT_UNROLL
+          for (int v = 0; v < 3; ++v) f[v] = fo[v];
+          vd d0 = rms3(y[0] * sc[0], y[1] * sc[1], y[2] * sc[2]);
+          d1 = rms3(f[0] * sc[0], f[1] * sc[1], f[2] * sc[2]);
+          h0 = sel((d0 < 1e-5) | (d1 < 1e-5), 1e-6, wt_div(0.01 * d0, d1));
+          h0 = vmin(h0, interval);
+          WT_UNROLL
+          for (int v = 0; v < 3; ++v) yy[v] = y[v] + h0 * f[v];
+        }
+      }
+      vd d2 = wt_div(rms3((fo[0] - f[0]) * sc[0], (fo[1] - f[1]) * sc[1], (fo[2] - f[2]) * sc[2]), h0);
       vd h1 = sel((d1 <= 1e-15) & (d2 <= 1e-15), vmax(h0 * 1e-3, 1e-6), vsqrt(vsqrt(wt_div(0.01, vmax(d1, d2)))));
       self_h_abs = vmin(vmin(100.0 * h0, h1), vmin(interval, max_step));
     }
@@ -1126,85 +1133,102 @@ struct WtPlantStep {
       vb cv = running & converged;
       if (!vany(cv)) continue;
 
-      // (7) error estimate and step control (radau.py:483-512)
+      // (7) error estimate and step control (radau.py:483-512), (8) acceptance (radau.py:514-545).
+      // Three passes through ONE copy of "evaluate the RHS, solve with the real LU, take the scaled norm"
+      // (the kernel is bound by instruction fetch, so the three call sites share their code):
+      //   pass 0  err = solve(f + ZE)                               for the converged plants
+      //   pass 1  err = solve(f(y + err) + ZE)                      only where a rejected step is about to be
+      //                                                             rejected again (radau.py:493-495)
+      //   pass 2  f(y_new) and the bookkeeping of an accepted step  (radau.py:514-545)
       vd Z[3][3], y_new[3], ZE[3], err[3], escale[3];
       WT_UNROLL
       for (int v = 0; v < 3; ++v) {
         Z[0][v] = zrow(0, v); Z[1][v] = zrow(1, v); Z[2][v] = zrow(2, v);
         y_new[v] = y[v] + Z[2][v];
         ZE[v] = ((Z[0][v] * WT_E0 + Z[1][v] * WT_E1) + Z[2][v] * WT_E2) * ih;
-        err[v] = f[v] + ZE[v];
+        err[v] = f[v];
+        escale[v] = wt_rcp(WT_ATOL + vmax(vabs(y[v]), vabs(y_new[v])) * WT_RTOL);
       }
-      solve_real(err);
-      WT_UNROLL
-      for (int v = 0; v < 3; ++v) escale[v] = wt_rcp(WT_ATOL + vmax(vabs(y[v]), vabs(y_new[v])) * WT_RTOL);
-      vd err_norm = rms3(err[0] * escale[0], err[1] * escale[1], err[2] * escale[2]);
-      vd safety = wt_div(vbroadcast(0.9 * (2 * WT_NEWTON_MAXITER + 1)), vfromint(n_iter + 2 * WT_NEWTON_MAXITER));
-      {
-        vb again = cv & rejected & (err_norm > 1.0);
-        if (vany(again)) {  // radau.py:493-495
-          vd fe[3];
+      const vd safety = wt_div(vbroadcast(0.9 * (2 * WT_NEWTON_MAXITER + 1)), vfromint(n_iter + 2 * WT_NEWTON_MAXITER));
+      vd err_norm = vbroadcast(0.0), pf = vbroadcast(0.0);
+      vb again = vbroadcast_b(false), acc = vbroadcast_b(false);
+      WT_NOUNROLL
+      for (int pass = 0; pass < 3; ++pass) {
+        vd F[3];
+        if (pass == 0) {
+          WT_UNROLL
+          for (int v = 0; v < 3; ++v) F[v] = f[v];
+        } else {
+          vb m;
+          vd pnt[3];
+          if (pass == 1) {
+            m = again;
+            WT_UNROLL
+            for (int v = 0; v < 3; ++v) pnt[v] = y[v] + err[v];
+          } else {
+            const vb rej = cv & (err_norm > 1.0);
+            acc = cv & !rej;
+            pf = predict_factor(h_abs, h_abs_old, err_norm, err_old, have_old);
+            h_abs = sel(rej, h_abs * vmax(safety * pf, 0.2), h_abs);
+            lu_valid = lu_valid & !rej;
+            rejected = rejected | rej;
+            cnt[WTC_NREJECT] = cnt[WTC_NREJECT] + seli(rej, 1, 0);
+            m = acc;
+            WT_UNROLL
+            for (int v = 0; v < 3; ++v) pnt[v] = y_new[v];
+          }
+          if (!vany(m)) continue;
           vb bad;
-          wt_rhs(g, c, y[0] + err[0], y[1] + err[1], y[2] + err[2], fe[0], fe[1], fe[2], bad);
-          cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(again, 1, 0);
-          vb tb = again & wt_gany(g, bad);
+          wt_rhs(g, c, pnt[0], pnt[1], pnt[2], F[0], F[1], F[2], bad);
+          cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(m, 1, 0);
+          const vb tb = m & wt_gany(g, bad);
           trange = trange | tb;
           running = running & !tb;
           cv = cv & !tb;
-          vd e2[3];
-          WT_UNROLL
-          for (int v = 0; v < 3; ++v) e2[v] = fe[v] + ZE[v];
-          solve_real(e2);
-          vd en2 = rms3(e2[0] * escale[0], e2[1] * escale[1], e2[2] * escale[2]);
-          err_norm = sel(again, en2, err_norm);
-        }
-      }
-      vb rej = cv & (err_norm > 1.0);
-      vb acc = cv & !rej;
-      vd pf = predict_factor(h_abs, h_abs_old, err_norm, err_old, have_old);
-      {
-        h_abs = sel(rej, h_abs * vmax(safety * pf, 0.2), h_abs);
-        lu_valid = lu_valid & !rej;
-        rejected = rejected | rej;
-        cnt[WTC_NREJECT] = cnt[WTC_NREJECT] + seli(rej, 1, 0);
-      }
-      if (vany(acc)) {  // radau.py:514-545
-        vb recompute = (n_iter > 2) & (rate > 1e-3);
-        vd fct = vmin(safety * pf, 10.0);
-        vb keep = (!recompute) & (fct < 1.2);
-        fct = sel(keep, 1.0, fct);
-        lu_valid = lu_valid & !(acc & !keep);
-        vd fn[3];
-        vb bad;
-        wt_rhs(g, c, y_new[0], y_new[1], y_new[2], fn[0], fn[1], fn[2], bad);
-        cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(acc, 1, 0);
-        {
-          vb tb = acc & wt_gany(g, bad);
-          trange = trange | tb;
-          running = running & !tb;
           acc = acc & !tb;
         }
-        need_jac = need_jac | (acc & recompute);
-        current_jac = selb(acc, vbroadcast_b(false), current_jac);  // set again by num_jac when recomputed
-        self_h_abs_old = sel(acc, self_h_abs, self_h_abs_old);
-        self_err_old = sel(acc, err_norm, self_err_old);
-        self_have_old = self_have_old | acc;
-        self_h_abs = sel(acc, h_abs * fct, self_h_abs);
-        WT_UNROLL
-        for (int v = 0; v < 3; ++v) {
-          Q[v][0] = sel(acc, (Z[0][v] * WT_P00 + Z[1][v] * WT_P10) + Z[2][v] * WT_P20, Q[v][0]);
-          Q[v][1] = sel(acc, (Z[0][v] * WT_P01 + Z[1][v] * WT_P11) + Z[2][v] * WT_P21, Q[v][1]);
-          Q[v][2] = sel(acc, (Z[0][v] * WT_P02 + Z[1][v] * WT_P12) + Z[2][v] * WT_P22, Q[v][2]);
-          yold[v] = sel(acc, y[v], yold[v]);
-          y[v] = sel(acc, y_new[v], y[v]);
-          f[v] = sel(acc, fn[v], f[v]);
+        if (pass < 2) {
+          vd e[3];
+          WT_UNROLL
+          for (int v = 0; v < 3; ++v) e[v] = F[v] + ZE[v];
+          solve_real(e);
+          const vd en = rms3(e[0] * escale[0], e[1] * escale[1], e[2] * escale[2]);
+          if (pass == 0) {
+            WT_UNROLL
+            for (int v = 0; v < 3; ++v) err[v] = e[v];
+            err_norm = en;
+            again = cv & rejected & (err_norm > 1.0);
+          } else {
+            err_norm = sel(again, en, err_norm);
+          }
+        } else {  // radau.py:514-545
+          const vb recompute = (n_iter > 2) & (rate > 1e-3);
+          vd fct = vmin(safety * pf, 10.0);
+          const vb keep = (!recompute) & (fct < 1.2);
+          fct = sel(keep, 1.0, fct);
+          lu_valid = lu_valid & !(acc & !keep);
+          need_jac = need_jac | (acc & recompute);
+          current_jac = selb(acc, vbroadcast_b(false), current_jac);  // set again by num_jac when recomputed
+          self_h_abs_old = sel(acc, self_h_abs, self_h_abs_old);
+          self_err_old = sel(acc, err_norm, self_err_old);
+          self_have_old = self_have_old | acc;
+          self_h_abs = sel(acc, h_abs * fct, self_h_abs);
+          WT_UNROLL
+          for (int v = 0; v < 3; ++v) {
+            Q[v][0] = sel(acc, (Z[0][v] * WT_P00 + Z[1][v] * WT_P10) + Z[2][v] * WT_P20, Q[v][0]);
+            Q[v][1] = sel(acc, (Z[0][v] * WT_P01 + Z[1][v] * WT_P11) + Z[2][v] * WT_P21, Q[v][1]);
+            Q[v][2] = sel(acc, (Z[0][v] * WT_P02 + Z[1][v] * WT_P12) + Z[2][v] * WT_P22, Q[v][2]);
+            yold[v] = sel(acc, y[v], yold[v]);
+            y[v] = sel(acc, y_new[v], y[v]);
+            f[v] = sel(acc, F[v], f[v]);
+          }
+          sol_told = sel(acc, t, sol_told);
+          sol_h = sel(acc, t_new - t, sol_h);
+          have_sol = have_sol | acc;
+          t = sel(acc, t_new, t);
+          new_step = new_step | acc;
+          cnt[WTC_NSTEPS] = cnt[WTC_NSTEPS] + seli(acc, 1, 0);
         }
-        sol_told = sel(acc, t, sol_told);
-        sol_h = sel(acc, t_new - t, sol_h);
-        have_sol = have_sol | acc;
-        t = sel(acc, t_new, t);
-        new_step = new_step | acc;
-        cnt[WTC_NSTEPS] = cnt[WTC_NSTEPS] + seli(acc, 1, 0);
       }
     }
   }
