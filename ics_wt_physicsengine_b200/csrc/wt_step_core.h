@@ -297,13 +297,16 @@ WT_DEV vd wt_arrhenius(vd T) {
 }
 WT_DEV vb wt_t_out_of_range(vd T) { return (T < 0.0) | (T > 100.0); }  // thermodynamics.py:146-157
 
-// chemistry.py:422-437 (+ :181-191): beta(pH) * ln(10)
+// chemistry.py:422-437 (+ :181-191): beta(pH) * ln(10).  Split into "denominators", "reciprocals" and "the rest"
+// so that the RHS can take the three reciprocals of a zone (1/H, 1/D, 1/(H + Ka_HOCl)) in one interleaved
+// wt_rcp_n<3> while num_jac, which needs them one at a time, runs the very same arithmetic.
 template <class Store>
-WT_DEV vd wt_beta_ln10(const WtConstT<Store> &c, vd H, vb &bpos) {
-  vd bw = 2.303 * (H + c.Kw() * wt_rcp(H));
+WT_DEV vd wt_beta_den(const WtConstT<Store> &c, vd H) { return H * H + c.Ka1() * H + c.Ka12(); }
+template <class Store>
+WT_DEV vd wt_beta_ln10_r(const WtConstT<Store> &c, vd H, vd iH, vd iD, vb &bpos) {
+  vd bw = 2.303 * (H + c.Kw() * iH);
   vd HH = H * H;
-  vd D = HH + c.Ka1() * H + c.Ka12();
-  vd iD = wt_rcp(D);  // the three alphas share one reciprocal (<= 1 ulp from three divisions)
+  // the three alphas share one reciprocal (<= 1 ulp from three divisions)
   vd a0 = HH * iD;
   vd a1 = (c.Ka1() * H) * iD;
   vd a2 = c.Ka12() * iD;
@@ -312,13 +315,18 @@ WT_DEV vd wt_beta_ln10(const WtConstT<Store> &c, vd H, vb &bpos) {
   bpos = beta > 0.0;
   return beta * WT_LN10;
 }
+template <class Store>
+WT_DEV vd wt_beta_ln10(const WtConstT<Store> &c, vd H, vb &bpos) {
+  return wt_beta_ln10_r(c, H, wt_rcp(H), wt_rcp(wt_beta_den(c, H)), bpos);
+}
 
 // chemistry.py:510-523
 template <class Store>
-WT_DEV vd wt_decay_factor(const WtConstT<Store> &c, vd H) {
-  vd iden = wt_rcp(H + c.KaCl());
+WT_DEV vd wt_decay_factor_r(const WtConstT<Store> &c, vd H, vd iden) {
   return (H * iden) * 1.0 + (c.KaCl() * iden) * 0.02;
 }
+template <class Store>
+WT_DEV vd wt_decay_factor(const WtConstT<Store> &c, vd H) { return wt_decay_factor_r(c, H, wt_rcp(H + c.KaCl())); }
 
 struct WtMix { vd off_dn, off_up, diag; };
 
@@ -368,12 +376,15 @@ WT_DEV void wt_rhs(const WtGroup &g, const WtConstT<Store> &c, vd pH, vd Cl, vd 
   vd s_up = wt_suppression(c, rho, shfl_down(rho, 1));
   vd s_dn = shfl_up(s_up, 1);
   WtMix m = wt_mix_row(g, c, s_dn, s_up);
-  vd H = vexp10(-pH);
+  vd H, ke;
+  wt_h_and_arrh(pH, T, H, ke);  // H = 10^-pH and the Arrhenius exponential, chains interleaved
+  vd den[3] = {H, wt_beta_den(c, H), H + c.KaCl()}, inv[3];
+  wt_rcp_n<3>(den, inv);  // three Newton chains interleaved
   vb bpos;
-  vd ibl = wt_rcp(wt_beta_ln10(c, H, bpos));
+  vd ibl = wt_rcp(wt_beta_ln10_r(c, H, inv[0], inv[1], bpos));
   vd mixH = wt_mix(m, wt_dnc(g, H), H, wt_upc(g, H));
   dpH = wt_dph(wt_dph_inlet(g, c, H, ibl, bpos), mixH, ibl, bpos);
-  vd kf = wt_arrhenius(T) * wt_decay_factor(c, H);
+  vd kf = (0.0001 * ke) * wt_decay_factor_r(c, H, inv[2]);
   dCl = wt_dcl(g, c, Cl, wt_mix(m, wt_dnc(g, Cl), Cl, wt_upc(g, Cl)), kf);
   dT = wt_dt(g, c, T, wt_mix(m, wt_dnc(g, T), T, wt_upc(g, T)));
   bad = wt_t_out_of_range(T);
@@ -531,50 +542,63 @@ struct WtPlantStep {
     WT_NOUNROLL
     for (int s = 1; s < g.n; s <<= 1, ++l) {
       const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
+      // Written PHASE-major (all reciprocals, then all exchanges, then all updates) so that the six
+      // factorizations advance together: ptxas keeps the statement order when registers are tight, and
+      // system-major order ran the six reciprocal chains (MUFU + 5 dependent DFMAs each) back to back.
+      vd den[6], inv[6];  // 0..2 real pivots, 3..5 |complex pivot|^2
+      WT_UNROLL
+      for (int q = 0; q < 3; ++q) { den[q] = b[q]; den[3 + q] = br[q] * br[q] + bi[q] * bi[q]; }
+      wt_rcp_n<6>(den, inv);
+      vd rr[3], ri[3];  // 1 / complex pivot
+      WT_UNROLL
+      for (int q = 0; q < 3; ++q) { rr[q] = br[q] * inv[3 + q]; ri[q] = -(bi[q] * inv[3 + q]); }
+      vd k1[3], k2[3], k1r[3], k1i[3], k2r[3], k2i[3];
       WT_UNROLL
       for (int q = 0; q < 3; ++q) {
-        {  // real
-          const int s0 = slot_real(q);
-          vd r = wt_rcp(b[q]);
-          vd k1 = a[q] * shfl_idx(r, sd);
-          vd k2 = c_[q] * shfl_idx(r, su);
-          vd a_dn = shfl_idx(a[q], sd), c_dn = shfl_idx(c_[q], sd);
-          vd a_up = shfl_idx(a[q], su), c_up = shfl_idx(c_[q], su);
-          b[q] = b[q] - c_dn * k1 - a_up * k2;
-          a[q] = -(a_dn * k1);
-          c_[q] = -(c_up * k2);
-          lu->put(s0 + 2 * l, k1, mask);
-          lu->put(s0 + 2 * l + 1, k2, mask);
-        }
-        {  // complex
-          const int s0 = slot_cplx(q);
-          vd iden = wt_rcp(br[q] * br[q] + bi[q] * bi[q]);
-          vd rr = br[q] * iden, ri = -(bi[q] * iden);  // 1 / b
-          vd rdr = shfl_idx(rr, sd), rdi = shfl_idx(ri, sd);
-          vd rur = shfl_idx(rr, su), rui = shfl_idx(ri, su);
-          vd k1r = ar[q] * rdr - ai[q] * rdi, k1i = ar[q] * rdi + ai[q] * rdr;
-          vd k2r = cr[q] * rur - ci[q] * rui, k2i = cr[q] * rui + ci[q] * rur;
-          vd adr = shfl_idx(ar[q], sd), adi = shfl_idx(ai[q], sd), cdr = shfl_idx(cr[q], sd), cdi = shfl_idx(ci[q], sd);
-          vd aur = shfl_idx(ar[q], su), aui = shfl_idx(ai[q], su), cur = shfl_idx(cr[q], su), cui = shfl_idx(ci[q], su);
-          br[q] = br[q] - (cdr * k1r - cdi * k1i) - (aur * k2r - aui * k2i);
-          bi[q] = bi[q] - (cdr * k1i + cdi * k1r) - (aur * k2i + aui * k2r);
-          ar[q] = -(adr * k1r - adi * k1i);
-          ai[q] = -(adr * k1i + adi * k1r);
-          cr[q] = -(cur * k2r - cui * k2i);
-          ci[q] = -(cur * k2i + cui * k2r);
-          lu->put(s0 + 4 * l + 0, k1r, mask);
-          lu->put(s0 + 4 * l + 1, k1i, mask);
-          lu->put(s0 + 4 * l + 2, k2r, mask);
-          lu->put(s0 + 4 * l + 3, k2i, mask);
-        }
+        k1[q] = a[q] * shfl_idx(inv[q], sd);
+        k2[q] = c_[q] * shfl_idx(inv[q], su);
+        const vd rdr = shfl_idx(rr[q], sd), rdi = shfl_idx(ri[q], sd);
+        const vd rur = shfl_idx(rr[q], su), rui = shfl_idx(ri[q], su);
+        k1r[q] = ar[q] * rdr - ai[q] * rdi; k1i[q] = ar[q] * rdi + ai[q] * rdr;
+        k2r[q] = cr[q] * rur - ci[q] * rui; k2i[q] = cr[q] * rui + ci[q] * rur;
+      }
+      WT_UNROLL
+      for (int q = 0; q < 3; ++q) {
+        const vd a_dn = shfl_idx(a[q], sd), c_dn = shfl_idx(c_[q], sd);
+        const vd a_up = shfl_idx(a[q], su), c_up = shfl_idx(c_[q], su);
+        b[q] = b[q] - c_dn * k1[q] - a_up * k2[q];
+        a[q] = -(a_dn * k1[q]);
+        c_[q] = -(c_up * k2[q]);
+        const vd adr = shfl_idx(ar[q], sd), adi = shfl_idx(ai[q], sd), cdr = shfl_idx(cr[q], sd), cdi = shfl_idx(ci[q], sd);
+        const vd aur = shfl_idx(ar[q], su), aui = shfl_idx(ai[q], su), cur = shfl_idx(cr[q], su), cui = shfl_idx(ci[q], su);
+        br[q] = br[q] - (cdr * k1r[q] - cdi * k1i[q]) - (aur * k2r[q] - aui * k2i[q]);
+        bi[q] = bi[q] - (cdr * k1i[q] + cdi * k1r[q]) - (aur * k2i[q] + aui * k2r[q]);
+        ar[q] = -(adr * k1r[q] - adi * k1i[q]);
+        ai[q] = -(adr * k1i[q] + adi * k1r[q]);
+        cr[q] = -(cur * k2r[q] - cui * k2i[q]);
+        ci[q] = -(cur * k2i[q] + cui * k2r[q]);
+      }
+      WT_UNROLL
+      for (int q = 0; q < 3; ++q) {
+        lu->put(slot_real(q) + 2 * l, k1[q], mask);
+        lu->put(slot_real(q) + 2 * l + 1, k2[q], mask);
+        lu->put(slot_cplx(q) + 4 * l + 0, k1r[q], mask);
+        lu->put(slot_cplx(q) + 4 * l + 1, k1i[q], mask);
+        lu->put(slot_cplx(q) + 4 * l + 2, k2r[q], mask);
+        lu->put(slot_cplx(q) + 4 * l + 3, k2i[q], mask);
       }
     }
-    WT_UNROLL
-    for (int q = 0; q < 3; ++q) {
-      lu->put(slot_real(q) + 2 * l, wt_rcp(b[q]), mask);
-      vd iden = wt_rcp(br[q] * br[q] + bi[q] * bi[q]);
-      lu->put(slot_cplx(q) + 4 * l + 0, br[q] * iden, mask);
-      lu->put(slot_cplx(q) + 4 * l + 1, -(bi[q] * iden), mask);
+    {
+      vd den[6], inv[6];
+      WT_UNROLL
+      for (int q = 0; q < 3; ++q) { den[q] = b[q]; den[3 + q] = br[q] * br[q] + bi[q] * bi[q]; }
+      wt_rcp_n<6>(den, inv);
+      WT_UNROLL
+      for (int q = 0; q < 3; ++q) {
+        lu->put(slot_real(q) + 2 * l, inv[q], mask);
+        lu->put(slot_cplx(q) + 4 * l + 0, br[q] * inv[3 + q], mask);
+        lu->put(slot_cplx(q) + 4 * l + 1, -(bi[q] * inv[3 + q]), mask);
+      }
     }
   }
   WT_DEV vd tri_mv(const vd *row, vd xdn, vd x, vd xup) const { return (row[0] * xdn + row[1] * x) + row[2] * xup; }
