@@ -37,6 +37,14 @@ static int cuda_err(cudaError_t e, const char *where) {
 struct SmemLu {
   double *p;   // &lu_region[lane]; slot stride = 32 doubles
   double *cp;  // constants of this lane's plant (one copy per plant, read as a broadcast)
+  int *ci;     // solver path counters of this lane's plant (WTC_*): in shared memory, not in 8 registers per lane that
+               // ptxas spilled; every lane of the plant adds the same increment to the same word (benign)
+  __device__ __forceinline__ void czero() {
+#pragma unroll
+    for (int k = 0; k < WTC_NCNT; ++k) ci[k] = 0;
+  }
+  __device__ __forceinline__ void cadd(int k, int inc) { ci[k] += inc; }
+  __device__ __forceinline__ int cval(int k) const { return ci[k]; }
   // predicated store: an `if (mask)` here becomes a branch around each group of stores, and a branch ends
   // the basic block ptxas schedules in (the six factorizations of a PCR level then run one after the other)
   __device__ __forceinline__ void put(int slot, double x, bool mask) {
@@ -57,7 +65,8 @@ __host__ __device__ inline int wt_lu_slots(int n) {
 // + the lane-private constants (LK_*) kept after the LU multipliers
 __host__ __device__ inline int wt_lane_slots(int n) { return wt_lu_slots(n) + LK_N; }
 // doubles of shared memory per warp: LU slots for 32 lanes + constants for (32/n + 1) plants
-__host__ __device__ inline int wt_warp_smem_doubles(int n) { return wt_lane_slots(n) * 32 + (32 / n + 1) * CK_N; }
+#define WT_PLANT_DOUBLES (CK_N + WTC_NCNT / 2)  // per-plant constants + the path counters (ints)
+__host__ __device__ inline int wt_warp_smem_doubles(int n) { return wt_lane_slots(n) * 32 + (32 / n + 1) * WT_PLANT_DOUBLES; }
 
 struct StepArgs {
   int P, n, n_steps, bnd_stride, max_attempts;
@@ -116,7 +125,9 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
 
   SmemLu lu;
   lu.p = smem + (size_t)warp * wt_warp_smem_doubles(n) + lane;
-  lu.cp = smem + (size_t)warp * wt_warp_smem_doubles(n) + wt_lane_slots(n) * 32 + (gi < gpw ? gi : gpw) * CK_N;
+  lu.cp = smem + (size_t)warp * wt_warp_smem_doubles(n) + wt_lane_slots(n) * 32 + (gi < gpw ? gi : gpw) * WT_PLANT_DOUBLES;
+  lu.ci = (int *)(lu.cp + CK_N);
+  lu.czero();
 
   WtPlantStep<SmemLu> ps;
   ps.g = wt_make_group(n);
@@ -127,9 +138,6 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
 #pragma unroll
   for (int v = 0; v < 3; ++v) ps.y[v] = y0[v];
 
-  int32_t acc[WTC_NCNT];
-#pragma unroll
-  for (int k = 0; k < WTC_NCNT; ++k) acc[k] = 0;
   uint32_t st = st_in;
   double der[3] = {0.0, 0.0, 0.0};
   bool stepped = false;
@@ -145,8 +153,6 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
     if (on) {
       st = (uint32_t)sb;
       if (adv) { t += a.dt; stepped = true; }
-#pragma unroll
-      for (int k = 0; k < WTC_NCNT; ++k) acc[k] += ps.cnt[k];
       if (sb & WTS_HALT_MASK) on = false;
     }
   }
@@ -165,9 +171,9 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
       if (a.counters) {
         // fire-and-forget reductions: a load-add-store here made the whole warp wait for eight loads
 #pragma unroll
-        for (int k = 0; k < WTC_NCNT; ++k) atomicAdd(&a.counters[(size_t)k * P + p], acc[k]);
+        for (int k = 0; k < WTC_NCNT; ++k) atomicAdd(&a.counters[(size_t)k * P + p], lu.cval(k));
       }
-      if (a.cost) a.cost[p] = acc[WTC_NSTEPS] + acc[WTC_NREJECT] + acc[WTC_NNEWTON_FAIL] + acc[WTC_NNEWTON];
+      if (a.cost) a.cost[p] = lu.cval(WTC_NSTEPS) + lu.cval(WTC_NREJECT) + lu.cval(WTC_NNEWTON_FAIL) + lu.cval(WTC_NNEWTON);
     }
   }
 }
@@ -187,6 +193,7 @@ __global__ void wt_derivatives_kernel(int P, int n, const double *par_, const do
   SmemLu st;
   st.p = &cs[threadIdx.x >> 5][17 * CK_N + lane];
   st.cp = &cs[threadIdx.x >> 5][(gi < gpw ? gi : gpw) * CK_N];
+  st.ci = nullptr;  // the RHS alone counts nothing
   double par[WTP_NPAR], bnd[WTB_NBND];
 #pragma unroll
   for (int k = 0; k < WTP_NPAR; ++k) par[k] = par_[(size_t)k * P + p];

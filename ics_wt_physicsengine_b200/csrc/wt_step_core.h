@@ -504,16 +504,22 @@ struct WtPlantStep {
   vd y[3], f[3];
   WtJac J;
   vd jfac[3];
-  vb have_jfac;
+  // Per-plant decisions of the solver, one bit each in ONE register (as separate bools ptxas kept them in
+  // byte lanes of several registers and spilled those to local memory, which misses L1 here: long_sb stalls)
+  enum { F_RUNNING = 1, F_NEED_JAC = 2, F_CURRENT_JAC = 4, F_LU_VALID = 8, F_NEW_STEP = 16, F_HAVE_OLD = 32,
+         F_REJECTED = 64, F_HAVE_JFAC = 128, F_HAVE_SOL = 256, F_TRANGE = 512, F_FAILED = 1024,
+         F_WORKLIMIT = 2048, F_SELF_HAVE_OLD = 4096 };
+  vi fl;
+  WT_DEV vb fget(int bit) const { return (fl & bit) != 0; }
+  WT_DEV void fset(int bit, vb m) { fl = fl | seli(m, bit, 0); }      // set where m
+  WT_DEV void fclr(int bit, vb m) { fl = fl & seli(m, ~bit, -1); }    // clear where m
+  WT_DEV vb trange() const { return fget(F_TRANGE); }      // the reference would have raised ValueError inside the solve
+  WT_DEV vb failed() const { return fget(F_FAILED); }      // TOO_SMALL_STEP
+  WT_DEV vb worklimit() const { return fget(F_WORKLIMIT); }  // engine policy: attempt budget exhausted (not reference behaviour)
   vd W[3][3];     // W[k][var]
   vd Q[3][3];     // dense output, Q[var][k]   (radau.py:547-553)
   vd yold[3];
   vd sol_told, sol_h;
-  vb have_sol;
-  vi cnt[WTC_NCNT];
-  vb trange;      // the reference would have raised ValueError inside the solve
-  vb failed;      // TOO_SMALL_STEP
-  vb worklimit;   // engine policy: attempt budget exhausted (not reference behaviour)
 
   WT_DEV int slot_real(int sys) const { return sys * (2 * g.L + 1); }
   WT_DEV int slot_cplx(int sys) const { return 3 * (2 * g.L + 1) + sys * (4 * g.L + 2); }
@@ -664,11 +670,11 @@ struct WtPlantStep {
     const double SMALL = 1.8189894035458565e-12;   // EPS ** 0.75
     const double BIG = 1.220703125e-4;             // EPS ** 0.25
     const double MINF = 1e3 * WT_EPS;
-    cnt[WTC_NJEV] = cnt[WTC_NJEV] + seli(m, 1, 0);
+    lu->cadd(WTC_NJEV, seli(m, 1, 0));
 
     WT_UNROLL
-    for (int v = 0; v < 3; ++v) jfac[v] = sel(m & !have_jfac, 1.4901161193847656e-08, jfac[v]);  // EPS ** 0.5
-    have_jfac = have_jfac | m;
+    for (int v = 0; v < 3; ++v) jfac[v] = sel(m & !fget(F_HAVE_JFAC), 1.4901161193847656e-08, jfac[v]);  // EPS ** 0.5
+    fset(F_HAVE_JFAC, m);
 
     // ---- base intermediates at y (identical bits to the evaluation that produced f)
     const vd pH = y[0], Cl = y[1], T = y[2];
@@ -726,7 +732,7 @@ struct WtPlantStep {
       if (pass == 1) {
         vb anyretry = m & (retry[0] | retry[1] | retry[2]);
         if (!vany(anyretry)) break;
-        cnt[WTC_JAC_RETRY] = cnt[WTC_JAC_RETRY] + seli(anyretry, 1, 0);
+        lu->cadd(WTC_JAC_RETRY, seli(anyretry, 1, 0));
       }
       WT_UNROLL
       for (int v = 0; v < 3; ++v)
@@ -740,7 +746,7 @@ struct WtPlantStep {
       vd kfp_pH = kk * wt_decay_factor(c, Hp);
       vd Clp = Cl + hc[1];
       vd Tp = T + hc[2];
-      trange = trange | (m & wt_gany(g, wt_t_out_of_range(Tp) | wt_t_out_of_range(T)));
+      fset(F_TRANGE, m & wt_gany(g, wt_t_out_of_range(Tp) | wt_t_out_of_range(T)));
       vd kfp_T = wt_arrhenius(Tp) * wt_decay_factor(c, H);
       vd rhop = wt_density(Tp);
 
@@ -916,13 +922,8 @@ struct WtPlantStep {
     vd t = t0;
     const vd t_bound = t0 + dt;
     const vd max_step = vmin(dt, 10.0);
-    WT_UNROLL
-    for (int k = 0; k < WTC_NCNT; ++k) cnt[k] = vbroadcast_i(0);
-    trange = vbroadcast_b(false);
-    failed = vbroadcast_b(false);
-    worklimit = vbroadcast_b(false);
-    have_jfac = vbroadcast_b(false);
-    have_sol = vbroadcast_b(false);
+    // running = plant_on; current_jac and new_step start true (radau.py:363-369, :413)
+    fl = seli(plant_on, (int)F_RUNNING, 0) | (int)(F_CURRENT_JAC | F_NEW_STEP);
     sol_told = vbroadcast(0.0);
     sol_h = vbroadcast(1.0);
     WT_UNROLL
@@ -939,7 +940,6 @@ struct WtPlantStep {
       J.cc[k] = vbroadcast(0.0); J.ct[k] = vbroadcast(0.0);
     }
 
-    vb running = plant_on;
     // ---- Radau.__init__: f0 and select_initial_step (radau.py:303-311, common.py:68-134)
     vd self_h_abs;
     {
@@ -953,8 +953,8 @@ struct WtPlantStep {
       for (int it = 0; it < 2; ++it) {
         vb bad;
         wt_rhs(g, c, yy[0], yy[1], yy[2], fo[0], fo[1], fo[2], bad);
-        cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(running, 1, 0);
-        trange = trange | (running & wt_gany(g, bad));
+        lu->cadd(WTC_NFEV, seli(fget(F_RUNNING), 1, 0));
+        fset(F_TRANGE, fget(F_RUNNING) & wt_gany(g, bad));
         if (it == 0) {
           WT_UNROLL
           for (int v = 0; v < 3; ++v) f[v] = fo[v];
@@ -970,41 +970,34 @@ struct WtPlantStep {
       vd h1 = sel((d1 <= 1e-15) & (d2 <= 1e-15), vmax(h0 * 1e-3, 1e-6), vsqrt(vsqrt(wt_div(0.01, vmax(d1, d2)))));
       self_h_abs = vmin(vmin(100.0 * h0, h1), vmin(interval, max_step));
     }
-    running = running & !trange;
+    fclr(F_RUNNING, trange());
 
     vd self_h_abs_old = vbroadcast(0.0), self_err_old = vbroadcast(0.0);
-    vb self_have_old = vbroadcast_b(false);
-    vb need_jac = running;      // first Jacobian (radau.py:363-369)
-    vb current_jac = vbroadcast_b(true);
-    vb lu_valid = vbroadcast_b(false);
-    vb new_step = vbroadcast_b(true);
+    fset(F_NEED_JAC, fget(F_RUNNING));  // first Jacobian (radau.py:363-369)
     vd h_abs = self_h_abs, h_abs_old = vbroadcast(0.0), err_old = vbroadcast(0.0);
-    vb have_old = vbroadcast_b(false);
-    vb rejected = vbroadcast_b(false);
     vd min_step = vbroadcast(0.0);
 
     vi attempts = vbroadcast_i(0);
-    while (wt_cta_any(vany(running))) {
+    while (wt_cta_any(vany(fget(F_RUNNING)))) {
       // (1) Jacobian: first one, stale-J refresh (radau.py:467-473) or post-accept refresh (:519-521)
       {
-        vb m = running & need_jac;
+        vb m = fget(F_RUNNING) & fget(F_NEED_JAC);
         if (vany(m)) {
           num_jac(m);
-          current_jac = current_jac | m;
-          lu_valid = lu_valid & !m;
-          need_jac = need_jac & !m;
-          running = running & !trange;
+          fset(F_CURRENT_JAC, m);
+          fclr(F_LU_VALID | F_NEED_JAC, m);
+          fclr(F_RUNNING, trange());
         }
       }
       // base.py:204-208: finished once t reached t_bound
-      running = running & !(t == t_bound);
+      fclr(F_RUNNING, t == t_bound);
 #ifndef WT_CTA_LOCKSTEP
-      if (!vany(running)) break;
+      if (!vany(fget(F_RUNNING))) break;
 #endif
 
       // (2) _step_impl entry (radau.py:413-428)
       {
-        vb m = running & new_step;
+        vb m = fget(F_RUNNING) & fget(F_NEW_STEP);
         vd ms = 10.0 * vabs(vnextafter_up(t) - t);
         min_step = sel(m, ms, min_step);
         vb big = self_h_abs > max_step, small = self_h_abs < ms;
@@ -1012,26 +1005,26 @@ struct WtPlantStep {
         h_abs = sel(m, hh_, h_abs);
         h_abs_old = sel(m, self_h_abs_old, h_abs_old);
         err_old = sel(m, self_err_old, err_old);
-        have_old = selb(m, self_have_old & !(big | small), have_old);
-        rejected = rejected & !m;
-        new_step = new_step & !m;
+        fclr(F_HAVE_OLD | F_REJECTED | F_NEW_STEP, m);
+        fset(F_HAVE_OLD, m & fget(F_SELF_HAVE_OLD) & !(big | small));
       }
       // (3) attempt setup (radau.py:439-457)
       {
-        vb f_ = running & (h_abs < min_step);
-        failed = failed | f_;
-        running = running & !f_;
+        vb f_ = fget(F_RUNNING) & (h_abs < min_step);
+        fset(F_FAILED, f_);
+        fclr(F_RUNNING, f_);
       }
       vd t_new = t + h_abs;
       t_new = sel(t_new - t_bound > 0.0, t_bound, t_new);
       const vd h = t_new - t;
-      h_abs = sel(running, vabs(h), h_abs);
+      h_abs = sel(fget(F_RUNNING), vabs(h), h_abs);
       vd scale[3];  // 1 / (atol + |y| rtol)
       WT_UNROLL
       for (int v = 0; v < 3; ++v) scale[v] = wt_rcp(WT_ATOL + vabs(y[v]) * WT_RTOL);
       const vd ih = wt_rcp(h);
       {
         const vd isolh = wt_rcp(sol_h);
+        const vb hs = fget(F_HAVE_SOL);
         // Z0 = sol(t + h*C).T - y, W = TI.dot(Z0)   (radau.py:451-454, 555-578, :64)
         vd x0 = ((t + h * WT_C0) - sol_told) * isolh;
         vd x1 = ((t + h * WT_C1) - sol_told) * isolh;
@@ -1041,9 +1034,9 @@ struct WtPlantStep {
           vd z0 = (((Q[v][0] * x0 + Q[v][1] * (x0 * x0)) + Q[v][2] * ((x0 * x0) * x0)) + yold[v]) - y[v];
           vd z1 = (((Q[v][0] * x1 + Q[v][1] * (x1 * x1)) + Q[v][2] * ((x1 * x1) * x1)) + yold[v]) - y[v];
           vd z2 = (((Q[v][0] * x2 + Q[v][1] * (x2 * x2)) + Q[v][2] * ((x2 * x2) * x2)) + yold[v]) - y[v];
-          z0 = sel(have_sol, z0, 0.0);
-          z1 = sel(have_sol, z1, 0.0);
-          z2 = sel(have_sol, z2, 0.0);
+          z0 = sel(hs, z0, 0.0);
+          z1 = sel(hs, z1, 0.0);
+          z2 = sel(hs, z2, 0.0);
           W[0][v] = (WT_TI00 * z0 + WT_TI01 * z1) + WT_TI02 * z2;
           W[1][v] = (WT_TI10 * z0 + WT_TI11 * z1) + WT_TI12 * z2;
           W[2][v] = (WT_TI20 * z0 + WT_TI21 * z1) + WT_TI22 * z2;
@@ -1051,33 +1044,33 @@ struct WtPlantStep {
       }
       // (4) LU of (MU/h I - J), real and complex (radau.py:460-462)
       {
-        vb m = running & !lu_valid;
+        vb m = fget(F_RUNNING) & !fget(F_LU_VALID);
         if (vany(m)) {
           factor(h, m);
-          cnt[WTC_NLU] = cnt[WTC_NLU] + seli(m, 2, 0);
-          lu_valid = lu_valid | m;
+          lu->cadd(WTC_NLU, seli(m, 2, 0));
+          fset(F_LU_VALID, m);
         }
       }
       // Engine policy (straggler policy): budget of collocation solves per step.
       // The reference has none; plants sitting on the 8 C density discontinuity make it grind
       // through millions of micro-steps.  Exhausted budget == exception: state left untouched.
       {
-        attempts = attempts + seli(running, 1, 0);
-        vb over = running & (attempts > max_attempts);
-        worklimit = worklimit | over;
-        running = running & !over;
+        attempts = attempts + seli(fget(F_RUNNING), 1, 0);
+        vb over = fget(F_RUNNING) & (attempts > max_attempts);
+        fset(F_WORKLIMIT, over);
+        fclr(F_RUNNING, over);
       }
       // (5) simplified Newton (radau.py:48-136)
       const vd M_real = WT_MU_REAL * ih, Mc_re = WT_MU_CRE * ih, Mc_im = WT_MU_CIM * ih;
       vb converged = vbroadcast_b(false);
-      vb active = running;
+      vb active = fget(F_RUNNING);
       vd dW_norm_old = vbroadcast(0.0), rate = vbroadcast(0.0);
       vb have_norm_old = vbroadcast_b(false), have_rate = vbroadcast_b(false);
       vi n_iter = vbroadcast_i(0);
       WT_NOUNROLL
       for (int k = 0; k < WT_NEWTON_MAXITER; ++k) {
         if (!vany(active)) break;
-        cnt[WTC_NNEWTON] = cnt[WTC_NNEWTON] + seli(active, 1, 0);
+        lu->cadd(WTC_NNEWTON, seli(active, 1, 0));
         n_iter = seli(active, k + 1, n_iter);
         vd fr[3], cr[3], ci[3];
         WT_UNROLL
@@ -1098,11 +1091,11 @@ struct WtPlantStep {
             ci[v] = ci[v] + F[v] * t2;
           }
         }
-        cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(active, 3, 0);
+        lu->cadd(WTC_NFEV, seli(active, 3, 0));
         {
           vb tb = active & wt_gany(g, bad_any);
-          trange = trange | tb;
-          running = running & !tb;
+          fset(F_TRANGE, tb);
+          fclr(F_RUNNING, tb);
           active = active & !tb;
         }
         active = active & !wt_gany(g, !finite);  // radau.py:91-92: break, not converged
@@ -1146,15 +1139,15 @@ struct WtPlantStep {
       }
       // (6) outcome of the collocation solve (radau.py:464-481)
       {
-        vb nc = running & !converged;
-        cnt[WTC_NNEWTON_FAIL] = cnt[WTC_NNEWTON_FAIL] + seli(nc, 1, 0);
-        vb stale = nc & !current_jac;
-        need_jac = need_jac | stale;  // recompute J at (t, y, f), same h
-        vb halve = nc & current_jac;
+        vb nc = fget(F_RUNNING) & !converged;
+        lu->cadd(WTC_NNEWTON_FAIL, seli(nc, 1, 0));
+        vb stale = nc & !fget(F_CURRENT_JAC);
+        fset(F_NEED_JAC, stale);  // recompute J at (t, y, f), same h
+        vb halve = nc & fget(F_CURRENT_JAC);
         h_abs = sel(halve, h_abs * 0.5, h_abs);
-        lu_valid = lu_valid & !halve;
+        fclr(F_LU_VALID, halve);
       }
-      vb cv = running & converged;
+      vb cv = fget(F_RUNNING) & converged;
       if (!vany(cv)) continue;
 
       // (7) error estimate and step control (radau.py:483-512), (8) acceptance (radau.py:514-545).
@@ -1192,11 +1185,11 @@ struct WtPlantStep {
           } else {
             const vb rej = cv & (err_norm > 1.0);
             acc = cv & !rej;
-            pf = predict_factor(h_abs, h_abs_old, err_norm, err_old, have_old);
+            pf = predict_factor(h_abs, h_abs_old, err_norm, err_old, fget(F_HAVE_OLD));
             h_abs = sel(rej, h_abs * vmax(safety * pf, 0.2), h_abs);
-            lu_valid = lu_valid & !rej;
-            rejected = rejected | rej;
-            cnt[WTC_NREJECT] = cnt[WTC_NREJECT] + seli(rej, 1, 0);
+            fclr(F_LU_VALID, rej);
+            fset(F_REJECTED, rej);
+            lu->cadd(WTC_NREJECT, seli(rej, 1, 0));
             m = acc;
             WT_UNROLL
             for (int v = 0; v < 3; ++v) pnt[v] = y_new[v];
@@ -1204,10 +1197,10 @@ struct WtPlantStep {
           if (!vany(m)) continue;
           vb bad;
           wt_rhs(g, c, pnt[0], pnt[1], pnt[2], F[0], F[1], F[2], bad);
-          cnt[WTC_NFEV] = cnt[WTC_NFEV] + seli(m, 1, 0);
+          lu->cadd(WTC_NFEV, seli(m, 1, 0));
           const vb tb = m & wt_gany(g, bad);
-          trange = trange | tb;
-          running = running & !tb;
+          fset(F_TRANGE, tb);
+          fclr(F_RUNNING, tb);
           cv = cv & !tb;
           acc = acc & !tb;
         }
@@ -1221,7 +1214,7 @@ struct WtPlantStep {
             WT_UNROLL
             for (int v = 0; v < 3; ++v) err[v] = e[v];
             err_norm = en;
-            again = cv & rejected & (err_norm > 1.0);
+            again = cv & fget(F_REJECTED) & (err_norm > 1.0);
           } else {
             err_norm = sel(again, en, err_norm);
           }
@@ -1230,12 +1223,11 @@ struct WtPlantStep {
           vd fct = vmin(safety * pf, 10.0);
           const vb keep = (!recompute) & (fct < 1.2);
           fct = sel(keep, 1.0, fct);
-          lu_valid = lu_valid & !(acc & !keep);
-          need_jac = need_jac | (acc & recompute);
-          current_jac = selb(acc, vbroadcast_b(false), current_jac);  // set again by num_jac when recomputed
+          fclr(F_LU_VALID, acc & !keep);
+          fset(F_NEED_JAC, acc & recompute);
+          fclr(F_CURRENT_JAC, acc);  // set again by num_jac when recomputed
           self_h_abs_old = sel(acc, self_h_abs, self_h_abs_old);
           self_err_old = sel(acc, err_norm, self_err_old);
-          self_have_old = self_have_old | acc;
           self_h_abs = sel(acc, h_abs * fct, self_h_abs);
           WT_UNROLL
           for (int v = 0; v < 3; ++v) {
@@ -1248,10 +1240,9 @@ struct WtPlantStep {
           }
           sol_told = sel(acc, t, sol_told);
           sol_h = sel(acc, t_new - t, sol_h);
-          have_sol = have_sol | acc;
+          fset(F_SELF_HAVE_OLD | F_HAVE_SOL | F_NEW_STEP, acc);
           t = sel(acc, t_new, t);
-          new_step = new_step | acc;
-          cnt[WTC_NSTEPS] = cnt[WTC_NSTEPS] + seli(acc, 1, 0);
+          lu->cadd(WTC_NSTEPS, seli(acc, 1, 0));
         }
       }
     }
@@ -1265,9 +1256,9 @@ struct WtPlantStep {
 template <class LuStore>
 WT_DEV vi wt_finish_step(WtPlantStep<LuStore> &ps, const vd *y_in, vd *derived, vb &advance) {
   const WtGroup &g = ps.g;
-  vi st = seli(ps.failed, (int)WTS_SOLVER_FAILED, 0);
-  st = st | seli(ps.trange, (int)WTS_T_RANGE, 0) | seli(ps.worklimit, (int)WTS_WORK_LIMIT, 0);
-  advance = !(ps.trange | ps.worklimit);  // exception inside solve_ivp: state untouched, time not advanced
+  vi st = seli(ps.failed(), (int)WTS_SOLVER_FAILED, 0);
+  st = st | seli(ps.trange(), (int)WTS_T_RANGE, 0) | seli(ps.worklimit(), (int)WTS_WORK_LIMIT, 0);
+  advance = !(ps.trange() | ps.worklimit());  // exception inside solve_ivp: state untouched, time not advanced
   WT_UNROLL
   for (int v = 0; v < 3; ++v) ps.y[v] = sel(advance, ps.y[v], y_in[v]);
   vb nonfin = !(visfinite(ps.y[0]) & visfinite(ps.y[1]) & visfinite(ps.y[2]));

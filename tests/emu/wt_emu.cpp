@@ -17,6 +17,9 @@ struct EmuLu {
   void cput(int k, const vd &x) { cst[k] = x; }
   vd cget(int k) const { return cst[k]; }
   void csync() {}
+  vi cnt[WTC_NCNT];
+  void czero() { for (int k = 0; k < WTC_NCNT; ++k) cnt[k] = vbroadcast_i(0); }
+  void cadd(int k, const vi &inc) { cnt[k] = cnt[k] + inc; }
 };
 
 extern "C" {
@@ -48,6 +51,7 @@ void wt_emu_step_batch(int P, int n, int nsteps, double dt, const double *par, c
         for (int v = 0; v < 3; ++v) yin[v].v[l] = y[(size_t)pp * 3 * n + v * n + z];
       }
       ps.c = wt_make_const(&lu, ps.g, 110, vpar, vbnd);
+      lu.czero();
       for (int v = 0; v < 3; ++v) ps.y[v] = yin[v];
       ps.integrate(t0, vdt, on, max_attempts);
       vd der[3];
@@ -69,7 +73,7 @@ void wt_emu_step_batch(int P, int n, int nsteps, double dt, const double *par, c
           }
           if (status) status[p] = (uint32_t)st.v[l];
           if (counters)
-            for (int k = 0; k < WTC_NCNT; ++k) counters[(size_t)p * WTC_NCNT + k] += ps.cnt[k].v[l];
+            for (int k = 0; k < WTC_NCNT; ++k) counters[(size_t)p * WTC_NCNT + k] += lu.cnt[k].v[l];
         }
       }
     }

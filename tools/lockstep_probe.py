@@ -30,6 +30,7 @@ def warp_cost(c, order):
     return tot.sum().item() * gpw  # per-plant-equivalent
 
 prev = None
+prev2 = None
 for s in range(int(os.environ.get("STEPS", 8))):
     eng.reset_counters()
     eng.step(1.0, bnd)
@@ -46,6 +47,12 @@ for s in range(int(os.environ.get("STEPS", 8))):
         out["signature(prev)"] = warp_cost(c, torch.argsort(sig, descending=True)) / ideal
         sig2 = ((pn.long() * 16 + pl.long()) * 64 + pa.long()) * 4 + pj.long()
         out["sig-newton-first(prev)"] = warp_cost(c, torch.argsort(sig2, descending=True)) / ideal
+    if prev2 is not None:
+        pc2 = cost_of(prev2)[0]
+        out["max(prev,prev2)"] = warp_cost(c, torch.argsort(torch.maximum(pc, pc2), descending=True)) / ideal
+        out["prev+0.5prev2"] = warp_cost(c, torch.argsort(pc + 0.5 * pc2, descending=True)) / ideal
+        out["lexi(prev,prev2)"] = warp_cost(c, torch.argsort(pc * 1e6 + pc2, descending=True)) / ideal
     out["oracle(same step signature)"] = warp_cost(c, torch.argsort(cost_of(c)[0], descending=True)) / ideal
     print(s, " ".join(f"{k}={v:.3f}" for k, v in out.items()), flush=True)
+    prev2 = prev
     prev = c

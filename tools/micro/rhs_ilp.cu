@@ -11,6 +11,7 @@ struct SmemLu {
   __device__ __forceinline__ void cput(int k, double x) { cp[k] = x; }
   __device__ __forceinline__ double cget(int k) const { return cp[k]; }
   __device__ __forceinline__ void csync() { __syncwarp(); }
+  __device__ __forceinline__ void cadd(int, int) {}
 };
 template <int UNROLL>
 __global__ void __launch_bounds__(128, 2) k_rhs(double *out, int iters, int n, long long *clk) {
