@@ -45,6 +45,9 @@ struct SmemLu {
   }
   __device__ __forceinline__ void cadd(int k, int inc) { ci[k] += inc; }
   __device__ __forceinline__ int cval(int k) const { return ci[k]; }
+  // per-plant step-control scalars (WtPlantStep::PV_*), after the constants and the counters
+  __device__ __forceinline__ double pvget(int k) const { return cp[CK_N + WTC_NCNT / 2 + k]; }
+  __device__ __forceinline__ void pvput(int k, double x) { cp[CK_N + WTC_NCNT / 2 + k] = x; }
   // predicated store: an `if (mask)` here becomes a branch around each group of stores, and a branch ends
   // the basic block ptxas schedules in (the six factorizations of a PCR level then run one after the other)
   __device__ __forceinline__ void put(int slot, double x, bool mask) {
@@ -65,8 +68,10 @@ __host__ __device__ inline int wt_lu_slots(int n) {
 // + the lane-private constants (LK_*) kept after the LU multipliers
 __host__ __device__ inline int wt_lane_slots(int n) { return wt_lu_slots(n) + LK_N; }
 // doubles of shared memory per warp: LU slots for 32 lanes + constants for (32/n + 1) plants
-#define WT_PLANT_DOUBLES (CK_N + WTC_NCNT / 2)  // per-plant constants + the path counters (ints)
+#define WT_PLANT_DOUBLES (CK_N + WTC_NCNT / 2 + 10)  // per-plant constants + path counters (ints) + step-control scalars (PV_N)
 __host__ __device__ inline int wt_warp_smem_doubles(int n) { return wt_lane_slots(n) * 32 + (32 / n + 1) * WT_PLANT_DOUBLES; }
+
+static_assert(WtPlantStep<SmemLu>::PV_N == 10 && WTC_NCNT % 2 == 0, "per-plant store layout out of sync with WT_PLANT_DOUBLES");
 
 struct StepArgs {
   int P, n, n_steps, bnd_stride, max_attempts;

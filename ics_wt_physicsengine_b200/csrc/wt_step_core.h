@@ -519,7 +519,13 @@ struct WtPlantStep {
   vd W[3][3];     // W[k][var]
   vd Q[3][3];     // dense output, Q[var][k]   (radau.py:547-553)
   vd yold[3];
-  vd sol_told, sol_h;
+  // Per-plant step-control scalars live in the per-plant store (shared memory), not replicated in two
+  // registers per lane for the whole step: they are touched a few times per attempt, never in the Newton loop.
+  enum { PV_SELF_H = 0, PV_SELF_H_OLD, PV_SELF_ERR_OLD, PV_H_OLD, PV_ERR_OLD, PV_MIN_STEP, PV_SOL_TOLD, PV_SOL_H,
+         PV_T_BOUND, PV_MAX_STEP, PV_N };
+  WT_DEV vd pv(int k) const { return lu->pvget(k); }
+  WT_DEV void pvset(int k, vd x) { lu->pvput(k, x); }                          // every lane of the plant stores the same value
+  WT_DEV void pvset(int k, vd x, vb m) { lu->pvput(k, sel(m, x, lu->pvget(k))); }  // ... where m
 
   WT_DEV int slot_real(int sys) const { return sys * (2 * g.L + 1); }
   WT_DEV int slot_cplx(int sys) const { return 3 * (2 * g.L + 1) + sys * (4 * g.L + 2); }
@@ -920,12 +926,12 @@ struct WtPlantStep {
   WT_DEV void integrate(vd t0, vd dt, vb plant_on, int max_attempts) {
     if (max_attempts <= 0 || max_attempts > WT_HARD_MAX_ATTEMPTS) max_attempts = WT_HARD_MAX_ATTEMPTS;
     vd t = t0;
-    const vd t_bound = t0 + dt;
-    const vd max_step = vmin(dt, 10.0);
+    pvset(PV_T_BOUND, t0 + dt);
+    pvset(PV_MAX_STEP, vmin(dt, 10.0));
     // running = plant_on; current_jac and new_step start true (radau.py:363-369, :413)
     fl = seli(plant_on, (int)F_RUNNING, 0) | (int)(F_CURRENT_JAC | F_NEW_STEP);
-    sol_told = vbroadcast(0.0);
-    sol_h = vbroadcast(1.0);
+    pvset(PV_SOL_TOLD, vbroadcast(0.0));
+    pvset(PV_SOL_H, vbroadcast(1.0));
     WT_UNROLL
     for (int v = 0; v < 3; ++v) {
       jfac[v] = vbroadcast(0.0);
@@ -941,12 +947,12 @@ struct WtPlantStep {
     }
 
     // ---- Radau.__init__: f0 and select_initial_step (radau.py:303-311, common.py:68-134)
-    vd self_h_abs;
+    vd h_abs;
     {
       // f0 = f(y) and f1 = f(y + h0 f0) go through ONE rolled copy of the RHS (instruction-fetch bound kernel)
       vd sc[3], yy[3], fo[3];  // sc = 1 / scale
       vd d1 = vbroadcast(0.0), h0 = vbroadcast(0.0);
-      const vd interval = vabs(t_bound - t0);
+      const vd interval = vabs(pv(PV_T_BOUND) - t0);
       WT_UNROLL
       for (int v = 0; v < 3; ++v) { yy[v] = y[v]; sc[v] = wt_rcp(WT_ATOL + vabs(y[v]) * WT_RTOL); }
       WT_NOUNROLL
@@ -968,14 +974,17 @@ struct WtPlantStep {
       }
       vd d2 = wt_div(rms3((fo[0] - f[0]) * sc[0], (fo[1] - f[1]) * sc[1], (fo[2] - f[2]) * sc[2]), h0);
       vd h1 = sel((d1 <= 1e-15) & (d2 <= 1e-15), vmax(h0 * 1e-3, 1e-6), vsqrt(vsqrt(wt_div(0.01, vmax(d1, d2)))));
-      self_h_abs = vmin(vmin(100.0 * h0, h1), vmin(interval, max_step));
+      h_abs = vmin(vmin(100.0 * h0, h1), vmin(interval, pv(PV_MAX_STEP)));
+      pvset(PV_SELF_H, h_abs);
     }
     fclr(F_RUNNING, trange());
 
-    vd self_h_abs_old = vbroadcast(0.0), self_err_old = vbroadcast(0.0);
+    pvset(PV_SELF_H_OLD, vbroadcast(0.0));
+    pvset(PV_SELF_ERR_OLD, vbroadcast(0.0));
     fset(F_NEED_JAC, fget(F_RUNNING));  // first Jacobian (radau.py:363-369)
-    vd h_abs = self_h_abs, h_abs_old = vbroadcast(0.0), err_old = vbroadcast(0.0);
-    vd min_step = vbroadcast(0.0);
+    pvset(PV_H_OLD, vbroadcast(0.0));
+    pvset(PV_ERR_OLD, vbroadcast(0.0));
+    pvset(PV_MIN_STEP, vbroadcast(0.0));
 
     vi attempts = vbroadcast_i(0);
     while (wt_cta_any(vany(fget(F_RUNNING)))) {
@@ -990,7 +999,7 @@ struct WtPlantStep {
         }
       }
       // base.py:204-208: finished once t reached t_bound
-      fclr(F_RUNNING, t == t_bound);
+      fclr(F_RUNNING, t == pv(PV_T_BOUND));
 #ifndef WT_CTA_LOCKSTEP
       if (!vany(fget(F_RUNNING))) break;
 #endif
@@ -999,23 +1008,27 @@ struct WtPlantStep {
       {
         vb m = fget(F_RUNNING) & fget(F_NEW_STEP);
         vd ms = 10.0 * vabs(vnextafter_up(t) - t);
-        min_step = sel(m, ms, min_step);
+        pvset(PV_MIN_STEP, ms, m);
+        const vd self_h_abs = pv(PV_SELF_H), max_step = pv(PV_MAX_STEP);
         vb big = self_h_abs > max_step, small = self_h_abs < ms;
         vd hh_ = sel(big, max_step, sel(small, ms, self_h_abs));
         h_abs = sel(m, hh_, h_abs);
-        h_abs_old = sel(m, self_h_abs_old, h_abs_old);
-        err_old = sel(m, self_err_old, err_old);
+        pvset(PV_H_OLD, pv(PV_SELF_H_OLD), m);
+        pvset(PV_ERR_OLD, pv(PV_SELF_ERR_OLD), m);
         fclr(F_HAVE_OLD | F_REJECTED | F_NEW_STEP, m);
         fset(F_HAVE_OLD, m & fget(F_SELF_HAVE_OLD) & !(big | small));
       }
       // (3) attempt setup (radau.py:439-457)
       {
-        vb f_ = fget(F_RUNNING) & (h_abs < min_step);
+        vb f_ = fget(F_RUNNING) & (h_abs < pv(PV_MIN_STEP));
         fset(F_FAILED, f_);
         fclr(F_RUNNING, f_);
       }
       vd t_new = t + h_abs;
-      t_new = sel(t_new - t_bound > 0.0, t_bound, t_new);
+      {
+        const vd t_bound = pv(PV_T_BOUND);
+        t_new = sel(t_new - t_bound > 0.0, t_bound, t_new);
+      }
       const vd h = t_new - t;
       h_abs = sel(fget(F_RUNNING), vabs(h), h_abs);
       vd scale[3];  // 1 / (atol + |y| rtol)
@@ -1023,7 +1036,7 @@ struct WtPlantStep {
       for (int v = 0; v < 3; ++v) scale[v] = wt_rcp(WT_ATOL + vabs(y[v]) * WT_RTOL);
       const vd ih = wt_rcp(h);
       {
-        const vd isolh = wt_rcp(sol_h);
+        const vd isolh = wt_rcp(pv(PV_SOL_H)), sol_told = pv(PV_SOL_TOLD);
         const vb hs = fget(F_HAVE_SOL);
         // Z0 = sol(t + h*C).T - y, W = TI.dot(Z0)   (radau.py:451-454, 555-578, :64)
         vd x0 = ((t + h * WT_C0) - sol_told) * isolh;
@@ -1185,7 +1198,7 @@ struct WtPlantStep {
           } else {
             const vb rej = cv & (err_norm > 1.0);
             acc = cv & !rej;
-            pf = predict_factor(h_abs, h_abs_old, err_norm, err_old, fget(F_HAVE_OLD));
+            pf = predict_factor(h_abs, pv(PV_H_OLD), err_norm, pv(PV_ERR_OLD), fget(F_HAVE_OLD));
             h_abs = sel(rej, h_abs * vmax(safety * pf, 0.2), h_abs);
             fclr(F_LU_VALID, rej);
             fset(F_REJECTED, rej);
@@ -1226,9 +1239,9 @@ struct WtPlantStep {
           fclr(F_LU_VALID, acc & !keep);
           fset(F_NEED_JAC, acc & recompute);
           fclr(F_CURRENT_JAC, acc);  // set again by num_jac when recomputed
-          self_h_abs_old = sel(acc, self_h_abs, self_h_abs_old);
-          self_err_old = sel(acc, err_norm, self_err_old);
-          self_h_abs = sel(acc, h_abs * fct, self_h_abs);
+          pvset(PV_SELF_H_OLD, pv(PV_SELF_H), acc);
+          pvset(PV_SELF_ERR_OLD, err_norm, acc);
+          pvset(PV_SELF_H, h_abs * fct, acc);
           WT_UNROLL
           for (int v = 0; v < 3; ++v) {
             Q[v][0] = sel(acc, (Z[0][v] * WT_P00 + Z[1][v] * WT_P10) + Z[2][v] * WT_P20, Q[v][0]);
@@ -1238,8 +1251,8 @@ struct WtPlantStep {
             y[v] = sel(acc, y_new[v], y[v]);
             f[v] = sel(acc, F[v], f[v]);
           }
-          sol_told = sel(acc, t, sol_told);
-          sol_h = sel(acc, t_new - t, sol_h);
+          pvset(PV_SOL_TOLD, t, acc);
+          pvset(PV_SOL_H, t_new - t, acc);
           fset(F_SELF_HAVE_OLD | F_HAVE_SOL | F_NEW_STEP, acc);
           t = sel(acc, t_new, t);
           lu->cadd(WTC_NSTEPS, seli(acc, 1, 0));

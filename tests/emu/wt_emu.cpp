@@ -18,6 +18,9 @@ struct EmuLu {
   vd cget(int k) const { return cst[k]; }
   void csync() {}
   vi cnt[WTC_NCNT];
+  vd pvs[16];
+  vd pvget(int k) const { return pvs[k]; }
+  void pvput(int k, const vd &x) { pvs[k] = x; }
   void czero() { for (int k = 0; k < WTC_NCNT; ++k) cnt[k] = vbroadcast_i(0); }
   void cadd(int k, const vi &inc) { cnt[k] = cnt[k] + inc; }
 };

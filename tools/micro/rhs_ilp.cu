@@ -12,6 +12,8 @@ struct SmemLu {
   __device__ __forceinline__ double cget(int k) const { return cp[k]; }
   __device__ __forceinline__ void csync() { __syncwarp(); }
   __device__ __forceinline__ void cadd(int, int) {}
+  __device__ __forceinline__ double pvget(int) const { return 0.0; }
+  __device__ __forceinline__ void pvput(int, double) {}
 };
 template <int UNROLL>
 __global__ void __launch_bounds__(128, 2) k_rhs(double *out, int iters, int n, long long *clk) {
