@@ -294,8 +294,6 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_ach = bytes_alg(timed_plant_steps, N_ZONES) / world / (step_ms * 1e-3) / 1e9
 
-    pass
-
     cpu = None
     if not args.no_cpu_baseline and world == 1:   # rank 0 at N=1 only
         cpu = cpu_baseline(args)
@@ -316,10 +314,10 @@ def main():
         "roofline": {
             "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": achieved_tf / fp64_peak if fp64_peak else None,
-            # dram__bytes_read+write of one wt_step launch: 86.5 B per plant-zone-step measured by ncu --set full on
-            # the 262,144-plant launch (profiles/r1_step_kernel_v3_final.txt), scaled to this launch's units
-            "traffic": 86.5 * (timed_plant_steps / max(1, args.steps)) * N_ZONES / world,
-            "traffic_source": "ncu capture of the 262144-plant launch scaled by units (profiles/r1_step_kernel_v3_final.txt)",
+            # dram__bytes_read+write of one wt_step launch: 82.2 B per plant-zone-step measured by ncu --set full on
+            # the 262,144-plant launch (profiles/r1_step_kernel_v4_session2.txt), scaled to this launch's units
+            "traffic": 82.2 * (timed_plant_steps / max(1, args.steps)) * N_ZONES / world,
+            "traffic_source": "ncu capture of the 262144-plant launch scaled by units (profiles/r1_step_kernel_v4_session2.txt)",
             "peak_source": "measured in this run by wt_measure_fp64_peak (8 independent DFMA chains/thread); "
                            "MEASURED_PEAKS.json carries no FP64 figure",
             "flops_model": "SURVEY 8(d): 310(nfev+9njev)+950(nlu/2)+740 newton+240 steps+900 per zone, from emitted counters",
