@@ -273,8 +273,8 @@ def main():
         dist.all_reduce(e2e_max, op=dist.ReduceOp.MAX)
     e2e = {"value": float(e2e_agg[0]) * N_ZONES * k_e2e / float(e2e_max[1]), "unit": UNIT,
            "h2d_bytes_per_step": int(e2e_agg[2]), "d2h_bytes_per_step": int(e2e_agg[3]), "steps": k_e2e,
-           "api": "wt_step_host (C ABI, pinned host buffers: H2D of state+boundary, step, D2H of state+time+flow+status per call; "
-                  "per-plant constants resident after the first call)", "n_gpus": world}
+           "api": "wt_step_host (C ABI, pinned host buffers: H2D of state+boundary, step, D2H of state+time+flow+status per call, "
+                  "pipelined over column slabs on three streams; per-plant constants resident after the first call)", "n_gpus": world}
 
     if rank != 0:
         if world > 1:

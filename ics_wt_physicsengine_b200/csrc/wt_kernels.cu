@@ -75,6 +75,7 @@ static_assert(WtPlantStep<SmemLu>::PV_N == 10 && WTC_NCNT % 2 == 0, "per-plant s
 
 struct StepArgs {
   int P, n, n_steps, bnd_stride, max_attempts;
+  int ld;                // row stride of every SoA array (= P unless a column slab of a larger ensemble is stepped)
   double dt;
   const double *par, *bnd;
   double *time, *y, *flow, *derived;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
   const bool in_plant = gi < gpw && pl < a.P;
   const int p = in_plant ? (a.order ? a.order[pl] : (int)pl) : 0;
   const int z = in_plant ? lane - gi * n : 0;
-  const size_t P = (size_t)a.P;
+  const size_t P = (size_t)a.ld;  // row stride; a.P bounds the plant index
 
   // Every global load of the launch is issued here, back to back and before the first use: the prologue
   // then waits for ONE round trip to HBM instead of one per dependent group (status -> params -> state).
@@ -393,7 +394,7 @@ int wt_advance(int P, int n, int n_steps, double dt, const double *par, const do
   if (!par || !bnd || !time || !y || !status) return set_err(WT_ERR_BAD_ARG, "null device pointer");
   if (bnd_stride != 0 && bnd_stride != P) return set_err(WT_ERR_BAD_ARG, "bnd_stride must be 0 or P");
   StepArgs a;
-  a.P = P; a.n = n; a.n_steps = n_steps; a.bnd_stride = bnd_stride; a.max_attempts = max_attempts;
+  a.P = P; a.ld = P; a.n = n; a.n_steps = n_steps; a.bnd_stride = bnd_stride; a.max_attempts = max_attempts;
   a.dt = dt; a.par = par; a.bnd = bnd; a.time = time; a.y = y; a.flow = flow; a.derived = derived;
   a.status = status; a.counters = counters; a.order = order; a.cost = cost;
   return launch_step(a, (cudaStream_t)stream);
@@ -514,6 +515,7 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
   if (rc) return rc;
   if (!par || !bnd || !time || !y || !status) return set_err(WT_ERR_BAD_ARG, "null host pointer");
   if (bnd_stride != 0 && bnd_stride != P) return set_err(WT_ERR_BAD_ARG, "bnd_stride must be 0 or P");
+  if (!(dt > 0.0)) return set_err(WT_ERR_BAD_ARG, "dt must be positive");
   const size_t Pz = (size_t)P;
   const size_t b_par = WT_NPAR * Pz * 8, b_bnd = WT_NBND * (bnd_stride ? Pz : 1) * 8, b_t = Pz * 8,
                b_y = 3 * (size_t)n * Pz * 8, b_f = Pz * 8, b_s = Pz * 4;
@@ -535,23 +537,62 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
   double *d_y = (double *)q; q += al(b_y);
   double *d_f = (double *)q; q += al(b_f);
   uint32_t *d_s = (uint32_t *)q;
-  cudaStream_t s = 0;
   // WT_HOST_PARAMS_RESIDENT: the derived constants uploaded by the previous call (same P, n) are reused
   static int res_P = 0, res_n = 0;
-  if (!(flags & 1) || res_P != P || res_n != n) cudaMemcpyAsync(d_par, par, b_par, cudaMemcpyHostToDevice, s);
+  const bool up_par = !(flags & 1) || res_P != P || res_n != n;
   res_P = P; res_n = n;
-  cudaMemcpyAsync(d_bnd, bnd, b_bnd, cudaMemcpyHostToDevice, s);
-  cudaMemcpyAsync(d_t, time, b_t, cudaMemcpyHostToDevice, s);
-  cudaMemcpyAsync(d_y, y, b_y, cudaMemcpyHostToDevice, s);
-  cudaMemcpyAsync(d_s, status, b_s, cudaMemcpyHostToDevice, s);
-  if (flow) cudaMemcpyAsync(d_f, flow, b_f, cudaMemcpyHostToDevice, s);
-  rc = wt_step(P, n, dt, d_par, d_bnd, bnd_stride, d_t, d_y, flow ? d_f : nullptr, nullptr, d_s, nullptr, max_attempts, s);
-  if (rc) return rc;
-  cudaMemcpyAsync(time, d_t, b_t, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(y, d_y, b_y, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(status, d_s, b_s, cudaMemcpyDeviceToHost, s);
-  if (flow) cudaMemcpyAsync(flow, d_f, b_f, cudaMemcpyDeviceToHost, s);
-  return cuda_err(cudaStreamSynchronize(s), "wt_step_host");
+
+  // Pipelined over column slabs of the SoA arrays: slab c's H2D copies, its kernel and its D2H copies go to
+  // stream c % 3, so the copies of one slab overlap the kernel of another (PCIe is full duplex and the
+  // device has separate copy engines per direction).  A slab of plants is a column range of every row:
+  // 2-D copies with the row pitch P.  Plants are independent, so slabs need no ordering among themselves.
+  enum { NSTREAM = 3 };
+  static cudaStream_t st[NSTREAM] = {nullptr, nullptr, nullptr};
+  if (!st[0]) {
+    for (int i = 0; i < NSTREAM; ++i) {
+      cudaError_t e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+      if (e != cudaSuccess) return cuda_err(e, "cudaStreamCreate");
+    }
+  }
+  int slabs = P / 32768;
+  if (slabs < 1) slabs = 1;
+  if (slabs > 16) slabs = 16;
+  const int per = ((P + slabs - 1) / slabs + 31) & ~31;  // plants per slab, a multiple of the warp width
+  const size_t pitch = Pz * 8;
+  if (!bnd_stride) {  // one broadcast boundary row: uploaded once, the other streams wait for it
+    static cudaEvent_t ev = nullptr;
+    if (!ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    cudaMemcpyAsync(d_bnd, bnd, b_bnd, cudaMemcpyHostToDevice, st[0]);
+    cudaEventRecord(ev, st[0]);
+    for (int i = 1; i < NSTREAM; ++i) cudaStreamWaitEvent(st[i], ev, 0);
+  }
+  for (int c = 0; c * per < P; ++c) {
+    const int p0 = c * per, w = (P - p0 < per) ? P - p0 : per;
+    cudaStream_t s = st[c % NSTREAM];
+    const size_t wb = (size_t)w * 8;
+    if (up_par) cudaMemcpy2DAsync(d_par + p0, pitch, par + p0, pitch, wb, WT_NPAR, cudaMemcpyHostToDevice, s);
+    if (bnd_stride) cudaMemcpy2DAsync(d_bnd + p0, pitch, bnd + p0, pitch, wb, WT_NBND, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_t + p0, time + p0, wb, cudaMemcpyHostToDevice, s);
+    cudaMemcpy2DAsync(d_y + p0, pitch, y + p0, pitch, wb, 3 * (size_t)n, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_s + p0, status + p0, (size_t)w * 4, cudaMemcpyHostToDevice, s);
+    if (flow) cudaMemcpyAsync(d_f + p0, flow + p0, wb, cudaMemcpyHostToDevice, s);
+    StepArgs a;
+    a.P = w; a.ld = P; a.n = n; a.n_steps = 1; a.bnd_stride = bnd_stride; a.max_attempts = max_attempts;
+    a.dt = dt; a.par = d_par + p0; a.bnd = bnd_stride ? d_bnd + p0 : d_bnd; a.time = d_t + p0; a.y = d_y + p0;
+    a.flow = flow ? d_f + p0 : nullptr; a.derived = nullptr; a.status = d_s + p0; a.counters = nullptr;
+    a.order = nullptr; a.cost = nullptr;
+    rc = launch_step(a, s);
+    if (rc) return rc;
+    cudaMemcpyAsync(time + p0, d_t + p0, wb, cudaMemcpyDeviceToHost, s);
+    cudaMemcpy2DAsync(y + p0, pitch, d_y + p0, pitch, wb, 3 * (size_t)n, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(status + p0, d_s + p0, (size_t)w * 4, cudaMemcpyDeviceToHost, s);
+    if (flow) cudaMemcpyAsync(flow + p0, d_f + p0, wb, cudaMemcpyDeviceToHost, s);
+  }
+  for (int i = 0; i < NSTREAM; ++i) {
+    rc = cuda_err(cudaStreamSynchronize(st[i]), "wt_step_host");
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 int wt_measure_fp64_peak(double *tflops_out, int iters) {

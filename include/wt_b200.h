@@ -117,7 +117,9 @@ int wt_derivatives(int P, int n_zones, const double *par_dev, const double *bnd_
  * state / boundary (and the constants) in, runs wt_step, copies state / time / flow / status back,
  * and waits for completion.  All pointers are HOST pointers with the SoA layouts above;
  * bnd_stride is P or 0.  flags: WT_HOST_PARAMS_RESIDENT = the per-plant constants `par` are
- * unchanged since the previous call with the same (P, n_zones) and are not uploaded again. */
+ * unchanged since the previous call with the same (P, n_zones) and are not uploaded again.
+ * Internally the call is pipelined over column slabs of the arrays on three streams (H2D of one slab
+ * overlaps the kernel of another and the D2H of a third); pinned host buffers are needed for the overlap. */
 #define WT_HOST_PARAMS_RESIDENT 1
 int wt_step_host(int P, int n_zones, double dt, const double *par, const double *bnd,
                  int bnd_stride, double *time, double *y, double *flow_rate, uint32_t *status,

@@ -311,3 +311,36 @@ def test_sorted_scheduling_does_not_change_results():
     assert torch.equal(a.state.temperature, b.state.temperature) and torch.equal(a.status, b.status)
     assert torch.equal(a.counters, b.counters) and torch.equal(a.state.time, b.state.time)
     assert b._order is not None and sorted(b._order.cpu().tolist()) == list(range(30011))
+
+
+@pytest.mark.parametrize("P,bcast", [(33, False), (70001, False), (70001, True), (131072 + 77, False)])
+def test_host_buffer_entry_point_equals_the_device_path(P, bcast):
+    """wt_step_host (host SoA buffers in, pipelined over column slabs on three streams) runs the same kernel
+    as the device-resident path: bit-identical state, time, flow and status, for ragged sizes, one and several
+    slabs, per-plant and broadcast boundaries, repeated calls with the constants kept resident."""
+    import ctypes as C
+
+    from ics_wt_physicsengine_b200 import _lib
+    n = 10
+    e = ens.config2(P, n, seed=4242)
+    eng = PlantEnsemble(e, max_attempts=CAP)
+    bnd_rows = np.ascontiguousarray(e.bnd[0]) if bcast else np.ascontiguousarray(e.bnd)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    par = pin(eng.par_host.T)
+    bnd = pin(bnd_rows if bcast else bnd_rows.T)
+    y = pin(np.stack([e.pH0.T, e.Cl0.T, e.T0.T]))
+    t = torch.zeros(P, dtype=torch.float64).pin_memory()
+    flow = torch.zeros(P, dtype=torch.float64).pin_memory()
+    st = torch.zeros(P, dtype=torch.int32).pin_memory()
+    p = lambda x: C.c_void_p(x.data_ptr())
+    for k in range(3):
+        rc = _lib.lib().wt_step_host(P, n, 1.0, p(par), p(bnd), 0 if bcast else P, p(t), p(y), p(flow), p(st), CAP,
+                                     1 if k else 0)
+        _lib.check(rc, "wt_step_host")
+        eng.step(1.0, bnd_rows)
+        torch.cuda.synchronize()
+        assert np.array_equal(y.numpy().reshape(3 * n, P).T, eng.state_numpy())
+        assert np.array_equal(t.numpy(), eng.state.time.cpu().numpy())
+        assert np.array_equal(st.numpy(), eng.status.cpu().numpy())
+        live = (st.numpy() & HALT) == 0
+        assert np.array_equal(flow.numpy()[live], eng.state.flow_rate.cpu().numpy()[live])
