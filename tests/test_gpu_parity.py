@@ -344,3 +344,32 @@ def test_host_buffer_entry_point_equals_the_device_path(P, bcast):
         assert np.array_equal(st.numpy(), eng.status.cpu().numpy())
         live = (st.numpy() & HALT) == 0
         assert np.array_equal(flow.numpy()[live], eng.state.flow_rate.cpu().numpy()[live])
+
+
+def test_pipelined_shard_equals_one_ensemble():
+    """A shard run as independent sub-ensembles on their own CUDA streams (partition.PipelinedShard) gives
+    bit-identical plant states, sensor readings (noise is keyed by the global plant id) and statistics."""
+    from ics_wt_physicsengine_b200.partition import EnsembleStatistics, PipelinedShard
+    from ics_wt_physicsengine_b200.sensors import create_realistic_sensor_suite
+    P, n = 3001, 10
+    e = ens.config2(P, n, seed=99)
+    one = PlantEnsemble(e, max_attempts=CAP)
+    suite = create_realistic_sensor_suite(one, seed=7, plant0=1000)
+    suite.initialize(0.0)
+    st = EnsembleStatistics(one)
+    sh = PipelinedShard(e, parts=3, plant0=1000, sensor_seed=7, max_attempts=CAP)
+    sh.initialize_sensors(0.0)
+    for k in range(5):
+        one.step(1.0, e.bnd)
+        suite.read(one.state, float(k))
+        sh.step(1.0, read_time=float(k))
+    v = sh.stats().clone()
+    torch.cuda.synchronize()
+    got = np.concatenate([x.state_numpy() for x in sh.engines])
+    assert np.array_equal(got, one.state_numpy())
+    assert np.array_equal(np.concatenate([x.status.cpu().numpy() for x in sh.engines]), one.status.cpu().numpy())
+    assert np.array_equal(torch.cat([s._out for s in sh.suites], dim=2).cpu().numpy(), suite._out.cpu().numpy(),
+                          equal_nan=True), "sensor readings differ"  # warming-up sensors read NaN
+    assert torch.equal(torch.cat([s._out_status for s in sh.suites], dim=1), suite._out_status)
+    w = st.local()
+    assert torch.allclose(v, w, rtol=1e-13, atol=1e-9)  # additive vector; only the summation order differs
