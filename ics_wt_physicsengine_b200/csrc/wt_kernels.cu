@@ -337,6 +337,92 @@ __global__ void wt_stats_final_kernel(int nblocks, int nstat, const double *part
   out[k] = accumulate ? out[k] + s : s;
 }
 
+// ---------------------------------------------------------------------------------------
+// K5: per-plant diagnostics: one thread per plant walks its zone rows
+// (coalesced across the plants of a warp).  HBM-bound: reads 3n (+n) doubles, writes WT_NDIAG (+ n-1).
+// Two-pass mean / population std as numpy's mean / std (reactor.py:570-611, transport.py:338-384,
+// spatial.py:322-379, 440-477).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) wt_diagnostics_kernel(int P, int n, const double *par, const double *y,
+                                                             const double *hc, double *out, double *n2, int32_t *bad) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const size_t Pz = (size_t)P;
+  const double zh = par[(size_t)WTP_ZH * Pz + p], volume = par[(size_t)WTP_VOLUME * Pz + p];
+  const bool strat = par[(size_t)WTP_STRAT * Pz + p] != 0.0;
+  const double zone_volume = volume / n, inv_n = 1.0 / n;
+  auto Y = [&](int v, int z) { return y[((size_t)v * n + z) * Pz + p]; };
+  auto O = [&](int k, double x) { out[(size_t)k * Pz + p] = x; };
+  // validate_conservation
+  const double T0 = Y(2, 0);
+  if (bad) bad[p] = (T0 < 0.0 || T0 > 100.0) ? 1 : 0;
+  const double Kw = 1.0e-14 * exp((55900.0 / 8.314) * (1.0 / 298.15 - 1.0 / (T0 + 273.15)));
+  double sH = 0.0, sOH = 0.0;
+  for (int z = 0; z < n; ++z) {
+    const double H = hc ? hc[(size_t)z * Pz + p] : exp10(-Y(0, z));
+    sH += H;
+    sOH += Kw / H;
+  }
+  const double tH = sH * zone_volume / 1000, tOH = sOH * zone_volume / 1000;
+  O(WT_DG_TOTAL_H_MOL, tH);
+  O(WT_DG_TOTAL_OH_MOL, tOH);
+  O(WT_DG_CHARGE_BALANCE_MOL, tH - tOH);
+  // spatial statistics of the three variables
+  for (int v = 0; v < 3; ++v) {
+    double s = 0.0, mx = -INFINITY, mn = INFINITY, gmax = -1.0, gsum = 0.0, prev = 0.0, sdev = 0.0;
+    int gloc = 0;
+    for (int z = 0; z < n; ++z) {
+      const double x = Y(v, z);
+      s += x;
+      mx = fmax(mx, x);  // np.max / np.min propagate NaN; a NaN state is reported by the step's status word
+      mn = fmin(mn, x);
+      if (z > 0) {
+        const double g = fabs((x - prev) / zh);
+        gsum += g;
+        if (g > gmax) { gmax = g; gloc = z - 1; }  // np.argmax: first maximum
+      }
+      prev = x;
+    }
+    const double mean = s * inv_n;
+    double thermal = 0.0;
+    for (int z = 0; z < n; ++z) {
+      const double x = Y(v, z), d = x - mean;
+      sdev += d * d;
+      thermal += x - 20.0;
+    }
+    const double sd = sqrt(sdev * inv_n);
+    const int k = WT_DG_GRAD0 + 8 * v;
+    O(k + 0, mean); O(k + 1, sd); O(k + 2, mx); O(k + 3, mn); O(k + 4, mx - mn);
+    O(k + 5, gmax); O(k + 6, gsum / (n - 1)); O(k + 7, (double)gloc);
+    if (v == 1) {  // chlorine: total mass + calculate_mixing_quality
+      O(WT_DG_TOTAL_CL_MG, s * zone_volume);
+      O(WT_DG_CL_CV, mean > 0.0 ? sd / mean : 0.0);
+      const double vs = mean * mean;
+      O(WT_DG_CL_SEGREGATION, vs > 0.0 ? fmin(fmax((sd * sd) / vs, 0.0), 1.0) : 0.0);
+    }
+    if (v == 2) {  // temperature: thermal energy relative to 20 C, thermocline
+      O(WT_DG_THERMAL_ENERGY_KJ, 998.2 * 4184 * (volume / 1000) * (thermal * inv_n) / 1000);
+      O(WT_DG_THERMOCLINE_DEPTH, (strat && gmax > 0.5) ? zh * n - (gloc + 0.5) * zh : nan(""));
+    }
+  }
+  // Brunt-Vaisala N^2 per interface
+  double n2max = -INFINITY, n2min = INFINITY, rho_prev = 0.0;
+  for (int z = 0; z < n; ++z) {
+    const double T = Y(2, z);
+    const double d4 = T - 4.0;
+    const double rho = T <= 8.0 ? 999.97 - 0.008 * (d4 * d4) : 998.2 - 2.1e-4 * 998.2 * (T - 20.0);
+    if (z > 0) {
+      const double v = -(9.81 / (0.5 * (rho_prev + rho))) * ((rho - rho_prev) / zh);
+      if (n2) n2[(size_t)(z - 1) * Pz + p] = v;
+      n2max = fmax(n2max, v);
+      n2min = fmin(n2min, v);
+    }
+    rho_prev = rho;
+  }
+  O(WT_DG_N2_MAX, n2max);
+  O(WT_DG_N2_MIN, n2min);
+}
+
 // 8 independent DFMA chains per thread: saturates the FP64 pipe without memory traffic
 __global__ void wt_dfma_peak_kernel(double *out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -430,6 +516,15 @@ int wt_calc_ph(int P, const double *alk, const double *ct, const double *temp, c
   return cuda_err(cudaGetLastError(), "wt_calc_ph_kernel launch");
 }
 
+
+int wt_diagnostics(int P, int n, const double *par, const double *y, const double *h, double *out, double *n2,
+                   int32_t *bad, void *stream) {
+  int rc = check_common(P, n);
+  if (rc) return rc;
+  if (!par || !y || !out) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  wt_diagnostics_kernel<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, n, par, y, h, out, n2, bad);
+  return cuda_err(cudaGetLastError(), "wt_diagnostics_kernel launch");
+}
 
 int wt_stats_size(int n) { return WT_STATS_HDR + 6 * n; }
 int wt_stats_scratch_doubles(int n) { return 1024 * (WT_STATS_HDR + 6 * n); }

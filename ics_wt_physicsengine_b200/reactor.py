@@ -21,6 +21,16 @@ from . import _lib
 from .ensembles import BND_FIELDS, CFG_FIELDS, NBND, NCFG, Ensemble
 from .params import NPAR, derive_params, validate_cfg
 
+# rows of wt_diagnostics (WT_DG_* of include/wt_b200.h)
+DIAG_FIELDS = (
+    "total_chlorine_mg", "total_H_mol", "total_OH_mol", "charge_balance_mol", "thermal_energy_kJ",
+    "chlorine_cv", "chlorine_segregation",
+    *[f"{v}_{k}" for v in ("pH", "chlorine", "temperature")
+      for k in ("mean_value", "std_value", "max_value", "min_value", "range", "max_gradient", "mean_gradient",
+                "gradient_location")],
+    "thermocline_depth", "brunt_vaisala_max", "brunt_vaisala_min",
+)
+
 logger = logging.getLogger(__name__)
 
 
@@ -318,6 +328,27 @@ class PlantEnsemble:
         _lib.check(rc, "wt_derivatives")
         return dy, bad
 
+    def diagnostics(self, with_n2: bool = False):
+        """Per-plant diagnostics of the current state in one kernel: validate_conservation
+        (reactor.py:570-611), calculate_mixing_quality of chlorine (transport.py:338-384),
+        calculate_spatial_gradients of pH / chlorine / temperature (spatial.py:440-477), identify_thermocline
+        (NaN where the reference returns None, spatial.py:353-379) and the Brunt-Vaisala N^2 extremes
+        (spatial.py:322-351).  Returns {field: tensor[P]} (+ "n2": [n-1, P] and "bad": [P] with ``with_n2``)."""
+        P, n = self.n_plants, self.n_zones
+        out = torch.empty((len(DIAG_FIELDS), P), dtype=torch.float64, device=self.device)
+        n2 = torch.empty((n - 1, P), dtype=torch.float64, device=self.device) if with_n2 else None
+        bad = torch.zeros(P, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = _lib.lib().wt_diagnostics(P, n, _ptr(self._par), _ptr(self._y), _ptr(self._derived[0]), _ptr(out),
+                                           _ptr(n2), _ptr(bad), C.c_void_p(stream))
+        _lib.check(rc, "wt_diagnostics")
+        res = {k: out[i] for i, k in enumerate(DIAG_FIELDS)}
+        res["bad"] = bad
+        if with_n2:
+            res["n2"] = n2
+        return res
+
 
 class IntegratedCSTR:
     """Drop-in for ``wt_simulator.core.reactor.IntegratedCSTR`` (reactor.py:189-611), one plant.
@@ -371,6 +402,19 @@ class IntegratedCSTR:
         if int(bad[0]):
             raise ValueError("Temperature outside liquid water range [0.0, 100.0]°C")
         return dy.reshape(3 * n).cpu().numpy()
+
+    def validate_conservation(self):
+        """reactor.py:570-611 for this plant, computed by the batched diagnostics kernel."""
+        e, s = self._ens, self.state
+        e.set_state(s.pH[None, :], s.chlorine[None, :], s.temperature[None, :], time=[s.time])
+        d = e.diagnostics()
+        if int(d["bad"][0]):
+            raise ValueError("Temperature outside liquid water range [0.0, 100.0]°C (thermodynamics.py:146-157)")
+        out = {k: float(d[k][0]) for k in ("total_chlorine_mg", "total_H_mol", "total_OH_mol", "charge_balance_mol",
+                                           "thermal_energy_kJ")}
+        out["zones"] = self.config.n_zones
+        out["timestamp"] = s.time
+        return out
 
     def get_state_at_location(self, zone_idx: int, parameter: str) -> float:
         """reactor.py:543-568"""

@@ -135,6 +135,27 @@ int wt_calc_ph(int P, const double *alk_dev, const double *ct_dev, const double 
                void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Per-plant diagnostics as one pass over the resident state.  Replaces,
+ * for every plant of the ensemble at once:
+ *   IntegratedCSTR.validate_conservation              reactor.py:570-611
+ *   TransportModel.calculate_mixing_quality(chlorine) transport.py:338-384
+ *   SpatialModel.calculate_spatial_gradients(x)       spatial.py:440-477    x = pH, chlorine, temperature
+ *   SpatialModel.identify_thermocline                 spatial.py:353-379    (None -> NaN)
+ *   SpatialModel.calculate_brunt_vaisala_frequency(i) spatial.py:322-351    on the density of the current T
+ *   out[k * P + p], k = WT_DG_*;  n2_dev[i * P + p] (optional, may be NULL) = N^2 of interface i, i < n-1;
+ *   h_dev (optional) = state.H_concentration rows (derived[0]); NULL -> 10^-pH;
+ *   bad_dev[p] (optional) != 0 where the reference raises ValueError (T[0] outside [0, 100] C).
+ * ------------------------------------------------------------------------------------- */
+enum {
+  WT_DG_TOTAL_CL_MG = 0, WT_DG_TOTAL_H_MOL, WT_DG_TOTAL_OH_MOL, WT_DG_CHARGE_BALANCE_MOL, WT_DG_THERMAL_ENERGY_KJ,
+  WT_DG_CL_CV, WT_DG_CL_SEGREGATION,
+  WT_DG_GRAD0,                       /* 3 variables x 8: mean, std, max, min, range, max_gradient, mean_gradient, gradient_location */
+  WT_DG_THERMOCLINE_DEPTH = WT_DG_GRAD0 + 24, WT_DG_N2_MAX, WT_DG_N2_MIN, WT_NDIAG
+};
+int wt_diagnostics(int P, int n_zones, const double *par_dev, const double *y_dev, const double *h_dev,
+                   double *out_dev, double *n2_dev, int32_t *bad_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Ensemble statistics: the payload of the ONE collective of the multi-GPU path.  The reference
  * has no counterpart (one plant, logging only: __main__.py:426-448, base_sensor.py:809-856);
  * BASELINE.json north_star asks for mean / variance / exceedance counts all-reduced over NCCL.
