@@ -32,7 +32,7 @@ CNT_NAMES = ("nfev", "njev", "nlu", "nsteps", "nnewton", "nreject", "nnewton_fai
 EXPORTS = (
     "wt_abi_version", "wt_device_count", "wt_last_error", "wt_step", "wt_advance", "wt_derivatives",
     "wt_step_host", "wt_calc_ph", "wt_measure_fp64_peak", "wt_stats", "wt_stats_size", "wt_stats_scratch_doubles",
-    "wt_sensors_init", "wt_sensors_calibrate", "wt_sensors_read", "wt_diagnostics",
+    "wt_sensors_init", "wt_sensors_calibrate", "wt_sensors_read", "wt_diagnostics", "wt_register_image",
 )
 
 
@@ -83,6 +83,8 @@ def lib() -> C.CDLL:
     L.wt_sensors_read.restype = C.c_int
     L.wt_diagnostics.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, ip, vp]
     L.wt_diagnostics.restype = C.c_int
+    L.wt_register_image.argtypes = [C.c_int, ip, C.c_int, dp, ip, C.c_double, vp, vp, vp, vp]
+    L.wt_register_image.restype = C.c_int
     L.wt_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.c_int]
     L.wt_measure_fp64_peak.restype = C.c_int
     _lib = L

@@ -423,6 +423,50 @@ __global__ void __launch_bounds__(128) wt_diagnostics_kernel(int P, int n, const
   O(WT_DG_N2_MIN, n2min);
 }
 
+// ---------------------------------------------------------------------------------------
+// K6: Modbus input-register image of selected plants (__main__.py:166-224,
+// modbus/protocols.py:34-58).  One thread per selected plant; byte work, bound by the 7 gathered reads.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void wt_put_f32(uint16_t *row, int addr, double v) {
+  const uint32_t b = __float_as_uint(__double2float_rn(v));  // struct.pack(">f", v): round to nearest even
+  row[addr] = (uint16_t)(b >> 16);                           // high word first (big-endian word order)
+  row[addr + 1] = (uint16_t)(b & 0xffffu);
+}
+__global__ void wt_register_image_kernel(int K, const int32_t *sel, int P, const double *value, const int32_t *fault,
+                                         double sim_time, uint16_t *ir, uint8_t *di, uint8_t *ok) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int p = sel[k];
+  uint16_t *row = ir + (size_t)k * WT_WIRE_NIR;
+  for (int a = 0; a < WT_WIRE_NIR; ++a) row[a] = 0;
+  uint8_t *bits = di + (size_t)k * WT_WIRE_NDI;
+  bits[0] = bits[1] = bits[2] = 0;
+  const bool in = p >= 0 && p < P;
+  double v[WT_NSENS];
+  int f[WT_NSENS];
+  bool good = in && sim_time >= -1e9 && sim_time <= 1e9;
+  for (int s = 0; s < WT_NSENS; ++s) {
+    double x = in ? value[(size_t)s * P + p] : 0.0;
+    if (x != x || x == INFINITY || x == -INFINITY) x = 0.0;  // safe_value (__main__.py:178-186)
+    v[s] = x;
+    f[s] = in ? fault[(size_t)s * P + p] : 0;
+    good = good && x >= -1e9 && x <= 1e9;                     // slave.py:146-148
+  }
+  if (ok) ok[k] = good ? 1 : 0;
+  if (!good) return;
+  const int addr[WT_NSENS] = {0, 4, 6, 8, 10, 12, 14};       // register_map.py:119-215
+  bool any = false;
+  for (int s = 0; s < WT_NSENS; ++s) {
+    wt_put_f32(row, addr[s], v[s]);
+    any = any || f[s] != 0;
+  }
+  wt_put_f32(row, 100, sim_time);
+  row[102] = any ? 1 : 0;
+  bits[0] = f[0] != 0;
+  bits[1] = f[1] != 0;
+  bits[2] = (f[2] != 0) || (f[3] != 0);
+}
+
 // 8 independent DFMA chains per thread: saturates the FP64 pipe without memory traffic
 __global__ void wt_dfma_peak_kernel(double *out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -524,6 +568,15 @@ int wt_diagnostics(int P, int n, const double *par, const double *y, const doubl
   if (!par || !y || !out) return set_err(WT_ERR_BAD_ARG, "null device pointer");
   wt_diagnostics_kernel<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, n, par, y, h, out, n2, bad);
   return cuda_err(cudaGetLastError(), "wt_diagnostics_kernel launch");
+}
+
+int wt_register_image(int K, const int32_t *sel, int P, const double *value, const int32_t *fault, double sim_time,
+                      uint16_t *ir, uint8_t *di, uint8_t *ok, void *stream) {
+  if (K <= 0 || P <= 0) return set_err(WT_ERR_BAD_ARG, "K and P must be positive");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (!sel || !value || !fault || !ir || !di) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  wt_register_image_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(K, sel, P, value, fault, sim_time, ir, di, ok);
+  return cuda_err(cudaGetLastError(), "wt_register_image_kernel launch");
 }
 
 int wt_stats_size(int n) { return WT_STATS_HDR + 6 * n; }

@@ -192,6 +192,25 @@ class SensorSuite:
                                    self._out_fault[s]) for s, name in enumerate(SENSOR_NAMES)}
 
 
+    def register_image(self, plants, sim_time: float):
+        """Modbus input-register image of the selected plants from the LAST read:
+        what update_modbus_inputs (__main__.py:166-224) hands to the Modbus slave, encoded on the device
+        (modbus/protocols.py:34-58).  Returns (ir [K, 104] int16 holding the uint16 words, di [K, 3] uint8,
+        ok [K] uint8); a row with ok == 0 is one the reference's update would have rejected."""
+        dev = self.ens.device
+        sel = torch.as_tensor(plants, dtype=torch.int32).reshape(-1).to(dev).contiguous()
+        K = int(sel.numel())
+        ir = torch.empty((K, 104), dtype=torch.int16, device=dev)
+        di = torch.empty((K, 3), dtype=torch.uint8, device=dev)
+        ok = torch.empty(K, dtype=torch.uint8, device=dev)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(dev):
+            rc = _lib.lib().wt_register_image(K, p(sel), self.ens.n_plants, p(self._out[0]), p(self._out_fault),
+                                              float(sim_time), p(ir), p(di), p(ok), self._stream())
+        _lib.check(rc, "wt_register_image")
+        return ir, di, ok
+
+
 def create_realistic_sensor_suite(ensemble, seed: int = 0, plant0: int = 0) -> SensorSuite:
     """Batched counterpart of sensors/__init__.py:41-120 for a PlantEnsemble (same 7 keys)."""
     return SensorSuite(ensemble, seed=seed, plant0=plant0)

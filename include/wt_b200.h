@@ -135,6 +135,27 @@ int wt_calc_ph(int P, const double *alk_dev, const double *ct_dev, const double 
                void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Wire-format tap: the Modbus input-register image of selected plants, built
+ * on the device from the last read of the sensor suite, so that the untouched host Modbus layer can serve
+ * any ensemble member (ModbusSlave.ir_block.setValues(0, row), di_block.setValues(0, bits)).  Replaces
+ * update_modbus_inputs (__main__.py:166-224) + ModbusEncoder.float32_to_registers (modbus/protocols.py:34-58,
+ * big-endian IEEE-754 single as (high word, low word)) + the |value| <= 1e9 check of
+ * ModbusSlave.update_input_register (modbus/slave.py:139-164), with the addresses of ModbusRegisterMap
+ * (modbus/register_map.py:119-244, 364-401):
+ *   ir[k * WT_WIRE_NIR + a], a = register address 0..103: 0 pH_inlet, 4 pH_outlet, 6/8 chlorine in/out,
+ *     10 flow_rate, 12/14 temperature in/out (two words each), 100 simulation_time, 102 system_status;
+ *     pH_middle (2..3) is never written by the reference and stays 0.  NaN / inf readings are sent as 0.0.
+ *   di[k * WT_WIRE_NDI + b]: b = 0 pH_inlet fault, 1 pH_outlet fault, 2 chlorine (inlet or outlet) fault
+ *   ok[k] = 0 where the reference's update raises (a value outside +-1e9): that row is left all zero.
+ *   sel_dev[K]: plant indices;  value_dev[s * P + p], fault_dev[s * P + p]: value row and fault codes of the
+ *   last wt_sensors_read (s = sensor 0..6).
+ * ------------------------------------------------------------------------------------- */
+#define WT_WIRE_NIR 104
+#define WT_WIRE_NDI 3
+int wt_register_image(int K, const int32_t *sel_dev, int P, const double *value_dev, const int32_t *fault_dev,
+                      double sim_time, uint16_t *ir_dev, uint8_t *di_dev, uint8_t *ok_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Per-plant diagnostics as one pass over the resident state.  Replaces,
  * for every plant of the ensemble at once:
  *   IntegratedCSTR.validate_conservation              reactor.py:570-611

@@ -172,3 +172,34 @@ def test_orchestrator_closed_loop_on_device():
     assert float(bnd[6].min()) >= 0.0 and float(bnd[6].max()) <= 1.0            # chlorine dosing in [0, 1]
     assert not torch.isnan(bnd).any()
     assert np.all(eng.state.time.cpu().numpy()[(eng.status.cpu().numpy() & 130) == 0] == 80.0)
+
+
+def test_register_image_matches_the_wire_oracle():
+    """K6 (wt_register_image): the Modbus input-register image of selected plants, bit for bit against the
+    restatement of update_modbus_inputs + ModbusEncoder (oracle/wt_wire_oracle.py, pinned against the
+    reference's own encoder), including NaN readings of warming-up sensors, faults and the +-1e9 rejection."""
+    from ics_wt_physicsengine_b200 import PlantEnsemble, ensembles as ens
+    from ics_wt_physicsengine_b200.sensors import create_realistic_sensor_suite
+    from oracle import wt_wire_oracle as ww
+    P, n = 5000, 10
+    e = ens.config2(P, n, seed=12)
+    eng = PlantEnsemble(e)
+    suite = create_realistic_sensor_suite(eng, seed=5)
+    suite.initialize(0.0)
+    for k in range(45):
+        eng.step(1.0, e.bnd)
+        suite.read(eng.state, float(k))
+    # poke special cases into the last read's outputs
+    suite._out[0, 2, 17] = float("inf")
+    suite._out[0, 5, 18] = 2.5e9        # the reference's update raises on this row
+    suite._out_fault[3, 19] = 3
+    sel = np.concatenate([np.arange(0, 64), [17, 18, 19, P - 1], np.random.default_rng(0).integers(0, P, 300)]).astype(np.int32)
+    ir, di, ok = suite.register_image(sel, 44.0)
+    torch.cuda.synchronize()
+    vals = suite._out[0].cpu().numpy().T[sel]
+    flt = suite._out_fault.cpu().numpy().T[sel]
+    want_ir, want_di, want_ok = ww.register_image(vals, flt, 44.0)
+    assert np.array_equal(ir.cpu().numpy().view(np.uint16), want_ir)
+    assert np.array_equal(di.cpu().numpy(), want_di)
+    assert np.array_equal(ok.cpu().numpy().astype(bool), want_ok)
+    assert not want_ok[65] and want_ok[64] and np.isnan(vals).any()   # the special cases are really in the sample
