@@ -608,8 +608,66 @@ __global__ void wt_sensors_calibrate_kernel(int P, int sensor, double t, const d
   // BaseSensor.calibrate (base_sensor.py:701-755): offset = reference - current_value, timers reset
   S[(size_t)WT_SF_CALOFF * WT_NSENS * Pz] = r - S[(size_t)WT_SF_CUR * WT_NSENS * Pz];
   S[(size_t)WT_SF_TCAL * WT_NSENS * Pz] = t;
+  S[(size_t)WT_SF_TPOWER * WT_NSENS * Pz] = t;
   sens_i[(size_t)sensor * Pz + p] = SS_NORMAL;
   sens_i[((size_t)WT_NSENS + sensor) * Pz + p] = SFLT_NONE;
+}
+
+// Maintenance operations of the reference sensors, for sensor `sensor` of every plant:
+//   op 0  pHSensor.calibrate_two_point(b1, b2, m1, m2, t)   ph_sensor.py:338-393
+//   op 1  pHSensor.clean_electrode(method, t)               ph_sensor.py:395-434   a0 = 0 water_rinse, 1 acid_clean, 2 pepsin_clean
+//   op 2  ChlorineSensor.replace_membrane(t)                chlorine_sensor.py:486-509
+//   op 3  ChlorineSensor.replace_reagent(t)                 chlorine_sensor.py:511-537
+// (slope_percentage is overwritten by every read, ph_sensor.py:256-262, and glass_etching is not used on the
+// read path, so neither is device state.)
+__global__ void wt_sensors_maintain_kernel(int P, int sensor, int op, double t, double a0, double a1, double *sens, int *sens_i) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const size_t Pz = (size_t)P;
+  double *S = sens + (size_t)sensor * Pz + p;
+#define MF(f) S[(size_t)(f) * WT_NSENS * Pz]
+  double reference = 0.0;
+  bool recal = true;
+  if (op == 0) {                       // two-point: junction cleaned, single-point calibration at the mid buffer
+    MF(WT_SF_AUX1) = 0.0;
+    reference = (a0 + a1) / 2.0;
+  } else if (op == 1) {                // cleaning: fouling removed, warm-up restarts, calibration untouched
+    const int m = (int)a0;
+    MF(WT_SF_AUX0) *= (m == 0 ? 0.5 : (m == 1 ? 0.1 : 0.2));
+    MF(WT_SF_AUX2) = 0.0;
+    MF(WT_SF_TPOWER) = t;
+    recal = false;
+  } else if (op == 2) {                // new membrane
+    MF(WT_SF_AUX0) = 0.0;
+    MF(WT_SF_AUX1) = 0.0;
+  } else {                             // new reagent
+    MF(WT_SF_AUX0) = 1.0;
+    MF(WT_SF_AUX1) = 0.0;
+    MF(WT_SF_AUX2) = 0.0;
+  }
+  if (recal) {                         // BaseSensor.calibrate(reference, t), base_sensor.py:701-755
+    MF(WT_SF_CALOFF) = reference - MF(WT_SF_CUR);
+    MF(WT_SF_TCAL) = t;
+    MF(WT_SF_TPOWER) = t;
+    sens_i[(size_t)sensor * Pz + p] = SS_NORMAL;
+    sens_i[((size_t)WT_NSENS + sensor) * Pz + p] = SFLT_NONE;
+  }
+#undef MF
+}
+
+int wt_sensors_maintain(int P, int sensor, int op, double t, double a0, double a1, double *sens, int32_t *sens_i, void *stream) {
+  if (P <= 0 || sensor < 0 || sensor >= WT_NSENS) return set_err(WT_ERR_BAD_ARG, "bad P or sensor index");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (!sens || !sens_i) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  const int type = wt_sensor_type(sensor);
+  // the reference raises ValueError for these (ph-only methods exist only on pHSensor)
+  if ((op == 0 || op == 1) && type != ST_PH) return set_err(WT_ERR_BAD_ARG, "calibrate_two_point / clean_electrode: not a pH sensor");
+  if (op == 1 && !(a0 == 0.0 || a0 == 1.0 || a0 == 2.0)) return set_err(WT_ERR_BAD_ARG, "Unknown cleaning method");
+  if (op == 2 && type != ST_CL_AMP) return set_err(WT_ERR_BAD_ARG, "Only amperometric sensors have membranes");
+  if (op == 3 && type != ST_CL_DPD) return set_err(WT_ERR_BAD_ARG, "Only DPD sensors have reagent");
+  if (op < 0 || op > 3) return set_err(WT_ERR_BAD_ARG, "unknown maintenance operation");
+  wt_sensors_maintain_kernel<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, sensor, op, t, a0, a1, sens, sens_i);
+  return cuda_err(cudaGetLastError(), "wt_sensors_maintain_kernel launch");
 }
 
 int wt_sensors_init(int P, double t0, const double *cfg_flow, const double *cfg_cl, const double *cfg_T, double *sens,

@@ -17,7 +17,7 @@
 // secrets.randbits (base_sensor.py:331), so only distributional parity with it is meaningful.
 //
 // State layout in HBM (fp64 / int32, plant index fastest):
-//   sens[(field * 7 + sensor) * P + p]      field: WT_SF_*
+//   sens[(field * 7 + sensor) * P + p]      field: WT_SF_*  (WT_NSF = 9 fields)
 //   sens_i[(field * 7 + sensor) * P + p]    field: 0 status, 1 fault
 //   ring[((line * WT_RING + slot) * 2 + f) * P + p]   f: 0 timestamp, 1 value   (the stored sample
 //       temperature of SampleLine.transport_sample is never used by read(): base_sensor.py:610-614)
@@ -32,12 +32,13 @@
 #define WT_SF_CUR 0       // current_value
 #define WT_SF_VOLT 1      // supply_voltage
 #define WT_SF_CALOFF 2    // calibration_offset
-#define WT_SF_TCAL 3      // last_calibration_time == power_on_time == calibration record timestamp
+#define WT_SF_TCAL 3      // last_calibration_time == calibration record timestamp
 #define WT_SF_LASTVAL 4   // reading_history[-1].value
 #define WT_SF_AUX0 5      // pH: membrane_fouling | Cl amp: membrane_fouling | DPD: reagent_potency | flow: electrode_fouling
 #define WT_SF_AUX1 6      // pH: reference_contamination | Cl amp: membrane_age_days | DPD: light_exposure_hours
 #define WT_SF_AUX2 7      // pH: days_since_cleaning | DPD: reagent_age_days
-#define WT_NSF 8
+#define WT_SF_TPOWER 8   // power_on_time (differs from WT_SF_TCAL only after clean_electrode)
+#define WT_NSF 9
 #define WT_SO_VALUE 0     // outputs: out[(field * 7 + sensor) * P + p]
 #define WT_SO_RAW 1
 #define WT_SO_NOISE 2
@@ -108,7 +109,7 @@ struct WtRng {
   }
 };
 
-__device__ __forceinline__ int wt_sensor_type(int s) { return s < 2 ? ST_PH : (s == 2 ? ST_CL_AMP : (s == 3 ? ST_CL_DPD : (s == 4 ? ST_FLOW_MAG : ST_TEMP_RTD))); }
+__host__ __device__ __forceinline__ int wt_sensor_type(int s) { return s < 2 ? ST_PH : (s == 2 ? ST_CL_AMP : (s == 3 ? ST_CL_DPD : (s == 4 ? ST_FLOW_MAG : ST_TEMP_RTD))); }
 
 // SampleLine.transport_sample (base_sensor.py:177-216): append, then the buffered sample whose
 // timestamp is nearest to t - delay; ties keep the FIRST (oldest) entry (strict '<').
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(128) wt_sensors_read_kernel(SensorArgs a) {
     const double volt = 24.0 + z0 * 1.0;          // :579
     SF(WT_SF_VOLT) = volt;
     const double tcal = SF(WT_SF_TCAL);
-    if (!(t - tcal >= warmup)) {                  // :582-595
+    if (!(t - SF(WT_SF_TPOWER) >= warmup)) {      // :582-595
       OUT(WT_SO_VALUE) = nan(""); OUT(WT_SO_RAW) = nan(""); OUT(WT_SO_NOISE) = 0.0; OUT(WT_SO_DRIFT) = 0.0; OUT(WT_SO_UNC) = 0.0;
       a.out_status[(size_t)s * P + p] = SS_WARMING_UP;
       a.out_fault[(size_t)s * P + p] = SFLT_NONE;
@@ -365,6 +366,7 @@ __global__ void wt_sensors_init_kernel(int P, double t0, const double *cfg_flow,
     S[(size_t)WT_SF_VOLT * WT_NSENS * Pz] = 24.0;
     S[(size_t)WT_SF_CALOFF * WT_NSENS * Pz] = ref - cur0;
     S[(size_t)WT_SF_TCAL * WT_NSENS * Pz] = t0;
+    S[(size_t)WT_SF_TPOWER * WT_NSENS * Pz] = t0;
     S[(size_t)WT_SF_LASTVAL * WT_NSENS * Pz] = nan("");
     S[(size_t)WT_SF_AUX0 * WT_NSENS * Pz] = type == ST_CL_DPD ? 1.0 : 0.0;  // reagent_potency = 1
     S[(size_t)WT_SF_AUX1 * WT_NSENS * Pz] = 0.0;

@@ -124,7 +124,7 @@ class SensorSuite:
         col = lambda k: torch.from_numpy(np.ascontiguousarray(cfg[:, CFG_FIELDS.index(k)])).to(dev)
         self._cfg_flow, self._cfg_cl, self._cfg_T = col("flow_rate"), col("initial_chlorine"), col("temperature")
         f64, i32 = torch.float64, torch.int32
-        self._sens = torch.zeros((8, 7, P), dtype=f64, device=dev)
+        self._sens = torch.zeros((9, 7, P), dtype=f64, device=dev)   # WT_NSF fields
         self._sens_i = torch.zeros((2, 7, P), dtype=i32, device=dev)
         self._ring = torch.zeros((2, 100, 2, P), dtype=f64, device=dev)
         self._ring_i = torch.zeros((2, 2, P), dtype=i32, device=dev)
@@ -191,6 +191,38 @@ class SensorSuite:
         return {name: BatchReading(float(current_time), o[0, s], o[1, s], o[2, s], o[3, s], self._out_status[s], o[4, s],
                                    self._out_fault[s]) for s, name in enumerate(SENSOR_NAMES)}
 
+
+    # ---- maintenance: the reference's per-sensor methods, for that sensor of every plant ----
+    def _maintain(self, name: str, op: int, t: float, a0: float = 0.0, a1: float = 0.0) -> None:
+        s = SENSOR_NAMES.index(name)
+        with torch.cuda.device(self.ens.device):
+            rc = _lib.lib().wt_sensors_maintain(self.ens.n_plants, s, op, float(t), float(a0), float(a1),
+                                                C.c_void_p(self._sens.data_ptr()), C.c_void_p(self._sens_i.data_ptr()),
+                                                self._stream())
+        if rc == -1:   # WT_ERR_BAD_ARG: the reference raises ValueError / AttributeError for these
+            raise ValueError(_lib.lib().wt_last_error().decode(errors="replace"))
+        _lib.check(rc, "wt_sensors_maintain")
+
+    def calibrate_two_point(self, name: str, buffer_pH_1: float, buffer_pH_2: float, measured_pH_1: float,
+                            measured_pH_2: float, current_time: float) -> None:
+        """pHSensor.calibrate_two_point (ph_sensor.py:338-393).  The measured values only set slope_percentage,
+        which the next read() overwrites (ph_sensor.py:256-262)."""
+        self._maintain(name, 0, current_time, buffer_pH_1, buffer_pH_2)
+
+    def clean_electrode(self, name: str, cleaning_method: str, current_time: float) -> None:
+        """pHSensor.clean_electrode (ph_sensor.py:395-434)."""
+        methods = {"water_rinse": 0, "acid_clean": 1, "pepsin_clean": 2}
+        if cleaning_method not in methods:
+            raise ValueError(f"Unknown cleaning method: {cleaning_method}")
+        self._maintain(name, 1, current_time, methods[cleaning_method])
+
+    def replace_membrane(self, name: str, current_time: float) -> None:
+        """ChlorineSensor.replace_membrane (chlorine_sensor.py:486-509): amperometric sensors only."""
+        self._maintain(name, 2, current_time)
+
+    def replace_reagent(self, name: str, current_time: float) -> None:
+        """ChlorineSensor.replace_reagent (chlorine_sensor.py:511-537): DPD sensors only."""
+        self._maintain(name, 3, current_time)
 
     def register_image(self, plants, sim_time: float):
         """Modbus input-register image of the selected plants from the LAST read:

@@ -201,8 +201,8 @@ int wt_stats(int P, int n_zones, const double *y_dev, const uint32_t *status_dev
  * pH_x and temp_x share one SampleLine, as in the reference.
  *
  * Device buffers (plant index fastest; shapes in elements):
- *   sens     double [8][7][P]      per-sensor state (WT_SF_*: current_value, supply_voltage,
- *                                  calibration_offset, calibration time, last history value, 3 aux)
+ *   sens     double [9][7][P]      per-sensor state (WT_SF_*: current_value, supply_voltage,
+ *                                  calibration_offset, calibration time, last history value, 3 aux, power-on time)
  *   sens_i   int32  [2][7][P]      sticky SensorStatus, SensorFault (enum order of base_sensor.py:49-75)
  *   ring     double [2][100][2][P] delay lines: (timestamp, value) per slot
  *   ring_i   int32  [2][2][P]      per line: head, count
@@ -227,6 +227,18 @@ int wt_sensors_init(int P, double t0, const double *cfg_flow_dev, const double *
                     int32_t *ring_i_dev, void *stream);
 int wt_sensors_calibrate(int P, int sensor, double t, const double *ref_dev, double ref_scalar,
                          double *sens_dev, int32_t *sens_i_dev, void *stream);
+
+/* Maintenance operations of sensor `sensor` of every plant:
+ *   op WT_MAINT_CAL2      pHSensor.calibrate_two_point(b1, b2, m1, m2, t)   ph_sensor.py:338-393     a0 = b1, a1 = b2
+ *   op WT_MAINT_CLEAN     pHSensor.clean_electrode(method, t)               ph_sensor.py:395-434     a0 = 0 water_rinse, 1 acid_clean, 2 pepsin_clean
+ *   op WT_MAINT_MEMBRANE  ChlorineSensor.replace_membrane(t)                chlorine_sensor.py:486-509
+ *   op WT_MAINT_REAGENT   ChlorineSensor.replace_reagent(t)                 chlorine_sensor.py:511-537
+ * Returns WT_ERR_BAD_ARG where the reference raises ValueError (wrong sensor kind, unknown cleaning method).
+ * The measured buffer values m1, m2 only enter slope_percentage, which every read() overwrites
+ * (ph_sensor.py:256-262): they do not change any later reading and are not part of the ABI. */
+enum { WT_MAINT_CAL2 = 0, WT_MAINT_CLEAN = 1, WT_MAINT_MEMBRANE = 2, WT_MAINT_REAGENT = 3 };
+int wt_sensors_maintain(int P, int sensor, int op, double t, double a0, double a1, double *sens_dev,
+                        int32_t *sens_i_dev, void *stream);
 int wt_sensors_read(int P, int n_zones, long long plant0, unsigned read_index, double t, double t_prev,
                     const double *y_dev, const double *flow_rate_dev, const double *cfg_flow_dev,
                     const double *cfg_chlorine_dev, const double *cfg_temperature_dev, double *sens_dev,

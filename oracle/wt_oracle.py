@@ -87,6 +87,12 @@ def lib():
         L.wt_oracle_sensors_read.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_uint, C.c_double, C.c_double, dp, dp,
                                              C.c_void_p, dp, ip, ip, dp, C.c_uint64, C.c_int]
         L.wt_oracle_sensors_read.restype = None
+        L.wt_oracle_sensors_maintain.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, dp, C.c_void_p]
+        L.wt_oracle_sensors_maintain.restype = C.c_int
+        L.wt_oracle_sensors_poke.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_void_p]
+        L.wt_oracle_sensors_poke.restype = None
+        L.wt_oracle_sensors_peek.argtypes = [C.c_int, C.c_int, dp, C.c_void_p]
+        L.wt_oracle_sensors_peek.restype = None
         _lib = L
     return _lib
 
@@ -185,6 +191,24 @@ class SensorSuiteOracle:
     def calibrate(self, sensor: int, reference, t: float):
         ref = np.ascontiguousarray(np.broadcast_to(np.asarray(reference, dtype=np.float64), (self.P,)))
         lib().wt_oracle_sensors_calibrate(self.P, sensor, float(t), _dp(ref), self._buf.ctypes.data)
+
+    FIELDS = ("current_value", "calibration_offset", "last_calibration_time", "power_on_time", "membrane_fouling",
+              "reference_contamination", "days_since_cleaning", "membrane_age_days", "reagent_potency",
+              "light_exposure_hours", "reagent_age_days", "status", "fault")
+
+    def maintain(self, sensor: int, op: int, t: float, args=(0.0, 0.0, 0.0, 0.0)) -> int:
+        """op 0 calibrate_two_point(b1, b2, m1, m2) | 1 clean_electrode(method code) | 2 replace_membrane | 3 replace_reagent."""
+        a = np.ascontiguousarray(np.asarray(args, dtype=np.float64).reshape(4))
+        return lib().wt_oracle_sensors_maintain(self.P, sensor, op, float(t), _dp(a), self._buf.ctypes.data)
+
+    def poke(self, sensor: int, field: str, values):
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=np.float64), (self.P,)))
+        lib().wt_oracle_sensors_poke(self.P, sensor, self.FIELDS.index(field), _dp(v), self._buf.ctypes.data)
+
+    def peek(self, sensor: int):
+        out = np.zeros((self.P, 13))
+        lib().wt_oracle_sensors_peek(self.P, sensor, _dp(out), self._buf.ctypes.data)
+        return {k: out[:, i] for i, k in enumerate(self.FIELDS)}
 
     def read(self, y_pn, flow, t, n):
         """y_pn [P,3n] species-major, flow [P] -> (out [P,7,5] value/raw/noise/drift/uncertainty, status [P,7], fault [P,7])."""

@@ -336,6 +336,77 @@ void wt_oracle_sensors_calibrate(int P, int sensor, double t, const double *ref,
   for (int p = 0; p < P; ++p) calibrate(&st[p].s[sensor], ref[p], t);
 }
 
+/* ---- maintenance operations -----------------------------------------------
+ * op 0  pHSensor.calibrate_two_point(b1, b2, m1, m2, t)      ph_sensor.py:338-393   arg = {b1, b2, m1, m2}
+ * op 1  pHSensor.clean_electrode(method, t)                  ph_sensor.py:395-434   arg[0] = 0 water_rinse, 1 acid_clean, 2 pepsin_clean
+ * op 2  ChlorineSensor.replace_membrane(t)  (amperometric)   chlorine_sensor.py:486-509
+ * op 3  ChlorineSensor.replace_reagent(t)   (DPD)            chlorine_sensor.py:511-537
+ * slope_percentage / glass_etching are not carried: read() overwrites slope_percentage on every call
+ * (ph_sensor.py:256-262) and nothing on the read path uses glass_etching.  Returns 0, or -1 where the
+ * reference raises ValueError (wrong sensor kind, unknown cleaning method). */
+static int maintain(sensor_t *s, int op, double t, const double *arg) {
+  switch (op) {
+    case 0:
+      if (s->kind != K_PH) return -1;
+      s->reference_contamination = 0.0;
+      calibrate(s, (arg[0] + arg[1]) / 2.0, t);
+      return 0;
+    case 1: {
+      if (s->kind != K_PH) return -1;
+      const int m = (int)arg[0];
+      if (m == 0) s->membrane_fouling *= 0.5;
+      else if (m == 1) s->membrane_fouling *= 0.1;
+      else if (m == 2) s->membrane_fouling *= 0.2;
+      else return -1;
+      s->days_since_cleaning = 0.0;
+      s->power_on_time = t;
+      return 0;
+    }
+    case 2:
+      if (s->kind != K_CL_AMP) return -1;
+      s->membrane_fouling = 0.0;
+      s->membrane_age_days = 0.0;
+      s->power_on_time = t;
+      calibrate(s, 0.0, t);
+      return 0;
+    case 3:
+      if (s->kind != K_CL_DPD) return -1;
+      s->reagent_potency = 1.0;
+      s->reagent_age_days = 0.0;
+      s->light_exposure_hours = 0.0;
+      calibrate(s, 0.0, t);
+      return 0;
+  }
+  return -1;
+}
+int wt_oracle_sensors_maintain(int P, int sensor, int op, double t, const double *arg, suite_t *st) {
+  int rc = 0;
+  for (int p = 0; p < P; ++p) rc |= maintain(&st[p].s[sensor], op, t, arg);
+  return rc;
+}
+/* state access for the tests: field 0 current_value 1 calibration_offset 2 last_calibration_time 3 power_on_time
+ * 4 membrane_fouling 5 reference_contamination 6 days_since_cleaning 7 membrane_age_days 8 reagent_potency
+ * 9 light_exposure_hours 10 reagent_age_days 11 status 12 fault */
+static double *field_ptr(sensor_t *s, int f) {
+  switch (f) {
+    case 0: return &s->current_value; case 1: return &s->calibration_offset; case 2: return &s->last_calibration_time;
+    case 3: return &s->power_on_time; case 4: return &s->membrane_fouling; case 5: return &s->reference_contamination;
+    case 6: return &s->days_since_cleaning; case 7: return &s->membrane_age_days; case 8: return &s->reagent_potency;
+    case 9: return &s->light_exposure_hours; case 10: return &s->reagent_age_days;
+  }
+  return 0;
+}
+void wt_oracle_sensors_poke(int P, int sensor, int field, const double *v, suite_t *st) {
+  for (int p = 0; p < P; ++p) *field_ptr(&st[p].s[sensor], field) = v[p];
+}
+void wt_oracle_sensors_peek(int P, int sensor, double *out13, suite_t *st) {
+  for (int p = 0; p < P; ++p) {
+    for (int f = 0; f < 11; ++f) out13[p * 13 + f] = *field_ptr(&st[p].s[sensor], f);
+    out13[p * 13 + 11] = st[p].s[sensor].status;
+    out13[p * 13 + 12] = st[p].s[sensor].fault;
+  }
+}
+
 typedef struct {
   int tid, nthreads, P, n;
   long long plant0;

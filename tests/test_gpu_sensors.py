@@ -203,3 +203,39 @@ def test_register_image_matches_the_wire_oracle():
     assert np.array_equal(di.cpu().numpy(), want_di)
     assert np.array_equal(ok.cpu().numpy().astype(bool), want_ok)
     assert not want_ok[65] and want_ok[64] and np.isnan(vals).any()   # the special cases are really in the sample
+
+
+def test_maintenance_operations_value_for_value(oracle):
+    """calibrate_two_point / clean_electrode / replace_membrane / replace_reagent applied between reads: every
+    later reading of the kernel equals the CPU port (itself pinned against the reference's own methods in
+    tests/test_sensors_oracle.py), and the reference's ValueError cases raise."""
+    P, n, t0 = 1024, 10, 0.0
+    e = ens.config2(P, n, seed=7)
+    eng = PlantEnsemble(e)
+    suite = create_realistic_sensor_suite(eng, seed=11, plant0=5)
+    suite.initialize(t0)
+    osu = oracle.SensorSuiteOracle(e.cfg[:, 3], e.cfg[:, 12], e.cfg[:, 13], t0, seed=11, plant0=5, nthreads=8)
+    ops = {400: [("clean_electrode", ("pH_inlet", "acid_clean"), (0, 1, (1.0,))),
+                 ("replace_membrane", ("chlorine_inlet",), (2, 2, ()))],
+           1900: [("calibrate_two_point", ("pH_outlet", 7.0, 4.0, 7.02, 4.05), (1, 0, (7.0, 4.0, 7.02, 4.05))),
+                  ("replace_reagent", ("chlorine_outlet",), (3, 3, ())),
+                  ("clean_electrode", ("pH_outlet", "water_rinse"), (1, 1, (0.0,)))]}
+    for k in range(0, 4000, 5):       # 5 s between reads: covers the 1800 s pH warm-up after each op
+        t = t0 + k
+        for name, gargs, (si, op, oargs) in ops.get(k, []):
+            getattr(suite, name)(*gargs, t)
+            assert osu.maintain(si, op, t, tuple(oargs) + (0.0,) * (4 - len(oargs))) == 0
+        eng.step(1.0, e.bnd)
+        out_g, st_g, ft_g = _gpu_read(suite, t)
+        out_o, st_o, ft_o = osu.read(eng.state_numpy(), eng.state.flow_rate.cpu().numpy(), t, n)
+        assert np.array_equal(st_g.T, st_o) and np.array_equal(ft_g.T, ft_o), k
+        if k % 100 == 0 or k in (405, 700, 705, 1905, 2200, 2205, 3700, 3705):
+            assert _close(np.transpose(out_g, (1, 0, 2)), out_o), k
+    with pytest.raises(ValueError):
+        suite.replace_membrane("chlorine_outlet", 5000.0)      # DPD has no membrane
+    with pytest.raises(ValueError):
+        suite.replace_reagent("chlorine_inlet", 5000.0)
+    with pytest.raises(ValueError):
+        suite.clean_electrode("pH_inlet", "sandblast", 5000.0)
+    with pytest.raises(ValueError):
+        suite.clean_electrode("flow_main", "water_rinse", 5000.0)

@@ -118,3 +118,31 @@ def test_emergent_quirks_are_reproduced(golden, oracle_samples):
     assert m(i400, 4) > 9.9                                    # flow saturates at full scale (offset = flow_rate)
     assert (stat[i400, 4] == 5).mean() > 0.5                   # ... and sits in DRIFT_WARNING
     assert np.isnan(vals[checks.index(1900), 4]).mean() > 0.15  # absorbing power / open-circuit faults
+
+
+def test_maintenance_operations_match_the_reference(oracle, golden_dir):
+    """calibrate_two_point / clean_electrode / replace_membrane / replace_reagent of the CPU port against the
+    attributes of the unmodified reference's sensors before and after the same call
+    (tests/golden/sensor_maintenance.npz, oracle/gen_golden_maint.py), including the ValueError cases."""
+    import os
+    g = np.load(os.path.join(golden_dir, "sensor_maintenance.npz"))
+    fields = oracle.SensorSuiteOracle.FIELDS
+    assert tuple(g["attrs"]) == fields[:11]
+    n_raise = 0
+    for row in g["cases"]:
+        si, op, t, args = int(row[0]), int(row[1]), row[2], row[3:7]
+        before, after, raised = row[7:20], row[20:33], int(row[33])
+        su = oracle.SensorSuiteOracle(np.array([5.0]), np.array([2.0]), np.array([20.0]), 0.0)
+        for i, f in enumerate(fields[:11]):
+            su.poke(si, f, before[i])
+        rc = su.maintain(si, op, t, args)
+        assert (rc != 0) == bool(raised)
+        n_raise += raised
+        if raised:
+            continue
+        got = su.peek(si)
+        for i, f in enumerate(fields):
+            kind_has = not (after[i] == 0.0 and before[i] == 0.0)   # attributes the sensor kind does not have are 0 in the dump
+            if kind_has or f in ("status", "fault"):
+                assert got[f][0] == after[i], (si, op, f, got[f][0], after[i])
+    assert n_raise == 120  # replace_membrane on the DPD sensor and replace_reagent on the amperometric one
