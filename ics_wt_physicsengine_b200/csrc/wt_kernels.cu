@@ -76,6 +76,7 @@ static_assert(WtPlantStep<SmemLu>::PV_N == 10 && WTC_NCNT % 2 == 0, "per-plant s
 struct StepArgs {
   int P, n, n_steps, bnd_stride, max_attempts;
   int ld;                // row stride of every SoA array (= P unless a column slab of a larger ensemble is stepped)
+  double inv_sqrtN, inv_sqrt3N;  // 1/sqrt(3n), 1/sqrt(9n) of the RMS norms, computed by the host
   double dt;
   const double *par, *bnd;
   double *time, *y, *flow, *derived;
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
   lu.czero();
 
   WtPlantStep<SmemLu> ps;
-  ps.g = wt_make_group(n);
+  ps.g = wt_make_group(n, a.inv_sqrtN, a.inv_sqrt3N);
   ps.lu = &lu;
   // reactor.py:500: flow_rate = inlet + acid + chlorine flow, parked with the plant's constants until the epilogue
   lu.cput(CK_flow, bnd[WTB_INLET_FLOW] + bnd[WTB_ACID_FLOW] + bnd[WTB_CL_FLOW]);
@@ -499,6 +500,8 @@ static int check_common(int P, int n) {
 }
 
 static int launch_step(StepArgs a, cudaStream_t s) {
+  a.inv_sqrtN = 1.0 / sqrt((double)(3 * a.n));
+  a.inv_sqrt3N = 1.0 / sqrt((double)(9 * a.n));
   const int gpw = 32 / a.n;
   const long long warps = ((long long)a.P + gpw - 1) / gpw;
   const long long blocks = (warps + WT_STEP_WARPS - 1) / WT_STEP_WARPS;

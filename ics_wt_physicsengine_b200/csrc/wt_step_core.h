@@ -135,32 +135,34 @@ struct WtGroup {
   vi src_dn1, src_up1;  // neighbour zones' lanes, clamped to the plant
 };
 
-WT_DEV WtGroup wt_make_group(int n) {
+// inv_sqrtN / inv_sqrt3N = 1/sqrt(3n), 1/sqrt(9n): warp-uniform, computed by the host (a double sqrt and a
+// division with their slow paths are ~100 instructions of once-per-step code in a kernel bound by instruction fetch)
+WT_DEV WtGroup wt_make_group(int n, double inv_sqrtN, double inv_sqrt3N) {
   WtGroup g;
   g.n = n;
   vi lane = lane_id();
   int gpw = WT_WARP / n;
   // lanes past the last whole plant form harmless one-lane pseudo groups
   vb in = lane < gpw * n;
-  vi q = vbroadcast_i(0);
-  for (int k = 1; k < gpw; ++k) q = q + seli(lane >= k * n, 1, 0);
+  vi q = vdivi(lane, n);
   g.base = seli(in, q * n, lane);
   g.z = seli(in, lane - g.base, 0);
   uint32_t full = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
-  vi m = vbroadcast_i(0);
-  for (int k = 0; k < gpw; ++k) m = seli(in & (q == k), (int)(full << (k * n)), m);
-  g.gmask = seli(in, m, vlanebit());
+  g.gmask = seli(in, vshl_i((int)full, g.base), vlanebit());
   g.first = g.z == 0;
   g.last = selb(in, g.z == (n - 1), vbroadcast_b(true));
   g.L = 0;
   for (int s = 1; s < n; s <<= 1) ++g.L;
-  g.inv_sqrtN = 1.0 / sqrt((double)(3 * n));
-  g.inv_sqrt3N = 1.0 / sqrt((double)(9 * n));
+  g.inv_sqrtN = inv_sqrtN;
+  g.inv_sqrt3N = inv_sqrt3N;
   g.lane = lane;
   g.last_lane = seli(in, g.base + (n - 1), lane);
   g.src_dn1 = vmaxi(lane - 1, g.base);
   g.src_up1 = vmini(lane + 1, g.last_lane);
   return g;
+}
+WT_DEV WtGroup wt_make_group(int n) {
+  return wt_make_group(n, 1.0 / sqrt((double)(3 * n)), 1.0 / sqrt((double)(9 * n)));
 }
 
 // neighbour access inside the plant; `dflt` outside
