@@ -1085,7 +1085,6 @@ struct WtPlantStep {
       WT_NOUNROLL
       for (int k = 0; k < WT_NEWTON_MAXITER; ++k) {
         if (!vany(active)) break;
-        lu->cadd(WTC_NNEWTON, seli(active, 1, 0));
         n_iter = seli(active, k + 1, n_iter);
         vd fr[3], cr[3], ci[3];
         WT_UNROLL
@@ -1106,7 +1105,6 @@ struct WtPlantStep {
             ci[v] = ci[v] + F[v] * t2;
           }
         }
-        lu->cadd(WTC_NFEV, seli(active, 3, 0));
         {
           vb tb = active & wt_gany(g, bad_any);
           fset(F_TRANGE, tb);
@@ -1152,6 +1150,10 @@ struct WtPlantStep {
         dW_norm_old = dW_norm;
         have_norm_old = vbroadcast_b(true);
       }
+      // path counters of this attempt: n_iter Newton iterations with three RHS evaluations each (one update here
+      // instead of two shared-memory read-modify-writes per iteration)
+      lu->cadd(WTC_NNEWTON, n_iter);
+      lu->cadd(WTC_NFEV, n_iter * 3);
       // (6) outcome of the collocation solve (radau.py:464-481)
       {
         vb nc = fget(F_RUNNING) & !converged;
