@@ -93,7 +93,9 @@ struct StepArgs {
 #define WT_STEP_MINBLOCKS 2
 #endif
 
-template <int WARPS>
+// NZ > 0: the zone count is a compile-time constant (the BASELINE shapes n = 10 and n = 20): lane geometry, PCR level
+// count and every LU slot offset fold to immediates after inlining; NZ = 0 reads n from the arguments.
+template <int WARPS, int NZ>
 #if WT_STEP_MINBLOCKS > 0
 __global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_kernel(StepArgs a) {
 #elif defined(WT_STEP_MAXNREG)
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
 #endif
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = a.n, gpw = 32 / n;
+  const int n = NZ > 0 ? NZ : a.n, gpw = 32 / n;
   const long long wg = (long long)blockIdx.x * WARPS + warp;
   const int gi = lane / n;
   const long long pl = wg * gpw + gi;
@@ -507,13 +509,19 @@ static int launch_step(StepArgs a, cudaStream_t s) {
   const long long blocks = (warps + WT_STEP_WARPS - 1) / WT_STEP_WARPS;
   size_t smem = (size_t)WT_STEP_WARPS * wt_warp_smem_doubles(a.n) * sizeof(double);
   if (const char *pad = getenv("WT_B200_SMEM_PAD_KB")) smem += (size_t)atoi(pad) * 1024;  // occupancy experiments only
+  void (*kern)(StepArgs) = a.n == 10 ? wt_step_kernel<WT_STEP_WARPS, 10>
+                           : (a.n == 20 ? wt_step_kernel<WT_STEP_WARPS, 20> : wt_step_kernel<WT_STEP_WARPS, 0>);
+  if (getenv("WT_B200_GENERIC_N")) kern = wt_step_kernel<WT_STEP_WARPS, 0>;  // A/B runs
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wt_step_kernel<WT_STEP_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute");
+    void (*all[3])(StepArgs) = {wt_step_kernel<WT_STEP_WARPS, 0>, wt_step_kernel<WT_STEP_WARPS, 10>, wt_step_kernel<WT_STEP_WARPS, 20>};
+    for (int i = 0; i < 3; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute");
+    }
     attr_done = true;
   }
-  wt_step_kernel<WT_STEP_WARPS><<<(unsigned)blocks, WT_STEP_WARPS * 32, smem, s>>>(a);
+  kern<<<(unsigned)blocks, WT_STEP_WARPS * 32, smem, s>>>(a);
   return cuda_err(cudaGetLastError(), "wt_step_kernel launch");
 }
 
