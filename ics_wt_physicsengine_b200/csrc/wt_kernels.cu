@@ -773,7 +773,8 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
   }
   int slabs = P / 32768;
   if (slabs < 1) slabs = 1;
-  if (slabs > 16) slabs = 16;
+  if (slabs > 32) slabs = 32;
+  if (const char *e = getenv("WT_B200_HOST_SLABS")) { slabs = atoi(e); if (slabs < 1) slabs = 1; }  // tuning runs
   const int per = ((P + slabs - 1) / slabs + 31) & ~31;  // plants per slab, a multiple of the warp width
   const size_t pitch = Pz * 8;
   if (!bnd_stride) {  // one broadcast boundary row: uploaded once, the other streams wait for it
