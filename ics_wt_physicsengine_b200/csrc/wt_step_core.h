@@ -274,8 +274,8 @@ WT_DEV WtConstT<Store> wt_make_const(Store *st, const WtGroup &g, int lk0, const
 // spatial.py:175-195
 WT_DEV vd wt_density(vd T) {
   vd d4 = T - 4.0;
-  vd cold = 999.97 + (-0.008) * (d4 * d4);
-  vd warm = 998.2 + (-2.1e-4 * 998.2) * (T - 20.0);
+  vd cold = WT_PC_RHO_A + WT_PC_RHO_B * (d4 * d4);
+  vd warm = WT_PC_RHO_W + WT_PC_RHO_WS * (T - 20.0);
   return sel(T <= 8.0, cold, warm);
 }
 
@@ -287,15 +287,15 @@ WT_DEV vd wt_suppression(const WtConstT<Store> &c, vd rho_lo, vd rho_hi) {
   vd ravg = 0.5 * (rho_lo + rho_hi);
   // Ri = (g drho zh)/(ravg v^2) > 0.25, cross-multiplied (ravg v^2 > 0): same decision except
   // within an ulp of the threshold; v <= 1e-6 -> Ri = +inf
-  vb stable = (!c.v_ok) | (((9.81 * drho) * c.zh()) > ravg * c.Ri_thr());
+  vb stable = (!c.v_ok) | (((WT_PC_G * drho) * c.zh()) > ravg * c.Ri_thr());
   return sel(c.strat & stable, 0.5, 1.0);
 }
 
 // thermodynamics.py:187-193
 WT_DEV vd wt_arrhenius(vd T) {
-  vd TK = T + 273.15;
-  vd e = -(45000.0 / 8.314) * (wt_rcp(TK) - 1.0 / 293.15);
-  return 0.0001 * vexp(e);
+  vd TK = T + WT_PC_T0K;
+  vd e = WT_PC_EA_R * (wt_rcp(TK) - WT_PC_ITREF);
+  return WT_PC_KREF * vexp(e);
 }
 WT_DEV vb wt_t_out_of_range(vd T) { return (T < 0.0) | (T > 100.0); }  // thermodynamics.py:146-157
 
@@ -306,7 +306,7 @@ template <class Store>
 WT_DEV vd wt_beta_den(const WtConstT<Store> &c, vd H) { return H * H + c.Ka1() * H + c.Ka12(); }
 template <class Store>
 WT_DEV vd wt_beta_ln10_r(const WtConstT<Store> &c, vd H, vd iH, vd iD, vb &bpos) {
-  vd bw = 2.303 * (H + c.Kw() * iH);
+  vd bw = WT_PC_2303 * (H + c.Kw() * iH);
   vd HH = H * H;
   // the three alphas share one reciprocal (<= 1 ulp from three divisions)
   vd a0 = HH * iD;
@@ -315,7 +315,7 @@ WT_DEV vd wt_beta_ln10_r(const WtConstT<Store> &c, vd H, vd iH, vd iD, vb &bpos)
   vd bc = c.CT2303() * (a0 * a1 + (4.0 * a1) * a2 + a0 * a2);
   vd beta = bw + bc;
   bpos = beta > 0.0;
-  return beta * WT_LN10;
+  return beta * WT_PC_LN10;
 }
 template <class Store>
 WT_DEV vd wt_beta_ln10(const WtConstT<Store> &c, vd H, vb &bpos) {
@@ -325,7 +325,7 @@ WT_DEV vd wt_beta_ln10(const WtConstT<Store> &c, vd H, vb &bpos) {
 // chemistry.py:510-523
 template <class Store>
 WT_DEV vd wt_decay_factor_r(const WtConstT<Store> &c, vd H, vd iden) {
-  return (H * iden) * 1.0 + (c.KaCl() * iden) * 0.02;
+  return (H * iden) * 1.0 + (c.KaCl() * iden) * WT_PC_OCL;
 }
 template <class Store>
 WT_DEV vd wt_decay_factor(const WtConstT<Store> &c, vd H) { return wt_decay_factor_r(c, H, wt_rcp(H + c.KaCl())); }
@@ -386,7 +386,7 @@ WT_DEV void wt_rhs(const WtGroup &g, const WtConstT<Store> &c, vd pH, vd Cl, vd 
   vd ibl = wt_rcp(wt_beta_ln10_r(c, H, inv[0], inv[1], bpos));
   vd mixH = wt_mix(m, wt_dnc(g, H), H, wt_upc(g, H));
   dpH = wt_dph(wt_dph_inlet(g, c, H, ibl, bpos), mixH, ibl, bpos);
-  vd kf = (0.0001 * ke) * wt_decay_factor_r(c, H, inv[2]);
+  vd kf = (WT_PC_KREF * ke) * wt_decay_factor_r(c, H, inv[2]);
   dCl = wt_dcl(g, c, Cl, wt_mix(m, wt_dnc(g, Cl), Cl, wt_upc(g, Cl)), kf);
   dT = wt_dt(g, c, T, wt_mix(m, wt_dnc(g, T), T, wt_upc(g, T)));
   bad = wt_t_out_of_range(T);
