@@ -33,7 +33,7 @@ EXPORTS = (
     "wt_abi_version", "wt_device_count", "wt_last_error", "wt_step", "wt_advance", "wt_derivatives",
     "wt_step_host", "wt_calc_ph", "wt_measure_fp64_peak", "wt_stats", "wt_stats_size", "wt_stats_scratch_doubles",
     "wt_sensors_init", "wt_sensors_calibrate", "wt_sensors_read", "wt_diagnostics", "wt_register_image",
-    "wt_sensors_maintain",
+    "wt_sensors_maintain", "wt_sensor_window_stats",
 )
 
 
@@ -88,6 +88,8 @@ def lib() -> C.CDLL:
     L.wt_register_image.restype = C.c_int
     L.wt_sensors_maintain.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, dp, ip, vp]
     L.wt_sensors_maintain.restype = C.c_int
+    L.wt_sensor_window_stats.argtypes = [C.c_int, C.c_int, dp, ip, C.c_int, dp, vp]
+    L.wt_sensor_window_stats.restype = C.c_int
     L.wt_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.c_int]
     L.wt_measure_fp64_peak.restype = C.c_int
     _lib = L

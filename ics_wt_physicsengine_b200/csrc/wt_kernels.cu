@@ -470,6 +470,38 @@ __global__ void wt_register_image_kernel(int K, const int32_t *sel, int P, const
   bits[2] = (f[2] != 0) || (f[3] != 0);
 }
 
+// BaseSensor.get_statistics over a window of history rows (base_sensor.py:809-856): one thread per plant,
+// two-pass mean / population std over the finite values like numpy.
+__global__ void wt_sensor_window_stats_kernel(int P, int m, const double *hist, const int32_t *rows, int sensor, double *out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const size_t Pz = (size_t)P;
+  double s = 0.0, mn = INFINITY, mx = -INFINITY;
+  int nf = 0;
+  for (int i = 0; i < m; ++i) {
+    const double v = hist[((size_t)rows[i] * WT_NSENS + sensor) * Pz + p];
+    if (isfinite(v)) { s += v; mn = fmin(mn, v); mx = fmax(mx, v); ++nf; }
+  }
+  double mean = nan(""), sd = nan("");
+  if (nf > 0) {
+    mean = s / nf;
+    double q = 0.0;
+    for (int i = 0; i < m; ++i) {
+      const double v = hist[((size_t)rows[i] * WT_NSENS + sensor) * Pz + p];
+      if (isfinite(v)) q += (v - mean) * (v - mean);
+    }
+    sd = sqrt(q / nf);
+  }
+  const bool none = m == 0;
+  out[0 * Pz + p] = none ? 0.0 : mean;
+  out[1 * Pz + p] = none ? 0.0 : sd;
+  out[2 * Pz + p] = none ? 0.0 : (nf > 0 ? mn : nan(""));
+  out[3 * Pz + p] = none ? 0.0 : (nf > 0 ? mx : nan(""));
+  out[4 * Pz + p] = (double)m;
+  out[5 * Pz + p] = 0.0;
+  out[6 * Pz + p] = none ? 0.0 : (nf > 0 ? (double)(m - nf) / m : 1.0);
+}
+
 // 8 independent DFMA chains per thread: saturates the FP64 pipe without memory traffic
 __global__ void wt_dfma_peak_kernel(double *out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -588,6 +620,14 @@ int wt_register_image(int K, const int32_t *sel, int P, const double *value, con
   if (!sel || !value || !fault || !ir || !di) return set_err(WT_ERR_BAD_ARG, "null device pointer");
   wt_register_image_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(K, sel, P, value, fault, sim_time, ir, di, ok);
   return cuda_err(cudaGetLastError(), "wt_register_image_kernel launch");
+}
+
+int wt_sensor_window_stats(int P, int m, const double *hist, const int32_t *rows, int sensor, double *out, void *stream) {
+  if (P <= 0 || m < 0 || sensor < 0 || sensor >= WT_NSENS) return set_err(WT_ERR_BAD_ARG, "bad P, m or sensor index");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (!out || (m > 0 && (!hist || !rows))) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  wt_sensor_window_stats_kernel<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, m, hist, rows, sensor, out);
+  return cuda_err(cudaGetLastError(), "wt_sensor_window_stats_kernel launch");
 }
 
 int wt_stats_size(int n) { return WT_STATS_HDR + 6 * n; }

@@ -107,7 +107,7 @@ class SensorSuite:
     """The 7-sensor suite of every plant of one ensemble shard, state resident in HBM."""
 
     def __init__(self, ensemble, seed: int = 0, plant0: int = 0, installation: Optional[InstallationQuality] = None,
-                 sample_line: Optional[SampleLine] = None):
+                 sample_line: Optional[SampleLine] = None, history: int = 0):
         _lib.require_device()
         self.ens = ensemble
         self.seed, self.plant0 = int(seed) & (2 ** 64 - 1), int(plant0)
@@ -134,6 +134,11 @@ class SensorSuite:
         self.read_index = 0
         self.last_time: Optional[float] = None
         self._initialized = False
+        # optional reading history for get_statistics (the reference keeps 1000 readings per sensor,
+        # base_sensor.py:248, 321; here a ring of `history` reads x 7 values per plant, off by default)
+        self.history = int(history)
+        self._hist = torch.zeros((self.history, 7, P), dtype=f64, device=dev) if self.history > 0 else None
+        self._hist_times: list = []
 
     def keys(self):
         return SENSOR_NAMES
@@ -185,6 +190,11 @@ class SensorSuite:
                 p(self._ring_i), p(self._out), p(self._out_status), p(self._out_fault),
                 self._suite6.ctypes.data_as(C.POINTER(C.c_double)), C.c_uint64(self.seed), self._stream())
         _lib.check(rc, "wt_sensors_read")
+        if self._hist is not None:
+            self._hist[self.read_index % self.history].copy_(self._out[0])
+            self._hist_times.append(float(current_time))
+            if len(self._hist_times) > self.history:
+                self._hist_times.pop(0)
         self.read_index += 1
         self.last_time = float(current_time)
         o = self._out
@@ -224,6 +234,29 @@ class SensorSuite:
         """ChlorineSensor.replace_reagent (chlorine_sensor.py:511-537): DPD sensors only."""
         self._maintain(name, 3, current_time)
 
+    def get_statistics(self, name: str, window_seconds: float = 60.0) -> Dict[str, torch.Tensor]:
+        """BaseSensor.get_statistics (base_sensor.py:809-856) of sensor `name` for every plant, over the readings
+        of the last `window_seconds` that are still in the history ring (construct the suite with history=K).
+        Returns {mean, std, min, max, count, drift_rate, fault_rate}: tensors [P]."""
+        if self._hist is None:
+            raise RuntimeError("construct the suite with history=K to keep K readings per sensor")
+        s = SENSOR_NAMES.index(name)
+        ts = self._hist_times
+        rows = []
+        if ts:
+            cutoff = ts[-1] - float(window_seconds)                       # base_sensor.py:771-775
+            newest = self.read_index - 1
+            rows = [(newest - j) % self.history for j in range(len(ts)) if ts[len(ts) - 1 - j] >= cutoff]
+        dev = self.ens.device
+        out = torch.empty((7, self.ens.n_plants), dtype=torch.float64, device=dev)
+        rows_dev = torch.tensor(rows if rows else [0], dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().wt_sensor_window_stats(self.ens.n_plants, len(rows), C.c_void_p(self._hist.data_ptr()),
+                                                   C.c_void_p(rows_dev.data_ptr()), s, C.c_void_p(out.data_ptr()),
+                                                   self._stream())
+        _lib.check(rc, "wt_sensor_window_stats")
+        return {k: out[i] for i, k in enumerate(("mean", "std", "min", "max", "count", "drift_rate", "fault_rate"))}
+
     def register_image(self, plants, sim_time: float):
         """Modbus input-register image of the selected plants from the LAST read:
         what update_modbus_inputs (__main__.py:166-224) hands to the Modbus slave, encoded on the device
@@ -243,6 +276,6 @@ class SensorSuite:
         return ir, di, ok
 
 
-def create_realistic_sensor_suite(ensemble, seed: int = 0, plant0: int = 0) -> SensorSuite:
+def create_realistic_sensor_suite(ensemble, seed: int = 0, plant0: int = 0, history: int = 0) -> SensorSuite:
     """Batched counterpart of sensors/__init__.py:41-120 for a PlantEnsemble (same 7 keys)."""
-    return SensorSuite(ensemble, seed=seed, plant0=plant0)
+    return SensorSuite(ensemble, seed=seed, plant0=plant0, history=history)

@@ -135,6 +135,21 @@ int wt_calc_ph(int P, const double *alk_dev, const double *ct_dev, const double 
                void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * BaseSensor.get_statistics(window_seconds) for one sensor of every plant (base_sensor.py:757-856;
+ * SURVEY.md section 8f rank 2) over a history of reading values kept on the device:
+ *   hist_dev[(row * 7 + sensor) * P + p]  value of `sensor` of plant p at history row `row` (a ring the caller
+ *                                         fills after each wt_sensors_read with the value rows of `out`)
+ *   rows_dev[m]                            the ring rows inside the window (get_recent_readings: timestamps are the
+ *                                          same for all plants, so the host selects them)
+ *   out_dev[k * P + p], k = 0 mean, 1 std, 2 min, 3 max (over the finite values; NaN if there is none),
+ *                       4 count (= m), 5 drift_rate (0.0: calculate_drift_rate takes the window newest-first, so
+ *                       its "dt > 0" never holds, base_sensor.py:777-807), 6 fault_rate (non-finite / m).
+ *   m == 0 (no readings yet) -> all zeros, as the reference.
+ * ------------------------------------------------------------------------------------- */
+int wt_sensor_window_stats(int P, int m, const double *hist_dev, const int32_t *rows_dev, int sensor,
+                           double *out_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Wire-format tap: the Modbus input-register image of selected plants, built
  * on the device from the last read of the sensor suite, so that the untouched host Modbus layer can serve
  * any ensemble member (ModbusSlave.ir_block.setValues(0, row), di_block.setValues(0, bits)).  Replaces

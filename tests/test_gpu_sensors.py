@@ -239,3 +239,44 @@ def test_maintenance_operations_value_for_value(oracle):
         suite.clean_electrode("pH_inlet", "sandblast", 5000.0)
     with pytest.raises(ValueError):
         suite.clean_electrode("flow_main", "water_rinse", 5000.0)
+
+
+def test_get_statistics_matches_the_oracle(golden_dir):
+    """wt_sensor_window_stats: BaseSensor.get_statistics over the device history ring, against the numpy oracle
+    (pinned against the reference in tests/test_sensor_stats_oracle.py), including the reference's golden inputs
+    pushed through the ring, a wrapped ring, an empty history and all-NaN sensors (warming up)."""
+    from oracle import wt_sensor_stats_oracle as ws
+    g = np.load(os.path.join(golden_dir, "sensor_statistics.npz"))
+    K, P = g["values"].shape
+    e = ens.config2(P, 10, seed=3)
+    eng = PlantEnsemble(e)
+    suite = create_realistic_sensor_suite(eng, seed=1, history=16)       # ring shorter than the 40 readings: it wraps
+    suite.initialize(0.0)
+    st0 = suite.get_statistics("pH_inlet", 60.0)
+    assert all(float(v.abs().max()) == 0.0 for v in st0.values())          # no readings yet: zeros
+    vals = torch.from_numpy(g["values"]).to(eng.device)
+    for k in range(K):
+        # drive the ring directly with the golden readings (sensor 0), as read() does with its outputs
+        suite._out[0, 0].copy_(vals[k])
+        suite._hist[suite.read_index % suite.history].copy_(suite._out[0])
+        suite._hist_times.append(float(g["timestamps"][k]))
+        if len(suite._hist_times) > suite.history:
+            suite._hist_times.pop(0)
+        suite.read_index += 1
+    for win in (0.5, 10.0, 20.0, 1e6):
+        got = suite.get_statistics("pH_inlet", win)
+        want = ws.statistics(g["values"][-16:], g["timestamps"][-16:], win)   # what is still in the ring
+        for i, k in enumerate(ws.FIELDS):
+            a, b = got[k].cpu().numpy(), want[i]
+            assert np.array_equal(np.isnan(a), np.isnan(b)), (k, win)
+            ok = ~np.isnan(b)
+            assert np.allclose(a[ok], b[ok], rtol=1e-13, atol=1e-15), (k, win)
+    # through the real read(): 40 reads of a warming-up pH sensor are all NaN -> fault_rate 1, NaN moments
+    suite2 = create_realistic_sensor_suite(eng, seed=1, history=8)
+    suite2.initialize(0.0)
+    for k in range(12):
+        suite2.read(eng.state, float(k))
+    s2 = suite2.get_statistics("pH_outlet", 5.0)
+    assert float(s2["count"][0]) == 6 and float(s2["fault_rate"].min()) == 1.0 and bool(torch.isnan(s2["mean"]).all())
+    f2 = suite2.get_statistics("flow_main", 100.0)                          # flow warms up in 10 s: finite values by now
+    assert float(f2["count"][0]) == 8 and bool(torch.isfinite(f2["mean"]).any())
