@@ -558,7 +558,7 @@ struct WtPlantStep {
       const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
       // Written PHASE-major (all reciprocals, then all exchanges, then all updates) so that the six
       // factorizations advance together: ptxas keeps the statement order when registers are tight, and
-      // system-major order ran the six reciprocal chains (MUFU + 5 dependent DFMAs each) back to back.
+      // system-major order ran the six reciprocal chains (MUFU + 3 dependent DFMAs each) back to back.
       vd den[6], inv[6];  // 0..2 real pivots, 3..5 |complex pivot|^2
       WT_UNROLL
       for (int q = 0; q < 3; ++q) { den[q] = b[q]; den[3 + q] = br[q] * br[q] + bi[q] * bi[q]; }
