@@ -326,9 +326,9 @@ def main():
         "roofline": {
             "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": achieved_tf / fp64_peak if fp64_peak else None,
-            # dram__bytes_read+write of one wt_step launch: 81.5 B per plant-zone-step measured by ncu --set full on
+            # dram__bytes_read+write of one wt_step launch: 81.1 B per plant-zone-step measured by ncu --set full on
             # the 262,144-plant launch (profiles/r1_step_kernel_v5_session2_final.txt), scaled to this launch's units
-            "traffic": 81.5 * (timed_plant_steps / max(1, args.steps)) * N_ZONES / world,
+            "traffic": 81.1 * (timed_plant_steps / max(1, args.steps)) * N_ZONES / world,
             "traffic_source": "ncu capture of the 262144-plant launch scaled by units (profiles/r1_step_kernel_v5_session2_final.txt)",
             "peak_source": "measured in this run by wt_measure_fp64_peak (8 independent DFMA chains/thread); "
                            "MEASURED_PEAKS.json carries no FP64 figure",
