@@ -760,11 +760,17 @@ int wt_sensors_read(int P, int n, long long plant0, unsigned read_index, double 
   return cuda_err(cudaGetLastError(), "wt_sensors_read_kernel launch");
 }
 
-// Host-buffer path: one workspace per process, grown on demand.
-static struct {
+// Host-buffer path: per device, one workspace grown on demand, three copy/compute streams, one event, and the
+// shape whose constants are resident.
+enum { WT_HOST_NSTREAM = 3 };
+struct HostCtx {
   size_t cap_bytes;
   char *dev;
-} g_ws = {0, nullptr};
+  cudaStream_t st[WT_HOST_NSTREAM];
+  cudaEvent_t ev;
+  int res_P, res_n;
+};
+static HostCtx g_host[64];
 
 int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, int bnd_stride, double *time,
                  double *y, double *flow, uint32_t *status, int max_attempts, int flags) {
@@ -777,6 +783,12 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
   const size_t b_par = WT_NPAR * Pz * 8, b_bnd = WT_NBND * (bnd_stride ? Pz : 1) * 8, b_t = Pz * 8,
                b_y = 3 * (size_t)n * Pz * 8, b_f = Pz * 8, b_s = Pz * 4;
   const size_t total = b_par + b_bnd + b_t + b_y + b_f + b_s + 256 * 6;
+  int dev = 0;
+  {
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= 64) return cuda_err(e != cudaSuccess ? e : cudaErrorInvalidDevice, "cudaGetDevice");
+  }
+  HostCtx &g_ws = g_host[dev];
   if (total > g_ws.cap_bytes) {
     flags &= ~1;
     if (g_ws.dev) cudaFree(g_ws.dev);
@@ -795,21 +807,22 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
   double *d_f = (double *)q; q += al(b_f);
   uint32_t *d_s = (uint32_t *)q;
   // WT_HOST_PARAMS_RESIDENT: the derived constants uploaded by the previous call (same P, n) are reused
-  static int res_P = 0, res_n = 0;
-  const bool up_par = !(flags & 1) || res_P != P || res_n != n;
-  res_P = P; res_n = n;
+  const bool up_par = !(flags & 1) || g_ws.res_P != P || g_ws.res_n != n;
+  g_ws.res_P = P; g_ws.res_n = n;
 
   // Pipelined over column slabs of the SoA arrays: slab c's H2D copies, its kernel and its D2H copies go to
   // stream c % 3, so the copies of one slab overlap the kernel of another (PCIe is full duplex and the
   // device has separate copy engines per direction).  A slab of plants is a column range of every row:
   // 2-D copies with the row pitch P.  Plants are independent, so slabs need no ordering among themselves.
-  enum { NSTREAM = 3 };
-  static cudaStream_t st[NSTREAM] = {nullptr, nullptr, nullptr};
+  enum { NSTREAM = WT_HOST_NSTREAM };
+  cudaStream_t *st = g_ws.st;
   if (!st[0]) {
     for (int i = 0; i < NSTREAM; ++i) {
       cudaError_t e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
       if (e != cudaSuccess) return cuda_err(e, "cudaStreamCreate");
     }
+    cudaError_t e = cudaEventCreateWithFlags(&g_ws.ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return cuda_err(e, "cudaEventCreate");
   }
   int slabs = P / 32768;
   if (slabs < 1) slabs = 1;
@@ -818,8 +831,7 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
   const int per = ((P + slabs - 1) / slabs + 31) & ~31;  // plants per slab, a multiple of the warp width
   const size_t pitch = Pz * 8;
   if (!bnd_stride) {  // one broadcast boundary row: uploaded once, the other streams wait for it
-    static cudaEvent_t ev = nullptr;
-    if (!ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    cudaEvent_t ev = g_ws.ev;
     cudaMemcpyAsync(d_bnd, bnd, b_bnd, cudaMemcpyHostToDevice, st[0]);
     cudaEventRecord(ev, st[0]);
     for (int i = 1; i < NSTREAM; ++i) cudaStreamWaitEvent(st[i], ev, 0);
