@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # WT_B200_LIB selects an alternative build of the SAME library (A/B tuning builds); never a CPU path
 LIB_PATH = os.environ.get("WT_B200_LIB") or os.path.join(_HERE, "csrc", "libwt_b200.so")
 
+ABI_VERSION = 2   # WT_ABI_VERSION of include/wt_b200.h
 NPAR = 12
 NBND = 10
 NCNT = 8
@@ -54,6 +55,10 @@ def lib() -> C.CDLL:
             "(python -c 'import __graft_entry__ as g; g.build()').  There is no CPU fallback."
         )
     L = C.CDLL(LIB_PATH)
+    L.wt_abi_version.restype = C.c_int
+    if L.wt_abi_version() != ABI_VERSION:
+        raise EngineError(f"{LIB_PATH} has ABI version {L.wt_abi_version()}, this package needs {ABI_VERSION}: rebuild "
+                          "(python -c 'import __graft_entry__ as g; g.build()')")
     vp, dp, ip, up = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p  # raw device addresses
     L.wt_abi_version.restype = C.c_int
     L.wt_device_count.restype = C.c_int

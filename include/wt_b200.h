@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WT_ABI_VERSION 1
+#define WT_ABI_VERSION 2   /* 2: sensor state has 9 fields (power-on time); wt_sensors_maintain, wt_sensor_window_stats, wt_diagnostics, wt_register_image */
 #define WT_MAX_ZONES 32
 
 /* derived per-plant constants; computed on the host exactly as the reference constructors do
