@@ -66,11 +66,7 @@ __host__ __device__ inline int wt_lu_slots(int n) {
   return 3 * (2 * L + 1) + 3 * (4 * L + 2);
 }
 // + the lane-private constants (LK_*) kept after the LU multipliers
-#ifdef WT_PARK
-__host__ __device__ inline int wt_lane_slots(int n) { return wt_lu_slots(n) + LK_N + 15; }
-#else
 __host__ __device__ inline int wt_lane_slots(int n) { return wt_lu_slots(n) + LK_N; }
-#endif
 // doubles of shared memory per warp: LU slots for 32 lanes + constants for (32/n + 1) plants
 #define WT_PLANT_DOUBLES (CK_N + WTC_NCNT / 2 + 10)  // per-plant constants + path counters (ints) + step-control scalars (PV_N)
 __host__ __device__ inline int wt_warp_smem_doubles(int n) { return wt_lane_slots(n) * 32 + (32 / n + 1) * WT_PLANT_DOUBLES; }
@@ -145,7 +141,6 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
   WtPlantStep<SmemLu> ps;
   ps.g = wt_make_group(n, a.inv_sqrtN, a.inv_sqrt3N);
   ps.lu = &lu;
-  ps.park0 = wt_lu_slots(n) + LK_N;
   // reactor.py:500: flow_rate = inlet + acid + chlorine flow, parked with the plant's constants until the epilogue
   lu.cput(CK_flow, bnd[WTB_INLET_FLOW] + bnd[WTB_ACID_FLOW] + bnd[WTB_CL_FLOW]);
   ps.c = wt_make_const(&lu, ps.g, wt_lu_slots(n), par, bnd);

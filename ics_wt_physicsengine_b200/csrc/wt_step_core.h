@@ -505,24 +505,7 @@ struct WtPlantStep {
   // state vector of this zone: 0 pH, 1 Cl, 2 T  (and f = dy/dt)
   vd y[3], f[3];
   WtJac J;
-  vd jfac_r[3];
-  int park0;  // first parked lane slot (WT_PARK)
-#ifdef WT_PARK
-  WT_DEV vd Qg(int v, int k) const { return lu->get(park0 + 3 * v + k); }
-  WT_DEV void Qs(int v, int k, vd x) { lu->put(park0 + 3 * v + k, x, vbroadcast_b(true)); }
-  WT_DEV vd yoldg(int v) const { return lu->get(park0 + 9 + v); }
-  WT_DEV void yolds(int v, vd x) { lu->put(park0 + 9 + v, x, vbroadcast_b(true)); }
-  WT_DEV vd jfacg(int v) const { return lu->get(park0 + 12 + v); }
-  WT_DEV void jfacs(int v, vd x) { lu->put(park0 + 12 + v, x, vbroadcast_b(true)); }
-#else
-  vd Q_r[3][3], yold_r[3];
-  WT_DEV vd Qg(int v, int k) const { return Q_r[v][k]; }
-  WT_DEV void Qs(int v, int k, vd x) { Q_r[v][k] = x; }
-  WT_DEV vd yoldg(int v) const { return yold_r[v]; }
-  WT_DEV void yolds(int v, vd x) { yold_r[v] = x; }
-  WT_DEV vd jfacg(int v) const { return jfac_r[v]; }
-  WT_DEV void jfacs(int v, vd x) { jfac_r[v] = x; }
-#endif
+  vd jfac[3];
   // Per-plant decisions of the solver, one bit each in ONE register (as separate bools ptxas kept them in
   // byte lanes of several registers and spilled those to local memory, which misses L1 here: long_sb stalls)
   enum { F_RUNNING = 1, F_NEED_JAC = 2, F_CURRENT_JAC = 4, F_LU_VALID = 8, F_NEW_STEP = 16, F_HAVE_OLD = 32,
@@ -536,6 +519,8 @@ struct WtPlantStep {
   WT_DEV vb failed() const { return fget(F_FAILED); }      // TOO_SMALL_STEP
   WT_DEV vb worklimit() const { return fget(F_WORKLIMIT); }  // engine policy: attempt budget exhausted (not reference behaviour)
   vd W[3][3];     // W[k][var]
+  vd Q[3][3];     // dense output, Q[var][k]   (radau.py:547-553)
+  vd yold[3];
   // Per-plant step-control scalars live in the per-plant store (shared memory), not replicated in two
   // registers per lane for the whole step: they are touched a few times per attempt, never in the Newton loop.
   enum { PV_SELF_H = 0, PV_SELF_H_OLD, PV_SELF_ERR_OLD, PV_H_OLD, PV_ERR_OLD, PV_MIN_STEP, PV_SOL_TOLD, PV_SOL_H,
@@ -696,9 +681,7 @@ struct WtPlantStep {
     lu->cadd(WTC_NJEV, seli(m, 1, 0));
 
     WT_UNROLL
-    vd jfac[3];
-    WT_UNROLL
-    for (int v = 0; v < 3; ++v) jfac[v] = sel(m & !fget(F_HAVE_JFAC), 1.4901161193847656e-08, jfacg(v));  // EPS ** 0.5
+    for (int v = 0; v < 3; ++v) jfac[v] = sel(m & !fget(F_HAVE_JFAC), 1.4901161193847656e-08, jfac[v]);  // EPS ** 0.5
     fset(F_HAVE_JFAC, m);
 
     // ---- base intermediates at y (identical bits to the evaluation that produced f)
@@ -919,7 +902,7 @@ struct WtPlantStep {
       fnew = sel(maxd[v] < SMALL * scl[v], fnew * 10.0, fnew);
       fnew = sel(maxd[v] > BIG * scl[v], fnew * 0.1, fnew);
       fnew = vmax(fnew, MINF);
-      jfacs(v, sel(m, fnew, jfac[v]));
+      jfac[v] = sel(m, fnew, jfac[v]);
     }
   }
 
@@ -953,10 +936,10 @@ struct WtPlantStep {
     pvset(PV_SOL_H, vbroadcast(1.0));
     WT_UNROLL
     for (int v = 0; v < 3; ++v) {
-      jfacs(v, vbroadcast(0.0));
-      yolds(v, y[v]);
+      jfac[v] = vbroadcast(0.0);
+      yold[v] = y[v];
       WT_UNROLL
-      for (int k = 0; k < 3; ++k) { W[k][v] = vbroadcast(0.0); Qs(v, k, vbroadcast(0.0)); }
+      for (int k = 0; k < 3; ++k) { W[k][v] = vbroadcast(0.0); Q[v][k] = vbroadcast(0.0); }
     }
     J.cp = vbroadcast(0.0);
     WT_UNROLL
@@ -1063,10 +1046,9 @@ struct WtPlantStep {
         vd x2 = ((t + h * 1.0) - sol_told) * isolh;
         WT_UNROLL
         for (int v = 0; v < 3; ++v) {
-          const vd q0 = Qg(v, 0), q1 = Qg(v, 1), q2 = Qg(v, 2), yo = yoldg(v);
-          vd z0 = (((q0 * x0 + q1 * (x0 * x0)) + q2 * ((x0 * x0) * x0)) + yo) - y[v];
-          vd z1 = (((q0 * x1 + q1 * (x1 * x1)) + q2 * ((x1 * x1) * x1)) + yo) - y[v];
-          vd z2 = (((q0 * x2 + q1 * (x2 * x2)) + q2 * ((x2 * x2) * x2)) + yo) - y[v];
+          vd z0 = (((Q[v][0] * x0 + Q[v][1] * (x0 * x0)) + Q[v][2] * ((x0 * x0) * x0)) + yold[v]) - y[v];
+          vd z1 = (((Q[v][0] * x1 + Q[v][1] * (x1 * x1)) + Q[v][2] * ((x1 * x1) * x1)) + yold[v]) - y[v];
+          vd z2 = (((Q[v][0] * x2 + Q[v][1] * (x2 * x2)) + Q[v][2] * ((x2 * x2) * x2)) + yold[v]) - y[v];
           z0 = sel(hs, z0, 0.0);
           z1 = sel(hs, z1, 0.0);
           z2 = sel(hs, z2, 0.0);
@@ -1266,10 +1248,10 @@ struct WtPlantStep {
           pvset(PV_SELF_H, h_abs * fct, acc);
           WT_UNROLL
           for (int v = 0; v < 3; ++v) {
-            Qs(v, 0, sel(acc, (Z[0][v] * WT_P00 + Z[1][v] * WT_P10) + Z[2][v] * WT_P20, Qg(v, 0)));
-            Qs(v, 1, sel(acc, (Z[0][v] * WT_P01 + Z[1][v] * WT_P11) + Z[2][v] * WT_P21, Qg(v, 1)));
-            Qs(v, 2, sel(acc, (Z[0][v] * WT_P02 + Z[1][v] * WT_P12) + Z[2][v] * WT_P22, Qg(v, 2)));
-            yolds(v, sel(acc, y[v], yoldg(v)));
+            Q[v][0] = sel(acc, (Z[0][v] * WT_P00 + Z[1][v] * WT_P10) + Z[2][v] * WT_P20, Q[v][0]);
+            Q[v][1] = sel(acc, (Z[0][v] * WT_P01 + Z[1][v] * WT_P11) + Z[2][v] * WT_P21, Q[v][1]);
+            Q[v][2] = sel(acc, (Z[0][v] * WT_P02 + Z[1][v] * WT_P12) + Z[2][v] * WT_P22, Q[v][2]);
+            yold[v] = sel(acc, y[v], yold[v]);
             y[v] = sel(acc, y_new[v], y[v]);
             f[v] = sel(acc, F[v], f[v]);
           }
