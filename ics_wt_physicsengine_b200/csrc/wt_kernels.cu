@@ -12,6 +12,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/wt_b200.h"
 #include "wt_step_core.h"
 #include "wt_sensors.cuh"
@@ -32,13 +34,39 @@ static int cuda_err(cudaError_t e, const char *where) {
 }
 
 // ---------------------------------------------------------------------------------------
-// per-warp shared-memory store of the PCR factorizations
+// per-warp store of the PCR factorizations: real multipliers in shared memory, complex ones in TENSOR MEMORY
 // ---------------------------------------------------------------------------------------
+// Tensor memory (256 KB per SM, 128 lanes x 512 32-bit columns) is idle in a kernel without tcgen05.mma.  With the
+// 32x32b shape, thread i of warp w reads / writes consecutive columns of TMEM lane 32 (w % 4) + i: a lane-private
+// array, addressed by a warp-uniform column.  The complex multipliers (12 L doubles per lane, 2/3 of the LU store)
+// live there: one LDTM.x8 fetches {k1r, k1i, k2r, k2i} of a level (it is scoreboarded like a shared-memory load,
+// ~18 cycles, measured in tools/micro/tmem.cu), and shared memory per warp drops from 23 KB to 9 KB, which is what
+// lets a third block onto the SM.  A block allocates 128 columns (24 L <= 120 for n <= 32); 4 blocks fit an SM.
+#define WT_TMEM_COLS 128
+__device__ __forceinline__ void wt_tmem_ld4(uint32_t a, double *x) {
+  int r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a));
+  // the wait is tied to the loaded registers so that no use can be scheduled above it (SASS: LDTM is scoreboarded,
+  // the wait itself is a NOP)
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = __hiloint2double(r[2 * i + 1], r[2 * i]);
+}
+__device__ __forceinline__ void wt_tmem_st4(uint32_t a, const double *x) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "r"(a), "r"(__double2loint(x[0])), "r"(__double2hiint(x[0])), "r"(__double2loint(x[1])), "r"(__double2hiint(x[1])),
+                  "r"(__double2loint(x[2])), "r"(__double2hiint(x[2])), "r"(__double2loint(x[3])), "r"(__double2hiint(x[3])));
+}
+
 struct SmemLu {
   double *p;   // &lu_region[lane]; slot stride = 32 doubles
   double *cp;  // constants of this lane's plant (one copy per plant, read as a broadcast)
   int *ci;     // solver path counters of this lane's plant (WTC_*): in shared memory, not in 8 registers per lane that
                // ptxas spilled; every lane of the plant adds the same increment to the same word (benign)
+  uint32_t tm; // tensor-memory address of column 0 of this warp's lane quarter
+  bool rmw;    // this factorization must preserve the stored factors of some plant of the warp
   __device__ __forceinline__ void czero() {
 #pragma unroll
     for (int k = 0; k < WTC_NCNT; ++k) ci[k] = 0;
@@ -55,15 +83,32 @@ struct SmemLu {
                  :: "r"((unsigned)__cvta_generic_to_shared(p + slot * 32)), "d"(x), "r"((int)mask) : "memory");
   }
   __device__ __forceinline__ double get(int slot) const { return p[slot * 32]; }
+  // complex slot space: tensor memory, two columns per double.  tcgen05.st is a warp-wide instruction and cannot be
+  // predicated per lane, so a factorization that must leave another plant's factors alone (rmw) merges with the
+  // stored values first; the common case (every plant of the warp factorizes, or the others hold nothing) stores.
+  __device__ __forceinline__ void begin_factor(bool keep) { rmw = __any_sync(0xffffffffu, keep); }
+  __device__ __forceinline__ void end_factor() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+  __device__ __forceinline__ void cx_get4(int slot, double *x) const { wt_tmem_ld4(tm + 2 * slot, x); }
+  __device__ __forceinline__ void cx_put4(int slot, const double *x, bool mask) {
+    double v[4] = {x[0], x[1], x[2], x[3]};
+    if (rmw) {
+      double o[4];
+      wt_tmem_ld4(tm + 2 * slot, o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = mask ? v[i] : o[i];
+    }
+    wt_tmem_st4(tm + 2 * slot, v);
+  }
   __device__ __forceinline__ void cput(int k, double x) { cp[k] = x; }
   __device__ __forceinline__ double cget(int k) const { return cp[k]; }
   __device__ __forceinline__ void csync() { __syncwarp(); }
 };
 
+// shared-memory lane slots: the real multipliers (3 systems x 2 L) ...
 __host__ __device__ inline int wt_lu_slots(int n) {
   int L = 0;
   for (int s = 1; s < n; s <<= 1) ++L;
-  return 3 * (2 * L + 1) + 3 * (4 * L + 2);
+  return 3 * 2 * L;
 }
 // + the lane-private constants (LK_*) kept after the LU multipliers
 __host__ __device__ inline int wt_lane_slots(int n) { return wt_lu_slots(n) + LK_N; }
@@ -72,6 +117,7 @@ __host__ __device__ inline int wt_lane_slots(int n) { return wt_lu_slots(n) + LK
 __host__ __device__ inline int wt_warp_smem_doubles(int n) { return wt_lane_slots(n) * 32 + (32 / n + 1) * WT_PLANT_DOUBLES; }
 
 static_assert(WtPlantStep<SmemLu>::PV_N == 10 && WTC_NCNT % 2 == 0, "per-plant store layout out of sync with WT_PLANT_DOUBLES");
+static_assert(24 * 5 <= WT_TMEM_COLS, "complex LU slots of n <= 32 zones (L <= 5) must fit the tensor-memory allocation");
 
 struct StepArgs {
   int P, n, n_steps, bnd_stride, max_attempts;
@@ -90,8 +136,12 @@ struct StepArgs {
 #define WT_STEP_WARPS 4
 #endif
 #ifndef WT_STEP_MINBLOCKS
-#define WT_STEP_MINBLOCKS 2
+#define WT_STEP_MINBLOCKS 3
 #endif
+#ifndef WT_STEP_CARVEOUT_PCT
+#define WT_STEP_CARVEOUT_PCT 50  // percent of the 228 KB: three blocks of ~36 KB (n = 10) or ~43 KB (n = 20)
+#endif
+#define WT_MAX_DEVICES 64
 
 // NZ > 0: the zone count is a compile-time constant (the BASELINE shapes n = 10 and n = 20): lane geometry, PCR level
 // count and every LU slot offset fold to immediates after inlining; NZ = 0 reads n from the arguments.
@@ -104,7 +154,21 @@ __global__ void __maxnreg__(WT_STEP_MAXNREG) wt_step_kernel(StepArgs a) {
 __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
 #endif
   extern __shared__ double smem[];
+  static_assert(WARPS == 4, "one warp per tensor-memory lane quarter");
+  __shared__ uint32_t tmem_slot;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // tensor memory for the complex LU multipliers: warp 0 allocates the block's columns (tcgen05.alloc writes the
+  // address to shared memory) and gives up the allocation permit so that the other resident blocks can allocate
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_slot)), "n"(WT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
   const int n = NZ > 0 ? NZ : a.n, gpw = 32 / n;
   const long long wg = (long long)blockIdx.x * WARPS + warp;
   const int gi = lane / n;
@@ -128,63 +192,66 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
   for (int v = 0; v < 3; ++v) y0[v] = a.y[((size_t)v * n + z) * P + p];
 
   bool on = in_plant && !(st_in & WTS_HALT_MASK);
-#ifndef WT_CTA_LOCKSTEP
-  if (!__any_sync(0xffffffffu, on)) return;
-#endif
+  // (a warp without a live plant skips the work but still meets the block at the barrier before the TMEM is freed)
+  if (__any_sync(0xffffffffu, on)) {
+    SmemLu lu;
+    lu.p = smem + (size_t)warp * wt_warp_smem_doubles(n) + lane;
+    lu.cp = smem + (size_t)warp * wt_warp_smem_doubles(n) + wt_lane_slots(n) * 32 + (gi < gpw ? gi : gpw) * WT_PLANT_DOUBLES;
+    lu.ci = (int *)(lu.cp + CK_N);
+    lu.tm = tmem_base + ((uint32_t)(warp * 32) << 16);
+    lu.rmw = false;
+    lu.czero();
 
-  SmemLu lu;
-  lu.p = smem + (size_t)warp * wt_warp_smem_doubles(n) + lane;
-  lu.cp = smem + (size_t)warp * wt_warp_smem_doubles(n) + wt_lane_slots(n) * 32 + (gi < gpw ? gi : gpw) * WT_PLANT_DOUBLES;
-  lu.ci = (int *)(lu.cp + CK_N);
-  lu.czero();
-
-  WtPlantStep<SmemLu> ps;
-  ps.g = wt_make_group(n, a.inv_sqrtN, a.inv_sqrt3N);
-  ps.lu = &lu;
-  // reactor.py:500: flow_rate = inlet + acid + chlorine flow, parked with the plant's constants until the epilogue
-  lu.cput(CK_flow, bnd[WTB_INLET_FLOW] + bnd[WTB_ACID_FLOW] + bnd[WTB_CL_FLOW]);
-  ps.c = wt_make_const(&lu, ps.g, wt_lu_slots(n), par, bnd);
+    WtPlantStep<SmemLu> ps;
+    ps.g = wt_make_group(n, a.inv_sqrtN, a.inv_sqrt3N);
+    ps.lu = &lu;
+    // reactor.py:500: flow_rate = inlet + acid + chlorine flow, parked with the plant's constants until the epilogue
+    lu.cput(CK_flow, bnd[WTB_INLET_FLOW] + bnd[WTB_ACID_FLOW] + bnd[WTB_CL_FLOW]);
+    ps.c = wt_make_const(&lu, ps.g, wt_lu_slots(n), par, bnd);
 #pragma unroll
-  for (int v = 0; v < 3; ++v) ps.y[v] = y0[v];
+    for (int v = 0; v < 3; ++v) ps.y[v] = y0[v];
 
-  uint32_t st = st_in;
-  double der[3] = {0.0, 0.0, 0.0};
-  bool stepped = false;
+    uint32_t st = st_in;
+    double der[3] = {0.0, 0.0, 0.0};
+    bool stepped = false;
 
-  for (int s = 0; s < a.n_steps; ++s) {
-#ifndef WT_CTA_LOCKSTEP
-    if (!__any_sync(0xffffffffu, on)) break;
-#endif
-    double yin[3] = {ps.y[0], ps.y[1], ps.y[2]};
-    ps.integrate(t, a.dt, on, a.max_attempts);
-    bool adv;
-    int sb = wt_finish_step(ps, yin, der, adv);
-    if (on) {
-      st = (uint32_t)sb;
-      if (adv) { t += a.dt; stepped = true; }
-      if (sb & WTS_HALT_MASK) on = false;
-    }
-  }
-
-  if (in_plant && !(st_in & WTS_HALT_MASK)) {
-#pragma unroll
-    for (int v = 0; v < 3; ++v) a.y[((size_t)v * n + z) * P + p] = ps.y[v];
-    if (a.derived && stepped) {
-#pragma unroll
-      for (int v = 0; v < 3; ++v) a.derived[((size_t)v * n + z) * P + p] = der[v];
-    }
-    if (z == 0) {
-      a.time[p] = t;
-      a.status[p] = st;
-      if (stepped && a.flow) a.flow[p] = lu.cget(CK_flow);
-      if (a.counters) {
-        // fire-and-forget reductions: a load-add-store here made the whole warp wait for eight loads
-#pragma unroll
-        for (int k = 0; k < WTC_NCNT; ++k) atomicAdd(&a.counters[(size_t)k * P + p], lu.cval(k));
+    for (int s = 0; s < a.n_steps; ++s) {
+      if (!__any_sync(0xffffffffu, on)) break;
+      double yin[3] = {ps.y[0], ps.y[1], ps.y[2]};
+      ps.integrate(t, a.dt, on, a.max_attempts);
+      bool adv;
+      int sb = wt_finish_step(ps, yin, der, adv);
+      if (on) {
+        st = (uint32_t)sb;
+        if (adv) { t += a.dt; stepped = true; }
+        if (sb & WTS_HALT_MASK) on = false;
       }
-      if (a.cost) a.cost[p] = lu.cval(WTC_NSTEPS) + lu.cval(WTC_NREJECT) + lu.cval(WTC_NNEWTON_FAIL) + lu.cval(WTC_NNEWTON);
+    }
+
+    if (in_plant && !(st_in & WTS_HALT_MASK)) {
+#pragma unroll
+      for (int v = 0; v < 3; ++v) a.y[((size_t)v * n + z) * P + p] = ps.y[v];
+      if (a.derived && stepped) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) a.derived[((size_t)v * n + z) * P + p] = der[v];
+      }
+      if (z == 0) {
+        a.time[p] = t;
+        a.status[p] = st;
+        if (stepped && a.flow) a.flow[p] = lu.cget(CK_flow);
+        if (a.counters) {
+          // fire-and-forget reductions: a load-add-store here made the whole warp wait for eight loads
+#pragma unroll
+          for (int k = 0; k < WTC_NCNT; ++k) atomicAdd(&a.counters[(size_t)k * P + p], lu.cval(k));
+        }
+        if (a.cost) a.cost[p] = lu.cval(WTC_NSTEPS) + lu.cval(WTC_NREJECT) + lu.cval(WTC_NNEWTON_FAIL) + lu.cval(WTC_NNEWTON);
+      }
     }
   }
+  // every warp is done with its tensor-memory columns: the allocating warp frees them
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(WT_TMEM_COLS) : "memory");
 }
 
 __global__ void wt_derivatives_kernel(int P, int n, const double *par_, const double *bnd_, int bnd_stride,
@@ -203,6 +270,8 @@ __global__ void wt_derivatives_kernel(int P, int n, const double *par_, const do
   st.p = &cs[threadIdx.x >> 5][17 * CK_N + lane];
   st.cp = &cs[threadIdx.x >> 5][(gi < gpw ? gi : gpw) * CK_N];
   st.ci = nullptr;  // the RHS alone counts nothing
+  st.tm = 0;
+  st.rmw = false;
   double par[WTP_NPAR], bnd[WTB_NBND];
 #pragma unroll
   for (int k = 0; k < WTP_NPAR; ++k) par[k] = par_[(size_t)k * P + p];
@@ -544,14 +613,28 @@ static int launch_step(StepArgs a, cudaStream_t s) {
   void (*kern)(StepArgs) = a.n == 10 ? wt_step_kernel<WT_STEP_WARPS, 10>
                            : (a.n == 20 ? wt_step_kernel<WT_STEP_WARPS, 20> : wt_step_kernel<WT_STEP_WARPS, 0>);
   if (getenv("WT_B200_GENERIC_N")) kern = wt_step_kernel<WT_STEP_WARPS, 0>;  // A/B runs
-  static bool attr_done = false;
-  if (!attr_done) {
-    void (*all[3])(StepArgs) = {wt_step_kernel<WT_STEP_WARPS, 0>, wt_step_kernel<WT_STEP_WARPS, 10>, wt_step_kernel<WT_STEP_WARPS, 20>};
-    for (int i = 0; i < 3; ++i) {
-      cudaError_t e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute");
+  // The attributes belong to the (kernel, device) pair: set them once per device, under a lock (several host
+  // threads, one per device, may call in).
+  {
+    static std::mutex mu;
+    static bool attr_done[WT_MAX_DEVICES];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= WT_MAX_DEVICES) return cuda_err(e != cudaSuccess ? e : cudaErrorInvalidDevice, "cudaGetDevice");
+    std::lock_guard<std::mutex> lock(mu);
+    if (!attr_done[dev]) {
+      void (*all[3])(StepArgs) = {wt_step_kernel<WT_STEP_WARPS, 0>, wt_step_kernel<WT_STEP_WARPS, 10>, wt_step_kernel<WT_STEP_WARPS, 20>};
+      for (int i = 0; i < 3; ++i) {
+        e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute");
+        // shared memory for the resident blocks, the rest of the 256 KB stays L1 (it backs the register spills)
+        int pct = WT_STEP_CARVEOUT_PCT;
+        if (const char *ev = getenv("WT_B200_CARVEOUT_PCT")) pct = atoi(ev);  // tuning runs
+        e = cudaFuncSetAttribute(all[i], cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(carveout)");
+      }
+      attr_done[dev] = true;
     }
-    attr_done = true;
   }
   kern<<<(unsigned)blocks, WT_STEP_WARPS * 32, smem, s>>>(a);
   return cuda_err(cudaGetLastError(), "wt_step_kernel launch");

@@ -395,93 +395,34 @@ WT_DEV void wt_rhs(const WtGroup &g, const WtConstT<Store> &c, vd pH, vd Cl, vd 
 // ----------------------------------------------------------------------------------------
 // tridiagonal systems across lanes: parallel cyclic reduction
 // ----------------------------------------------------------------------------------------
-// LuStore (backend-specific, see the kernel / the emulation harness) keeps, per lane, the
-// elimination multipliers of each level and the final reciprocal pivot:
-//   void put(int slot, vd x, vb mask);   vd get(int slot);
-
-WT_DEV int wt_pcr_levels(int n) { int L = 0; for (int s = 1; s < n; s <<= 1) ++L; return L; }
-
+// LuStore (backend-specific, see the kernel / the emulation harness) keeps, per lane, the elimination multipliers
+// of each level and the final reciprocal pivot, in two slot spaces:
+//   real     void put(int slot, vd x, vb mask);            vd get(int slot);
+//   complex  void cx_put4(int slot, const vd *x, vb mask);  void cx_get4(int slot, vd *x);   (4 consecutive slots)
+// plus begin_factor(keep) / end_factor() around a factorization (`keep` = lanes whose stored factors must survive it).
+// On the GPU the real slots live in shared memory and the complex ones in TENSOR MEMORY (one tcgen05.ld.x8 fetches
+// the four doubles of a level), which takes the store out of the shared-memory budget that capped the occupancy.
+//
 // Rows: a x[z-1] + b x[z] + c x[z+1] = d, with a = 0 on the first and c = 0 on the last zone.
 // At the level of stride s the multipliers that would touch a neighbour outside the plant are
 // exactly 0 (a stays 0 on zones < s, c on zones >= n-s), so fetched values need no masking.
-template <class LuStore>
-WT_DEV void wt_pcr_factor_real(const WtGroup &g, LuStore &lu, int slot0, vd a, vd b, vd c, vb mask) {
-  int l = 0;
-  WT_NOUNROLL
-  for (int s = 1; s < g.n; s <<= 1, ++l) {
-    const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
-    vd r = wt_rcp(b);
-    vd k1 = a * shfl_idx(r, sd);
-    vd k2 = c * shfl_idx(r, su);
-    vd a_dn = shfl_idx(a, sd), c_dn = shfl_idx(c, sd);
-    vd a_up = shfl_idx(a, su), c_up = shfl_idx(c, su);
-    b = b - c_dn * k1 - a_up * k2;
-    a = -(a_dn * k1);
-    c = -(c_up * k2);
-    lu.put(slot0 + 2 * l, k1, mask);
-    lu.put(slot0 + 2 * l + 1, k2, mask);
-  }
-  lu.put(slot0 + 2 * l, wt_rcp(b), mask);
-}
+// The LAST level (stride s = 2^(L-1), 2 s >= n) couples every zone with at most ONE partner (z - s or z + s),
+// so it keeps one multiplier and one exchange per zone instead of two (same bits: the other product was an exact 0).
+// Slots per system: real 2 L  = {k1, k2} x (L-1), k, pivot;  complex 4 L = {k1r, k1i, k2r, k2i} x (L-1), kr, ki, pr, pi.
+
+WT_DEV int wt_pcr_levels(int n) { int L = 0; for (int s = 1; s < n; s <<= 1) ++L; return L; }
+// partner lane of the last PCR level (clamped to the plant: a zone without partner has a zero multiplier)
+WT_DEV vi wt_src_last(const WtGroup &g, int s) { return seli(g.z >= s, g.lane - s, vmini(g.lane + s, g.last_lane)); }
+
 template <class LuStore>
 WT_DEV vd wt_pcr_solve_real(const WtGroup &g, LuStore &lu, int slot0, vd d) {
   int l = 0;
+  const int s_last = 1 << (g.L - 1);
   WT_NOUNROLL
-  for (int s = 1; s < g.n; s <<= 1, ++l)
+  for (int s = 1; s < s_last; s <<= 1, ++l)
     d = d - shfl_idx(d, wt_src_dn(g, s)) * lu.get(slot0 + 2 * l) - shfl_idx(d, wt_src_up(g, s)) * lu.get(slot0 + 2 * l + 1);
-  return d * lu.get(slot0 + 2 * l);
-}
-
-// complex: (ar + i ai) etc.; slots hold (re, im) pairs
-template <class LuStore>
-WT_DEV void wt_pcr_factor_cplx(const WtGroup &g, LuStore &lu, int slot0, vd ar, vd br, vd bi, vd cr,
-                               vb mask) {
-  vd ai = vbroadcast(0.0), ci = vbroadcast(0.0);
-  int l = 0;
-  WT_NOUNROLL
-  for (int s = 1; s < g.n; s <<= 1, ++l) {
-    const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
-    vd iden = wt_rcp(br * br + bi * bi);
-    vd rr = br * iden, ri = -(bi * iden);  // 1 / b
-    vd rdr = shfl_idx(rr, sd), rdi = shfl_idx(ri, sd);
-    vd rur = shfl_idx(rr, su), rui = shfl_idx(ri, su);
-    vd k1r = ar * rdr - ai * rdi, k1i = ar * rdi + ai * rdr;
-    vd k2r = cr * rur - ci * rui, k2i = cr * rui + ci * rur;
-    vd adr = shfl_idx(ar, sd), adi = shfl_idx(ai, sd), cdr = shfl_idx(cr, sd), cdi = shfl_idx(ci, sd);
-    vd aur = shfl_idx(ar, su), aui = shfl_idx(ai, su), cur = shfl_idx(cr, su), cui = shfl_idx(ci, su);
-    br = br - (cdr * k1r - cdi * k1i) - (aur * k2r - aui * k2i);
-    bi = bi - (cdr * k1i + cdi * k1r) - (aur * k2i + aui * k2r);
-    ar = -(adr * k1r - adi * k1i);
-    ai = -(adr * k1i + adi * k1r);
-    cr = -(cur * k2r - cui * k2i);
-    ci = -(cur * k2i + cui * k2r);
-    lu.put(slot0 + 4 * l + 0, k1r, mask);
-    lu.put(slot0 + 4 * l + 1, k1i, mask);
-    lu.put(slot0 + 4 * l + 2, k2r, mask);
-    lu.put(slot0 + 4 * l + 3, k2i, mask);
-  }
-  vd iden = wt_rcp(br * br + bi * bi);
-  lu.put(slot0 + 4 * l + 0, br * iden, mask);
-  lu.put(slot0 + 4 * l + 1, -(bi * iden), mask);
-}
-template <class LuStore>
-WT_DEV void wt_pcr_solve_cplx(const WtGroup &g, LuStore &lu, int slot0, vd &dr, vd &di) {
-  int l = 0;
-  WT_NOUNROLL
-  for (int s = 1; s < g.n; s <<= 1, ++l) {
-    const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
-    vd k1r = lu.get(slot0 + 4 * l + 0), k1i = lu.get(slot0 + 4 * l + 1);
-    vd k2r = lu.get(slot0 + 4 * l + 2), k2i = lu.get(slot0 + 4 * l + 3);
-    vd ddr = shfl_idx(dr, sd), ddi = shfl_idx(di, sd), dur = shfl_idx(dr, su), dui = shfl_idx(di, su);
-    vd nr = dr - (ddr * k1r - ddi * k1i) - (dur * k2r - dui * k2i);
-    vd ni = di - (ddr * k1i + ddi * k1r) - (dur * k2i + dui * k2r);
-    dr = nr;
-    di = ni;
-  }
-  vd rr = lu.get(slot0 + 4 * l + 0), ri = lu.get(slot0 + 4 * l + 1);
-  vd xr = dr * rr - di * ri, xi = dr * ri + di * rr;
-  dr = xr;
-  di = xi;
+  d = d - shfl_idx(d, wt_src_last(g, s_last)) * lu.get(slot0 + 2 * l);
+  return d * lu.get(slot0 + 2 * l + 1);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -529,15 +470,16 @@ struct WtPlantStep {
   WT_DEV void pvset(int k, vd x) { lu->pvput(k, x); }                          // every lane of the plant stores the same value
   WT_DEV void pvset(int k, vd x, vb m) { lu->pvput(k, sel(m, x, lu->pvget(k))); }  // ... where m
 
-  WT_DEV int slot_real(int sys) const { return sys * (2 * g.L + 1); }
-  WT_DEV int slot_cplx(int sys) const { return 3 * (2 * g.L + 1) + sys * (4 * g.L + 2); }
+  WT_DEV int slot_real(int sys) const { return sys * (2 * g.L); }   // real slot space (3 * 2 L slots)
+  WT_DEV int slot_cplx(int sys) const { return sys * (4 * g.L); }   // complex slot space (3 * 4 L slots)
 
   // -------------------------------------------------------------------------------------
   // linear algebra on the block-triangular structure.  System order: 0 = T, 1 = pH, 2 = Cl.
   // -------------------------------------------------------------------------------------
   // All six factorizations (real + complex of T, pH, Cl) share one sweep over the PCR levels:
   // six independent dependency chains per level instead of six sweeps back to back.
-  WT_DEV void factor(vd h, vb mask) {
+  WT_DEV void factor(vd h, vb mask, vb keep) {
+    lu->begin_factor(keep);
     const vd ih = wt_rcp(h);
     const vd mr = WT_MU_REAL * ih, gr = WT_MU_CRE * ih, gi = WT_MU_CIM * ih;
     vd a[3], b[3], c_[3];                         // real rows
@@ -553,8 +495,9 @@ struct WtPlantStep {
     }
     br[0] = gr - J.tt[1]; br[1] = gr - J.pp[1]; br[2] = gr - J.cc[1];
     int l = 0;
+    const int s_last = 1 << (g.L - 1);
     WT_NOUNROLL
-    for (int s = 1; s < g.n; s <<= 1, ++l) {
+    for (int s = 1; s < s_last; s <<= 1, ++l) {
       const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
       // Written PHASE-major (all reciprocals, then all exchanges, then all updates) so that the six
       // factorizations advance together: ptxas keeps the statement order when registers are tight, and
@@ -566,15 +509,15 @@ struct WtPlantStep {
       vd rr[3], ri[3];  // 1 / complex pivot
       WT_UNROLL
       for (int q = 0; q < 3; ++q) { rr[q] = br[q] * inv[3 + q]; ri[q] = -(bi[q] * inv[3 + q]); }
-      vd k1[3], k2[3], k1r[3], k1i[3], k2r[3], k2i[3];
+      vd k1[3], k2[3], kc[3][4];  // kc = k1r, k1i, k2r, k2i
       WT_UNROLL
       for (int q = 0; q < 3; ++q) {
         k1[q] = a[q] * shfl_idx(inv[q], sd);
         k2[q] = c_[q] * shfl_idx(inv[q], su);
         const vd rdr = shfl_idx(rr[q], sd), rdi = shfl_idx(ri[q], sd);
         const vd rur = shfl_idx(rr[q], su), rui = shfl_idx(ri[q], su);
-        k1r[q] = ar[q] * rdr - ai[q] * rdi; k1i[q] = ar[q] * rdi + ai[q] * rdr;
-        k2r[q] = cr[q] * rur - ci[q] * rui; k2i[q] = cr[q] * rui + ci[q] * rur;
+        kc[q][0] = ar[q] * rdr - ai[q] * rdi; kc[q][1] = ar[q] * rdi + ai[q] * rdr;
+        kc[q][2] = cr[q] * rur - ci[q] * rui; kc[q][3] = cr[q] * rui + ci[q] * rur;
       }
       WT_UNROLL
       for (int q = 0; q < 3; ++q) {
@@ -585,35 +528,54 @@ struct WtPlantStep {
         c_[q] = -(c_up * k2[q]);
         const vd adr = shfl_idx(ar[q], sd), adi = shfl_idx(ai[q], sd), cdr = shfl_idx(cr[q], sd), cdi = shfl_idx(ci[q], sd);
         const vd aur = shfl_idx(ar[q], su), aui = shfl_idx(ai[q], su), cur = shfl_idx(cr[q], su), cui = shfl_idx(ci[q], su);
-        br[q] = br[q] - (cdr * k1r[q] - cdi * k1i[q]) - (aur * k2r[q] - aui * k2i[q]);
-        bi[q] = bi[q] - (cdr * k1i[q] + cdi * k1r[q]) - (aur * k2i[q] + aui * k2r[q]);
-        ar[q] = -(adr * k1r[q] - adi * k1i[q]);
-        ai[q] = -(adr * k1i[q] + adi * k1r[q]);
-        cr[q] = -(cur * k2r[q] - cui * k2i[q]);
-        ci[q] = -(cur * k2i[q] + cui * k2r[q]);
+        br[q] = br[q] - (cdr * kc[q][0] - cdi * kc[q][1]) - (aur * kc[q][2] - aui * kc[q][3]);
+        bi[q] = bi[q] - (cdr * kc[q][1] + cdi * kc[q][0]) - (aur * kc[q][3] + aui * kc[q][2]);
+        ar[q] = -(adr * kc[q][0] - adi * kc[q][1]);
+        ai[q] = -(adr * kc[q][1] + adi * kc[q][0]);
+        cr[q] = -(cur * kc[q][2] - cui * kc[q][3]);
+        ci[q] = -(cur * kc[q][3] + cui * kc[q][2]);
       }
       WT_UNROLL
       for (int q = 0; q < 3; ++q) {
         lu->put(slot_real(q) + 2 * l, k1[q], mask);
         lu->put(slot_real(q) + 2 * l + 1, k2[q], mask);
-        lu->put(slot_cplx(q) + 4 * l + 0, k1r[q], mask);
-        lu->put(slot_cplx(q) + 4 * l + 1, k1i[q], mask);
-        lu->put(slot_cplx(q) + 4 * l + 2, k2r[q], mask);
-        lu->put(slot_cplx(q) + 4 * l + 3, k2i[q], mask);
+        lu->cx_put4(slot_cplx(q) + 4 * l, kc[q], mask);
       }
     }
     {
+      // last level: one partner per zone (z - s for the upper zones, z + s for the lower ones), then the pivots
+      const vb upper = g.z >= s_last;
+      const vi sl = wt_src_last(g, s_last);
       vd den[6], inv[6];
+      WT_UNROLL
+      for (int q = 0; q < 3; ++q) { den[q] = b[q]; den[3 + q] = br[q] * br[q] + bi[q] * bi[q]; }
+      wt_rcp_n<6>(den, inv);
+      vd k[3], kc[3][4];  // kc = kr, ki, pivot re, pivot im
+      WT_UNROLL
+      for (int q = 0; q < 3; ++q) {
+        const vd rr = br[q] * inv[3 + q], ri = -(bi[q] * inv[3 + q]);
+        const vd e = sel(upper, a[q], c_[q]), er = sel(upper, ar[q], cr[q]), ei = sel(upper, ai[q], ci[q]);
+        k[q] = e * shfl_idx(inv[q], sl);
+        const vd rpr = shfl_idx(rr, sl), rpi = shfl_idx(ri, sl);
+        kc[q][0] = er * rpr - ei * rpi; kc[q][1] = er * rpi + ei * rpr;
+        const vd ep = shfl_idx(e, sl), epr = shfl_idx(er, sl), epi = shfl_idx(ei, sl);
+        b[q] = b[q] - ep * k[q];
+        br[q] = br[q] - (epr * kc[q][0] - epi * kc[q][1]);
+        bi[q] = bi[q] - (epr * kc[q][1] + epi * kc[q][0]);
+      }
       WT_UNROLL
       for (int q = 0; q < 3; ++q) { den[q] = b[q]; den[3 + q] = br[q] * br[q] + bi[q] * bi[q]; }
       wt_rcp_n<6>(den, inv);
       WT_UNROLL
       for (int q = 0; q < 3; ++q) {
-        lu->put(slot_real(q) + 2 * l, inv[q], mask);
-        lu->put(slot_cplx(q) + 4 * l + 0, br[q] * inv[3 + q], mask);
-        lu->put(slot_cplx(q) + 4 * l + 1, -(bi[q] * inv[3 + q]), mask);
+        kc[q][2] = br[q] * inv[3 + q];
+        kc[q][3] = -(bi[q] * inv[3 + q]);
+        lu->put(slot_real(q) + 2 * l, k[q], mask);
+        lu->put(slot_real(q) + 2 * l + 1, inv[q], mask);
+        lu->cx_put4(slot_cplx(q) + 4 * l, kc[q], mask);
       }
     }
+    lu->end_factor();
   }
   WT_DEV vd tri_mv(const vd *row, vd xdn, vd x, vd xup) const { return (row[0] * xdn + row[1] * x) + row[2] * xup; }
   // (mu/h I - J) x = b, b and x indexed [0 pH, 1 Cl, 2 T]
@@ -628,25 +590,33 @@ struct WtPlantStep {
   WT_DEV void solve_sys3(int q, vd &d, vd &dr, vd &di) {
     const int sr = slot_real(q), sc = slot_cplx(q);
     int l = 0;
+    const int s_last = 1 << (g.L - 1);
     WT_NOUNROLL
-    for (int s = 1; s < g.n; s <<= 1, ++l) {
+    for (int s = 1; s < s_last; s <<= 1, ++l) {
       const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
+      vd kc[4];  // k1r, k1i, k2r, k2i
+      lu->cx_get4(sc + 4 * l, kc);
       vd k1 = lu->get(sr + 2 * l), k2 = lu->get(sr + 2 * l + 1);
-      vd k1r = lu->get(sc + 4 * l + 0), k1i = lu->get(sc + 4 * l + 1);
-      vd k2r = lu->get(sc + 4 * l + 2), k2i = lu->get(sc + 4 * l + 3);
       vd dd = shfl_idx(d, sd), du = shfl_idx(d, su);
       vd ddr = shfl_idx(dr, sd), ddi = shfl_idx(di, sd), dur = shfl_idx(dr, su), dui = shfl_idx(di, su);
       d = d - dd * k1 - du * k2;
-      vd nr = dr - (ddr * k1r - ddi * k1i) - (dur * k2r - dui * k2i);
-      vd ni = di - (ddr * k1i + ddi * k1r) - (dur * k2i + dui * k2r);
+      vd nr = dr - (ddr * kc[0] - ddi * kc[1]) - (dur * kc[2] - dui * kc[3]);
+      vd ni = di - (ddr * kc[1] + ddi * kc[0]) - (dur * kc[3] + dui * kc[2]);
       dr = nr;
       di = ni;
     }
-    d = d * lu->get(sr + 2 * l);
-    vd rr = lu->get(sc + 4 * l + 0), ri = lu->get(sc + 4 * l + 1);
-    vd xr = dr * rr - di * ri, xi = dr * ri + di * rr;
-    dr = xr;
-    di = xi;
+    {
+      const vi sl = wt_src_last(g, s_last);
+      vd kc[4];  // kr, ki, pivot re, pivot im
+      lu->cx_get4(sc + 4 * l, kc);
+      vd k = lu->get(sr + 2 * l), piv = lu->get(sr + 2 * l + 1);
+      vd dp = shfl_idx(d, sl), dpr = shfl_idx(dr, sl), dpi = shfl_idx(di, sl);
+      d = (d - dp * k) * piv;
+      vd nr = dr - (dpr * kc[0] - dpi * kc[1]);
+      vd ni = di - (dpr * kc[1] + dpi * kc[0]);
+      dr = nr * kc[2] - ni * kc[3];
+      di = nr * kc[3] + ni * kc[2];
+    }
   }
   // the real and the complex collocation systems of one Newton iteration together
   WT_DEV void solve_newton(vd *b, vd *br, vd *bi) {
@@ -1061,7 +1031,7 @@ struct WtPlantStep {
       {
         vb m = fget(F_RUNNING) & !fget(F_LU_VALID);
         if (vany(m)) {
-          factor(h, m);
+          factor(h, m, fget(F_RUNNING) & fget(F_LU_VALID));
           lu->cadd(WTC_NLU, seli(m, 2, 0));
           fset(F_LU_VALID, m);
         }

@@ -9,6 +9,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HALT = 2 | 128
+EXCUSE_CEILING = 1e-6  # largest error an ill-conditioned (excused) plant-step may show
 
 
 def relerr(a, b):
@@ -88,7 +89,9 @@ def check_step_parity(wo, got, want, par, bnd, n, t_before, y_before, dt, max_at
     for p in bad:
         b = bnd[p] if bnd.ndim == 2 else bnd
         s = oracle_sensitivity(wo, par[p], b, n, float(t_before[p]), y_before[p], dt, max_attempts, seed=int(p))
-        if s * 10.0 >= r[p] or s > tol / 10.0:
+        # excused only while the error stays within 10x what one ulp of input noise does to the oracle itself,
+        # and never beyond an absolute ceiling
+        if r[p] <= 10.0 * s and r[p] <= EXCUSE_CEILING:
             excused.append((int(p), float(r[p]), s))
         else:
             raise AssertionError(f"{what}: plant {p} off by {r[p]:.3e} (tol {tol:.1e}); the oracle's own 1-ulp "

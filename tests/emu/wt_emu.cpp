@@ -13,6 +13,11 @@ struct EmuLu {
   vd slot[128];
   void put(int s, const vd &x, const vb &m) { for (int l = 0; l < 32; ++l) if (m.v[l]) slot[s].v[l] = x.v[l]; }
   vd get(int s) const { return slot[s]; }
+  vd cslot[128];  // the complex slot space (tensor memory on the GPU)
+  void cx_put4(int s, const vd *x, const vb &m) { for (int i = 0; i < 4; ++i) for (int l = 0; l < 32; ++l) if (m.v[l]) cslot[s + i].v[l] = x[i].v[l]; }
+  void cx_get4(int s, vd *x) const { for (int i = 0; i < 4; ++i) x[i] = cslot[s + i]; }
+  void begin_factor(const vb &) {}
+  void end_factor() {}
   vd cst[CK_N];
   void cput(int k, const vd &x) { cst[k] = x; }
   vd cget(int k) const { return cst[k]; }
