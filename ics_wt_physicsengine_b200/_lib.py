@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # WT_B200_LIB selects an alternative build of the SAME library (A/B tuning builds); never a CPU path
 LIB_PATH = os.environ.get("WT_B200_LIB") or os.path.join(_HERE, "csrc", "libwt_b200.so")
 
-ABI_VERSION = 2   # WT_ABI_VERSION of include/wt_b200.h
+ABI_VERSION = 3   # WT_ABI_VERSION of include/wt_b200.h
 NPAR = 12
 NBND = 10
 NCNT = 8
@@ -32,7 +32,7 @@ CNT_NAMES = ("nfev", "njev", "nlu", "nsteps", "nnewton", "nreject", "nnewton_fai
 
 EXPORTS = (
     "wt_abi_version", "wt_device_count", "wt_last_error", "wt_step", "wt_advance", "wt_derivatives",
-    "wt_step_host", "wt_calc_ph", "wt_measure_fp64_peak", "wt_stats", "wt_stats_size", "wt_stats_scratch_doubles",
+    "wt_step_host", "wt_step_workspace_bytes", "wt_calc_ph", "wt_measure_fp64_peak", "wt_stats", "wt_stats_size", "wt_stats_scratch_doubles",
     "wt_sensors_init", "wt_sensors_calibrate", "wt_sensors_read", "wt_diagnostics", "wt_register_image",
     "wt_sensors_maintain", "wt_sensor_window_stats",
 )
@@ -63,10 +63,12 @@ def lib() -> C.CDLL:
     L.wt_abi_version.restype = C.c_int
     L.wt_device_count.restype = C.c_int
     L.wt_last_error.restype = C.c_char_p
-    L.wt_step.argtypes = [C.c_int, C.c_int, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, up, ip, C.c_int, vp]
+    L.wt_step.argtypes = [C.c_int, C.c_int, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, up, ip, C.c_int, vp, vp]
     L.wt_step.restype = C.c_int
+    L.wt_step_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    L.wt_step_workspace_bytes.restype = C.c_size_t
     L.wt_advance.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, up, ip,
-                             C.c_int, ip, ip, vp]
+                             C.c_int, ip, ip, vp, vp]
     L.wt_advance.restype = C.c_int
     L.wt_derivatives.argtypes = [C.c_int, C.c_int, dp, dp, C.c_int, dp, dp, ip, vp]
     L.wt_derivatives.restype = C.c_int

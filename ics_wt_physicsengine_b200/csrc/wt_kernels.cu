@@ -110,13 +110,15 @@ __host__ __device__ inline int wt_lu_slots(int n) {
   for (int s = 1; s < n; s <<= 1) ++L;
   return 3 * 2 * L;
 }
-// + the lane-private constants (LK_*) kept after the LU multipliers
-__host__ __device__ inline int wt_lane_slots(int n) { return wt_lu_slots(n) + LK_N; }
+// + the lane-private constants (LK_*) and the parked per-lane solver state (WtPlantStep::PK_*) after the LU multipliers
+#define WT_PARK_SLOTS 27
+__host__ __device__ inline int wt_lane_slots(int n) { return wt_lu_slots(n) + LK_N + WT_PARK_SLOTS; }
 // doubles of shared memory per warp: LU slots for 32 lanes + constants for (32/n + 1) plants
 #define WT_PLANT_DOUBLES (CK_N + WTC_NCNT / 2 + 10)  // per-plant constants + path counters (ints) + step-control scalars (PV_N)
 __host__ __device__ inline int wt_warp_smem_doubles(int n) { return wt_lane_slots(n) * 32 + (32 / n + 1) * WT_PLANT_DOUBLES; }
 
 static_assert(WtPlantStep<SmemLu>::PV_N == 10 && WTC_NCNT % 2 == 0, "per-plant store layout out of sync with WT_PLANT_DOUBLES");
+static_assert(WtPlantStep<SmemLu>::PK_N == WT_PARK_SLOTS, "parking slots out of sync with the core");
 static_assert(24 * 5 <= WT_TMEM_COLS, "complex LU slots of n <= 32 zones (L <= 5) must fit the tensor-memory allocation");
 
 struct StepArgs {
@@ -130,6 +132,8 @@ struct StepArgs {
   int32_t *counters;
   const int32_t *order;  // optional: slot -> plant (e.g. plants sorted by the cost of their last step)
   int32_t *cost;         // optional: per-plant work of this launch (collocation solves + Newton iterations)
+  char *ws;              // workspace (wt_step_workspace_bytes): work-queue counter + the begin -> run hand-off rows
+  int n_groups;          // warps' worth of plants in this launch (ceil(P / plants per warp))
 };
 
 #ifndef WT_STEP_WARPS
@@ -139,24 +143,119 @@ struct StepArgs {
 #define WT_STEP_MINBLOCKS 3
 #endif
 #ifndef WT_STEP_CARVEOUT_PCT
-#define WT_STEP_CARVEOUT_PCT 50  // percent of the 228 KB: three blocks of ~36 KB (n = 10) or ~43 KB (n = 20)
+#define WT_STEP_CARVEOUT_PCT 100  // percent of the 228 KB: three blocks of ~63 KB (n = 10) or ~69 KB (n = 20)
 #endif
 #define WT_MAX_DEVICES 64
+
+// ---------------------------------------------------------------------------------------
+// One step = TWO kernels.  The fused kernel of round 1 (5,000 SASS instructions, 80 KB) was bound by instruction
+// fetch: every warp streamed the whole kernel through a ~32 KB SM instruction cache once per step, the GPC-level
+// instruction cache ran at 84-95 % of its request rate, and a block kept its registers / shared memory until its
+// slowest warp had finished (30 % of the resident warp slots idle).  So:
+//   K1a  wt_step_begin_kernel  the once-per-step work whose control flow is the same for every plant (constants,
+//        f0, select_initial_step, the first finite-difference Jacobian).  All warps of all blocks walk the same code
+//        at the same time, so a fetched line serves every warp of the SM.  Leaves 22 doubles per lane + 2 per plant
+//        in the hand-off rows of the workspace (coalesced 256 B rows per warp).
+//   K1b  wt_step_run_kernel    the data-dependent attempt loop, as PERSISTENT warps: a warp that has finished its
+//        group of plants takes the next group from a work queue (one atomicAdd), so no warp slot waits for a block
+//        mate and every resident warp executes the same ~2,900 instructions of loop code.
+// ---------------------------------------------------------------------------------------
+enum { HO_F = 0, HO_JFAC = 3, HO_JD = 6, HO_JPT = 15, HO_JCT = 18, HO_JCP = 21, HO_SELF_H = 22, HO_FL = 23, HO_ROWS = 24 };
+#define WT_WS_HEADER 256  // bytes: [0] the work-queue counter of K1b
+__host__ __device__ inline size_t wt_ws_bytes(long long n_groups) { return WT_WS_HEADER + (size_t)n_groups * HO_ROWS * 32 * sizeof(double); }
+
+// shared memory per warp of K1a: no LU slots, only the lane constants, the parking slots and the per-plant rows
+__host__ __device__ inline int wt_begin_lane_slots() { return LK_N + WT_PARK_SLOTS; }
+__host__ __device__ inline int wt_begin_smem_doubles(int n) { return wt_begin_lane_slots() * 32 + (32 / n + 1) * WT_PLANT_DOUBLES; }
+
+// lane <-> plant mapping of group `wg` (both kernels use the same one)
+struct LaneMap { int p, z, gi; bool in_plant; };
+__device__ __forceinline__ LaneMap wt_lane_map(const StepArgs &a, long long wg, int lane, int n, int gpw) {
+  LaneMap m;
+  m.gi = lane / n;
+  const long long pl = wg * gpw + m.gi;
+  m.in_plant = m.gi < gpw && pl < a.P;
+  m.p = m.in_plant ? (a.order ? a.order[pl] : (int)pl) : 0;
+  m.z = m.in_plant ? lane - m.gi * n : 0;
+  return m;
+}
 
 // NZ > 0: the zone count is a compile-time constant (the BASELINE shapes n = 10 and n = 20): lane geometry, PCR level
 // count and every LU slot offset fold to immediates after inlining; NZ = 0 reads n from the arguments.
 template <int WARPS, int NZ>
-#if WT_STEP_MINBLOCKS > 0
-__global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_kernel(StepArgs a) {
-#elif defined(WT_STEP_MAXNREG)
-__global__ void __maxnreg__(WT_STEP_MAXNREG) wt_step_kernel(StepArgs a) {
-#else
-__global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
-#endif
+__global__ void __launch_bounds__(WARPS * 32, 3) wt_step_begin_kernel(StepArgs a) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = NZ > 0 ? NZ : a.n, gpw = 32 / n;
+  const long long wg = (long long)blockIdx.x * WARPS + warp;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *(int *)a.ws = 0;  // the work queue of the run kernel that follows
+  if (wg >= a.n_groups) return;
+  const LaneMap lm = wt_lane_map(a, wg, lane, n, gpw);
+  const int p = lm.p, z = lm.z;
+  const size_t P = (size_t)a.ld;
+
+  // every global load issued back to back before the first use (one round trip to HBM)
+  const uint32_t st_in = a.status[p];
+  double par[WTP_NPAR], bnd[WTB_NBND];
+#pragma unroll
+  for (int k = 0; k < WTP_NPAR; ++k) par[k] = a.par[(size_t)k * P + p];
+#pragma unroll
+  for (int k = 0; k < WTB_NBND; ++k) bnd[k] = a.bnd[a.bnd_stride ? (size_t)k * P + p : (size_t)k];
+  const double t = a.time[p];
+  double y0[3];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) y0[v] = a.y[((size_t)v * n + z) * P + p];
+
+  const bool on = lm.in_plant && !(st_in & WTS_HALT_MASK);
+  double *ho = (double *)(a.ws + WT_WS_HEADER) + (size_t)wg * HO_ROWS * 32 + lane;
+  if (!__any_sync(0xffffffffu, on)) {
+    ho[HO_FL * 32] = __longlong_as_double(0ll);  // nothing running in this group
+    return;
+  }
+  SmemLu lu;
+  lu.p = smem + (size_t)warp * wt_begin_smem_doubles(n) + lane;
+  lu.cp = smem + (size_t)warp * wt_begin_smem_doubles(n) + wt_begin_lane_slots() * 32 + (lm.gi < gpw ? lm.gi : gpw) * WT_PLANT_DOUBLES;
+  lu.ci = (int *)(lu.cp + CK_N);
+  lu.tm = 0;
+  lu.rmw = false;
+  lu.czero();
+  WtPlantStep<SmemLu> ps;
+  ps.g = wt_make_group(n, a.inv_sqrtN, a.inv_sqrt3N);
+  ps.lu = &lu;
+  ps.pk0 = LK_N;
+  ps.c = wt_make_const(&lu, ps.g, 0, par, bnd);
+#pragma unroll
+  for (int v = 0; v < 3; ++v) ps.y[v] = y0[v];
+  ps.begin(t, a.dt, on);
+
+  // hand-off rows (coalesced: row k of group wg is 32 consecutive doubles)
+  typedef WtPlantStep<SmemLu> PS;
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    ho[(HO_F + v) * 32] = ps.pk(PS::PK_F + v);
+    ho[(HO_JFAC + v) * 32] = ps.pk(PS::PK_JFAC + v);
+    ho[(HO_JPT + v) * 32] = ps.J.pt[v];
+    ho[(HO_JCT + v) * 32] = ps.J.ct[v];
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) ho[(HO_JD + k) * 32] = ps.pk(PS::PK_JD + k);
+  ho[HO_JCP * 32] = ps.J.cp;
+  ho[HO_SELF_H * 32] = ps.pv(PS::PV_SELF_H);
+  ho[HO_FL * 32] = __longlong_as_double((long long)ps.fl);
+  if (on && z == 0 && a.counters) {
+    atomicAdd(&a.counters[(size_t)WTC_NFEV * P + p], lu.cval(WTC_NFEV));
+    atomicAdd(&a.counters[(size_t)WTC_NJEV * P + p], lu.cval(WTC_NJEV));
+    if (lu.cval(WTC_JAC_RETRY)) atomicAdd(&a.counters[(size_t)WTC_JAC_RETRY * P + p], lu.cval(WTC_JAC_RETRY));
+  }
+}
+
+template <int WARPS, int NZ>
+__global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_run_kernel(StepArgs a) {
   extern __shared__ double smem[];
   static_assert(WARPS == 4, "one warp per tensor-memory lane quarter");
   __shared__ uint32_t tmem_slot;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // (the warp index through a warp reduction: a value ptxas knows to be warp-uniform, see the queue below)
+  const int lane = threadIdx.x & 31, warp = (int)__reduce_max_sync(0xffffffffu, threadIdx.x >> 5);
   // tensor memory for the complex LU multipliers: warp 0 allocates the block's columns (tcgen05.alloc writes the
   // address to shared memory) and gives up the allocation permit so that the other resident blocks can allocate
   if (warp == 0) {
@@ -170,83 +269,117 @@ __global__ void __launch_bounds__(WARPS * 32) wt_step_kernel(StepArgs a) {
   const uint32_t tmem_base = tmem_slot;
 
   const int n = NZ > 0 ? NZ : a.n, gpw = 32 / n;
-  const long long wg = (long long)blockIdx.x * WARPS + warp;
-  const int gi = lane / n;
-  const long long pl = wg * gpw + gi;
-  const bool in_plant = gi < gpw && pl < a.P;
-  const int p = in_plant ? (a.order ? a.order[pl] : (int)pl) : 0;
-  const int z = in_plant ? lane - gi * n : 0;
   const size_t P = (size_t)a.ld;  // row stride; a.P bounds the plant index
+  typedef WtPlantStep<SmemLu> PS;
+  SmemLu lu;
+  lu.p = smem + (size_t)warp * wt_warp_smem_doubles(n) + lane;
+  lu.ci = nullptr;
+  lu.cp = nullptr;
+  lu.tm = tmem_base + ((uint32_t)(warp * 32) << 16);
+  lu.rmw = false;
+  PS ps;
+  ps.g = wt_make_group(n, a.inv_sqrtN, a.inv_sqrt3N);
+  ps.lu = &lu;
+  ps.pk0 = wt_lu_slots(n) + LK_N;
+  int *queue = (int *)a.ws;
 
-  // Every global load of the launch is issued here, back to back and before the first use: the prologue
-  // then waits for ONE round trip to HBM instead of one per dependent group (status -> params -> state).
-  const uint32_t st_in = a.status[p];
-  double par[WTP_NPAR], bnd[WTB_NBND];
-#pragma unroll
-  for (int k = 0; k < WTP_NPAR; ++k) par[k] = a.par[(size_t)k * P + p];
-#pragma unroll
-  for (int k = 0; k < WTB_NBND; ++k) bnd[k] = a.bnd[a.bnd_stride ? (size_t)k * P + p : (size_t)k];
-  double t = a.time[p];
-  double y0[3];
-#pragma unroll
-  for (int v = 0; v < 3; ++v) y0[v] = a.y[((size_t)v * n + z) * P + p];
-
-  bool on = in_plant && !(st_in & WTS_HALT_MASK);
-  // (a warp without a live plant skips the work but still meets the block at the barrier before the TMEM is freed)
-  if (__any_sync(0xffffffffu, on)) {
-    SmemLu lu;
-    lu.p = smem + (size_t)warp * wt_warp_smem_doubles(n) + lane;
-    lu.cp = smem + (size_t)warp * wt_warp_smem_doubles(n) + wt_lane_slots(n) * 32 + (gi < gpw ? gi : gpw) * WT_PLANT_DOUBLES;
-    lu.ci = (int *)(lu.cp + CK_N);
-    lu.tm = tmem_base + ((uint32_t)(warp * 32) << 16);
-    lu.rmw = false;
-    lu.czero();
-
-    WtPlantStep<SmemLu> ps;
-    ps.g = wt_make_group(n, a.inv_sqrtN, a.inv_sqrt3N);
-    ps.lu = &lu;
-    // reactor.py:500: flow_rate = inlet + acid + chlorine flow, parked with the plant's constants until the epilogue
-    lu.cput(CK_flow, bnd[WTB_INLET_FLOW] + bnd[WTB_ACID_FLOW] + bnd[WTB_CL_FLOW]);
-    ps.c = wt_make_const(&lu, ps.g, wt_lu_slots(n), par, bnd);
-#pragma unroll
-    for (int v = 0; v < 3; ++v) ps.y[v] = y0[v];
-
-    uint32_t st = st_in;
-    double der[3] = {0.0, 0.0, 0.0};
-    bool stepped = false;
-
-    for (int s = 0; s < a.n_steps; ++s) {
-      if (!__any_sync(0xffffffffu, on)) break;
-      double yin[3] = {ps.y[0], ps.y[1], ps.y[2]};
-      ps.integrate(t, a.dt, on, a.max_attempts);
-      bool adv;
-      int sb = wt_finish_step(ps, yin, der, adv);
-      if (on) {
-        st = (uint32_t)sb;
-        if (adv) { t += a.dt; stepped = true; }
-        if (sb & WTS_HALT_MASK) on = false;
-      }
+  // persistent warps: the first group by position, the following ones from the queue
+  long long wg = (long long)blockIdx.x * WARPS + warp;
+  const long long first_wave = (long long)gridDim.x * WARPS;
+#pragma unroll 1
+  while (wg < a.n_groups) {
+    // The optional-argument tests below are loop invariant; left visible, the compiler "unswitches" the loop into
+    // one full copy of the 5,000-instruction body per combination.  Laundering them through an empty asm keeps ONE copy.
+    const int32_t *order = a.order;
+    int32_t *counters = a.counters, *cost = a.cost;
+    double *derived = a.derived, *flow = a.flow;
+    int bnd_stride = a.bnd_stride, or_status = a.n_steps;
+    asm volatile("" : "+l"(order), "+l"(counters), "+l"(cost), "+l"(derived), "+l"(flow), "+r"(bnd_stride), "+r"(or_status));
+    LaneMap lm;
+    {
+      lm.gi = lane / n;
+      const long long pl = wg * gpw + lm.gi;
+      lm.in_plant = lm.gi < gpw && pl < a.P;
+      lm.p = lm.in_plant ? (order ? order[pl] : (int)pl) : 0;
+      lm.z = lm.in_plant ? lane - lm.gi * n : 0;
     }
+    const int p = lm.p, z = lm.z;
+    const double *ho = (const double *)(a.ws + WT_WS_HEADER) + (size_t)wg * HO_ROWS * 32 + lane;
+    const int fl_in = (int)__double_as_longlong(ho[HO_FL * 32]);
+    const uint32_t st_in = a.status[p];
+    const bool live = lm.in_plant && !(st_in & WTS_HALT_MASK);
+    if (__any_sync(0xffffffffu, live)) {
+      // all loads of the group issued back to back
+      double par[WTP_NPAR], bnd[WTB_NBND], hrow[HO_SELF_H + 1];
+#pragma unroll
+      for (int k = 0; k < WTP_NPAR; ++k) par[k] = a.par[(size_t)k * P + p];
+#pragma unroll
+      for (int k = 0; k < WTB_NBND; ++k) bnd[k] = a.bnd[bnd_stride ? (size_t)k * P + p : (size_t)k];
+      double t = a.time[p];
+      double y0[3];
+#pragma unroll
+      for (int v = 0; v < 3; ++v) y0[v] = a.y[((size_t)v * n + z) * P + p];
+#pragma unroll
+      for (int k = 0; k <= HO_SELF_H; ++k) hrow[k] = ho[k * 32];
 
-    if (in_plant && !(st_in & WTS_HALT_MASK)) {
+      lu.cp = smem + (size_t)warp * wt_warp_smem_doubles(n) + wt_lane_slots(n) * 32 + (lm.gi < gpw ? lm.gi : gpw) * WT_PLANT_DOUBLES;
+      lu.ci = (int *)(lu.cp + CK_N);
+      __syncwarp();  // the previous group's per-plant rows are dead
+      lu.czero();
+      // reactor.py:500: flow_rate = inlet + acid + chlorine flow, parked with the plant's constants until the epilogue
+      lu.cput(CK_flow, bnd[WTB_INLET_FLOW] + bnd[WTB_ACID_FLOW] + bnd[WTB_CL_FLOW]);
+      ps.c = wt_make_const(&lu, ps.g, wt_lu_slots(n), par, bnd);
 #pragma unroll
-      for (int v = 0; v < 3; ++v) a.y[((size_t)v * n + z) * P + p] = ps.y[v];
-      if (a.derived && stepped) {
+      for (int v = 0; v < 3; ++v) ps.y[v] = y0[v];
+      // solver state as begin() left it
+      ps.reset(t, a.dt, live);
+      ps.fl = fl_in;
+      ps.pvset(PS::PV_SELF_H, hrow[HO_SELF_H]);
+      {
+        const bool all = true;
 #pragma unroll
-        for (int v = 0; v < 3; ++v) a.derived[((size_t)v * n + z) * P + p] = der[v];
-      }
-      if (z == 0) {
-        a.time[p] = t;
-        a.status[p] = st;
-        if (stepped && a.flow) a.flow[p] = lu.cget(CK_flow);
-        if (a.counters) {
-          // fire-and-forget reductions: a load-add-store here made the whole warp wait for eight loads
-#pragma unroll
-          for (int k = 0; k < WTC_NCNT; ++k) atomicAdd(&a.counters[(size_t)k * P + p], lu.cval(k));
+        for (int v = 0; v < 3; ++v) {
+          ps.pkset(PS::PK_F + v, hrow[HO_F + v], all);
+          ps.pkset(PS::PK_JFAC + v, hrow[HO_JFAC + v], all);
+          ps.J.pt[v] = hrow[HO_JPT + v];
+          ps.J.ct[v] = hrow[HO_JCT + v];
         }
-        if (a.cost) a.cost[p] = lu.cval(WTC_NSTEPS) + lu.cval(WTC_NREJECT) + lu.cval(WTC_NNEWTON_FAIL) + lu.cval(WTC_NNEWTON);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) ps.pkset(PS::PK_JD + k, hrow[HO_JD + k], all);
+        ps.J.cp = hrow[HO_JCP];
+      }
+      double yin[3] = {ps.y[0], ps.y[1], ps.y[2]};
+      ps.run(t, a.max_attempts);
+      double der[3];
+      bool adv;
+      const int sb = wt_finish_step(ps, yin, der, adv);
+      if (live) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) a.y[((size_t)v * n + z) * P + p] = ps.y[v];
+        if (derived && adv) {
+#pragma unroll
+          for (int v = 0; v < 3; ++v) derived[((size_t)v * n + z) * P + p] = der[v];
+        }
+        if (z == 0) {
+          if (adv) a.time[p] = t + a.dt;
+          a.status[p] = (uint32_t)sb | (or_status > 0 ? (st_in & ~(uint32_t)WTS_HALT_MASK) : 0u);
+          if (adv && flow) flow[p] = lu.cget(CK_flow);
+          if (counters) {
+            // fire-and-forget reductions: a load-add-store here made the whole warp wait for eight loads
+#pragma unroll
+            for (int k = 0; k < WTC_NCNT; ++k)
+              if (lu.cval(k)) atomicAdd(&counters[(size_t)k * P + p], lu.cval(k));
+          }
+          if (cost) cost[p] = lu.cval(WTC_NSTEPS) + lu.cval(WTC_NREJECT) + lu.cval(WTC_NNEWTON_FAIL) + lu.cval(WTC_NNEWTON);
+        }
       }
     }
+    // next group of plants: one atomic per warp
+    // (the warp reduction returns its result in a uniform register: ptxas then KNOWS the loop is warp-uniform and
+    // keeps the body free of WARPSYNC / divergence handling, which otherwise doubles its size)
+    unsigned nx = 0;
+    if (lane == 0) nx = (unsigned)atomicAdd(queue, 1);
+    wg = first_wave + (long long)__reduce_max_sync(0xffffffffu, nx);
   }
   // every warp is done with its tensor-memory columns: the allocating warp frees them
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -602,65 +735,98 @@ static int check_common(int P, int n) {
   return 0;
 }
 
+struct StepKernels { void (*begin)(StepArgs); void (*run)(StepArgs); };
+static StepKernels step_kernels(int n) {
+  if (getenv("WT_B200_GENERIC_N")) n = 0;  // A/B runs
+  if (n == 10) return {wt_step_begin_kernel<WT_STEP_WARPS, 10>, wt_step_run_kernel<WT_STEP_WARPS, 10>};
+  if (n == 20) return {wt_step_begin_kernel<WT_STEP_WARPS, 20>, wt_step_run_kernel<WT_STEP_WARPS, 20>};
+  return {wt_step_begin_kernel<WT_STEP_WARPS, 0>, wt_step_run_kernel<WT_STEP_WARPS, 0>};
+}
+
+// per-device launch facts, set up once per device under a lock (several host threads, one per device, may call in)
+struct DevInfo { bool done; int sms; };
+static int device_info(DevInfo *out) {
+  static std::mutex mu;
+  static DevInfo info[WT_MAX_DEVICES];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= WT_MAX_DEVICES) return cuda_err(e != cudaSuccess ? e : cudaErrorInvalidDevice, "cudaGetDevice");
+  std::lock_guard<std::mutex> lock(mu);
+  if (!info[dev].done) {
+    // the attributes belong to the (kernel, device) pair
+    const int shapes[3] = {0, 10, 20};
+    int pct = WT_STEP_CARVEOUT_PCT;
+    if (const char *ev = getenv("WT_B200_CARVEOUT_PCT")) pct = atoi(ev);  // tuning runs
+    for (int i = 0; i < 3; ++i) {
+      StepKernels k = step_kernels(shapes[i]);
+      e = cudaFuncSetAttribute(k.run, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k.begin, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      // shared memory for the resident blocks, the rest of the 256 KB stays L1 (it backs the register spills)
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k.run, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute");
+    }
+    e = cudaDeviceGetAttribute(&info[dev].sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return cuda_err(e, "cudaDeviceGetAttribute");
+    info[dev].done = true;
+  }
+  *out = info[dev];
+  return 0;
+}
+
 static int launch_step(StepArgs a, cudaStream_t s) {
   a.inv_sqrtN = 1.0 / sqrt((double)(3 * a.n));
   a.inv_sqrt3N = 1.0 / sqrt((double)(9 * a.n));
   const int gpw = 32 / a.n;
-  const long long warps = ((long long)a.P + gpw - 1) / gpw;
-  const long long blocks = (warps + WT_STEP_WARPS - 1) / WT_STEP_WARPS;
-  size_t smem = (size_t)WT_STEP_WARPS * wt_warp_smem_doubles(a.n) * sizeof(double);
-  if (const char *pad = getenv("WT_B200_SMEM_PAD_KB")) smem += (size_t)atoi(pad) * 1024;  // occupancy experiments only
-  void (*kern)(StepArgs) = a.n == 10 ? wt_step_kernel<WT_STEP_WARPS, 10>
-                           : (a.n == 20 ? wt_step_kernel<WT_STEP_WARPS, 20> : wt_step_kernel<WT_STEP_WARPS, 0>);
-  if (getenv("WT_B200_GENERIC_N")) kern = wt_step_kernel<WT_STEP_WARPS, 0>;  // A/B runs
-  // The attributes belong to the (kernel, device) pair: set them once per device, under a lock (several host
-  // threads, one per device, may call in).
-  {
-    static std::mutex mu;
-    static bool attr_done[WT_MAX_DEVICES];
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess || dev < 0 || dev >= WT_MAX_DEVICES) return cuda_err(e != cudaSuccess ? e : cudaErrorInvalidDevice, "cudaGetDevice");
-    std::lock_guard<std::mutex> lock(mu);
-    if (!attr_done[dev]) {
-      void (*all[3])(StepArgs) = {wt_step_kernel<WT_STEP_WARPS, 0>, wt_step_kernel<WT_STEP_WARPS, 10>, wt_step_kernel<WT_STEP_WARPS, 20>};
-      for (int i = 0; i < 3; ++i) {
-        e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute");
-        // shared memory for the resident blocks, the rest of the 256 KB stays L1 (it backs the register spills)
-        int pct = WT_STEP_CARVEOUT_PCT;
-        if (const char *ev = getenv("WT_B200_CARVEOUT_PCT")) pct = atoi(ev);  // tuning runs
-        e = cudaFuncSetAttribute(all[i], cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(carveout)");
-      }
-      attr_done[dev] = true;
-    }
+  const long long groups = ((long long)a.P + gpw - 1) / gpw;
+  a.n_groups = (int)groups;
+  const long long blocks = (groups + WT_STEP_WARPS - 1) / WT_STEP_WARPS;
+  DevInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  int per_sm = WT_STEP_MINBLOCKS;
+  if (const char *ev = getenv("WT_B200_RUN_BLOCKS_PER_SM")) per_sm = atoi(ev);  // tuning runs
+  long long run_blocks = (long long)di.sms * per_sm;
+  if (run_blocks > blocks) run_blocks = blocks;
+  const size_t smem_run = (size_t)WT_STEP_WARPS * wt_warp_smem_doubles(a.n) * sizeof(double);
+  const size_t smem_begin = (size_t)WT_STEP_WARPS * wt_begin_smem_doubles(a.n) * sizeof(double);
+  const StepKernels k = step_kernels(a.n);
+  const int n_steps = a.n_steps;
+  for (int i = 0; i < n_steps; ++i) {
+    a.n_steps = i;  // > 0: OR the non-halting status bits of the earlier steps into this step's word
+    k.begin<<<(unsigned)blocks, WT_STEP_WARPS * 32, smem_begin, s>>>(a);
+    k.run<<<(unsigned)run_blocks, WT_STEP_WARPS * 32, smem_run, s>>>(a);
   }
-  kern<<<(unsigned)blocks, WT_STEP_WARPS * 32, smem, s>>>(a);
-  return cuda_err(cudaGetLastError(), "wt_step_kernel launch");
+  return cuda_err(cudaGetLastError(), "wt_step kernels launch");
+}
+
+size_t wt_step_workspace_bytes(int P, int n) {
+  if (P <= 0 || n < 2 || n > WT_MAX_ZONES) return 0;
+  const int gpw = 32 / n;
+  return wt_ws_bytes(((long long)P + gpw - 1) / gpw);
 }
 
 int wt_advance(int P, int n, int n_steps, double dt, const double *par, const double *bnd, int bnd_stride,
                double *time, double *y, double *flow, double *derived, uint32_t *status, int32_t *counters,
-               int max_attempts, const int32_t *order, int32_t *cost, void *stream) {
+               int max_attempts, const int32_t *order, int32_t *cost, void *workspace, void *stream) {
   int rc = check_common(P, n);
   if (rc) return rc;
   if (!(dt > 0.0)) return set_err(WT_ERR_BAD_ARG, "dt must be positive");
   if (n_steps < 1) return set_err(WT_ERR_BAD_ARG, "n_steps must be >= 1");
   if (!par || !bnd || !time || !y || !status) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  if (!workspace) return set_err(WT_ERR_BAD_ARG, "null workspace (wt_step_workspace_bytes)");
   if (bnd_stride != 0 && bnd_stride != P) return set_err(WT_ERR_BAD_ARG, "bnd_stride must be 0 or P");
   StepArgs a;
   a.P = P; a.ld = P; a.n = n; a.n_steps = n_steps; a.bnd_stride = bnd_stride; a.max_attempts = max_attempts;
   a.dt = dt; a.par = par; a.bnd = bnd; a.time = time; a.y = y; a.flow = flow; a.derived = derived;
-  a.status = status; a.counters = counters; a.order = order; a.cost = cost;
+  a.status = status; a.counters = counters; a.order = order; a.cost = cost; a.ws = (char *)workspace;
   return launch_step(a, (cudaStream_t)stream);
 }
 
 int wt_step(int P, int n, double dt, const double *par, const double *bnd, int bnd_stride, double *time,
             double *y, double *flow, double *derived, uint32_t *status, int32_t *counters, int max_attempts,
-            void *stream) {
+            void *workspace, void *stream) {
   return wt_advance(P, n, 1, dt, par, bnd, bnd_stride, time, y, flow, derived, status, counters, max_attempts, nullptr,
-                    nullptr, stream);
+                    nullptr, workspace, stream);
 }
 
 int wt_derivatives(int P, int n, const double *par, const double *bnd, int bnd_stride, const double *y,
@@ -844,16 +1010,17 @@ int wt_sensors_read(int P, int n, long long plant0, unsigned read_index, double 
 }
 
 // Host-buffer path: per device, one workspace grown on demand, three copy/compute streams, one event, and the
-// shape whose constants are resident.
+// shape whose constants are resident.  One call at a time per device (the context is locked for the call).
 enum { WT_HOST_NSTREAM = 3 };
 struct HostCtx {
+  std::mutex mu;
   size_t cap_bytes;
   char *dev;
   cudaStream_t st[WT_HOST_NSTREAM];
   cudaEvent_t ev;
   int res_P, res_n;
 };
-static HostCtx g_host[64];
+static HostCtx g_host[WT_MAX_DEVICES];
 
 int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, int bnd_stride, double *time,
                  double *y, double *flow, uint32_t *status, int max_attempts, int flags) {
@@ -862,16 +1029,33 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
   if (!par || !bnd || !time || !y || !status) return set_err(WT_ERR_BAD_ARG, "null host pointer");
   if (bnd_stride != 0 && bnd_stride != P) return set_err(WT_ERR_BAD_ARG, "bnd_stride must be 0 or P");
   if (!(dt > 0.0)) return set_err(WT_ERR_BAD_ARG, "dt must be positive");
+  // Pipelined over column slabs of the SoA arrays: slab c's H2D copies, its kernels and its D2H copies go to
+  // stream c % 3, so the copies of one slab overlap the kernels of another (PCIe is full duplex and the
+  // device has separate copy engines per direction).  A slab of plants is a column range of every row:
+  // 2-D copies with the row pitch P.  Plants are independent, so slabs need no ordering among themselves.
+  // Slab count: at least 12 (four rounds over the three streams keep every engine busy even for the 131,072-plant
+  // shard of an 8-GPU run), at most 32, about 32,768 plants (9 MB of state) each in between.
+  enum { NSTREAM = WT_HOST_NSTREAM };
+  int slabs = P / 32768;
+  if (slabs < 12) slabs = 12;
+  if (slabs > 32) slabs = 32;
+  if (const char *e = getenv("WT_B200_HOST_SLABS")) slabs = atoi(e);  // tuning runs
+  if (slabs > (P + 95) / 96) slabs = (P + 95) / 96;
+  if (slabs < 1) slabs = 1;
+  const int per = ((P + slabs - 1) / slabs + 31) & ~31;  // plants per slab, a multiple of the warp width
   const size_t Pz = (size_t)P;
   const size_t b_par = WT_NPAR * Pz * 8, b_bnd = WT_NBND * (bnd_stride ? Pz : 1) * 8, b_t = Pz * 8,
                b_y = 3 * (size_t)n * Pz * 8, b_f = Pz * 8, b_s = Pz * 4;
-  const size_t total = b_par + b_bnd + b_t + b_y + b_f + b_s + 256 * 6;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_ws = al(wt_step_workspace_bytes(per, n));  // one step workspace per stream
+  const size_t total = al(b_par) + al(b_bnd) + al(b_t) + al(b_y) + al(b_f) + al(b_s) + NSTREAM * b_ws;
   int dev = 0;
   {
     cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess || dev < 0 || dev >= 64) return cuda_err(e != cudaSuccess ? e : cudaErrorInvalidDevice, "cudaGetDevice");
+    if (e != cudaSuccess || dev < 0 || dev >= WT_MAX_DEVICES) return cuda_err(e != cudaSuccess ? e : cudaErrorInvalidDevice, "cudaGetDevice");
   }
   HostCtx &g_ws = g_host[dev];
+  std::lock_guard<std::mutex> lock(g_ws.mu);
   if (total > g_ws.cap_bytes) {
     flags &= ~1;
     if (g_ws.dev) cudaFree(g_ws.dev);
@@ -881,23 +1065,18 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
     if (e != cudaSuccess) { cuda_err(e, "cudaMalloc workspace"); return WT_ERR_ALLOC; }
     g_ws.cap_bytes = total;
   }
-  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   char *q = g_ws.dev;
   double *d_par = (double *)q; q += al(b_par);
   double *d_bnd = (double *)q; q += al(b_bnd);
   double *d_t = (double *)q; q += al(b_t);
   double *d_y = (double *)q; q += al(b_y);
   double *d_f = (double *)q; q += al(b_f);
-  uint32_t *d_s = (uint32_t *)q;
+  uint32_t *d_s = (uint32_t *)q; q += al(b_s);
+  char *d_ws = q;
   // WT_HOST_PARAMS_RESIDENT: the derived constants uploaded by the previous call (same P, n) are reused
   const bool up_par = !(flags & 1) || g_ws.res_P != P || g_ws.res_n != n;
   g_ws.res_P = P; g_ws.res_n = n;
 
-  // Pipelined over column slabs of the SoA arrays: slab c's H2D copies, its kernel and its D2H copies go to
-  // stream c % 3, so the copies of one slab overlap the kernel of another (PCIe is full duplex and the
-  // device has separate copy engines per direction).  A slab of plants is a column range of every row:
-  // 2-D copies with the row pitch P.  Plants are independent, so slabs need no ordering among themselves.
-  enum { NSTREAM = WT_HOST_NSTREAM };
   cudaStream_t *st = g_ws.st;
   if (!st[0]) {
     for (int i = 0; i < NSTREAM; ++i) {
@@ -907,11 +1086,6 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
     cudaError_t e = cudaEventCreateWithFlags(&g_ws.ev, cudaEventDisableTiming);
     if (e != cudaSuccess) return cuda_err(e, "cudaEventCreate");
   }
-  int slabs = P / 32768;
-  if (slabs < 1) slabs = 1;
-  if (slabs > 32) slabs = 32;
-  if (const char *e = getenv("WT_B200_HOST_SLABS")) { slabs = atoi(e); if (slabs < 1) slabs = 1; }  // tuning runs
-  const int per = ((P + slabs - 1) / slabs + 31) & ~31;  // plants per slab, a multiple of the warp width
   const size_t pitch = Pz * 8;
   if (!bnd_stride) {  // one broadcast boundary row: uploaded once, the other streams wait for it
     cudaEvent_t ev = g_ws.ev;
@@ -933,7 +1107,7 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
     a.P = w; a.ld = P; a.n = n; a.n_steps = 1; a.bnd_stride = bnd_stride; a.max_attempts = max_attempts;
     a.dt = dt; a.par = d_par + p0; a.bnd = bnd_stride ? d_bnd + p0 : d_bnd; a.time = d_t + p0; a.y = d_y + p0;
     a.flow = flow ? d_f + p0 : nullptr; a.derived = nullptr; a.status = d_s + p0; a.counters = nullptr;
-    a.order = nullptr; a.cost = nullptr;
+    a.order = nullptr; a.cost = nullptr; a.ws = d_ws + (size_t)(c % NSTREAM) * b_ws;
     rc = launch_step(a, s);
     if (rc) return rc;
     cudaMemcpyAsync(time + p0, d_t + p0, wb, cudaMemcpyDeviceToHost, s);

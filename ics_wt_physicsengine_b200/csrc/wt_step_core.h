@@ -428,11 +428,10 @@ WT_DEV vd wt_pcr_solve_real(const WtGroup &g, LuStore &lu, int slot0, vd d) {
 // ----------------------------------------------------------------------------------------
 // finite-difference Jacobian rows of this lane's zone (index 0: column zone z-1, 1: z, 2: z+1)
 // ----------------------------------------------------------------------------------------
+// The diagonal blocks d(dT)/dT, d(dpH)/dpH, d(dCl)/dCl (3 x 3 doubles per lane) are only needed by the
+// factorization; num_jac parks them in the store (WtPlantStep::PK_JD).  The coupling blocks are used by every solve:
 struct WtJac {
-  vd tt[3];  // d(dT_z)/dT
-  vd pp[3];  // d(dpH_z)/dpH
   vd pt[3];  // d(dpH_z)/dT   (non-zero only when a perturbation flips a Richardson switch)
-  vd cc[3];  // d(dCl_z)/dCl
   vd ct[3];  // d(dCl_z)/dT
   vd cp;     // d(dCl_z)/dpH_z
 };
@@ -443,10 +442,18 @@ struct WtPlantStep {
   WtGroup g;
   WtConstT<LuStore> c;
   LuStore *lu;
-  // state vector of this zone: 0 pH, 1 Cl, 2 T  (and f = dy/dt)
-  vd y[3], f[3];
-  WtJac J;
-  vd jfac[3];
+  // state vector of this zone: 0 pH, 1 Cl, 2 T
+  vd y[3];
+  WtJac J;   // tt / pp / cc are only filled inside num_jac and factor (parked in between), pt / ct / cp stay in registers
+  // PARKED per-lane state: live for the whole step but touched once or twice per attempt, never inside the Newton
+  // loop.  It lives in lane-private slots of the store (shared memory), not in 54 registers per lane: with it parked
+  // the hot loops fit the 168 registers of three resident blocks per SM.
+  //   f = dy/dt at (t, y)           3      jfac (num_jac step factors)    3
+  //   Q dense output (radau.py:547) 9      yold                           3      J.tt / J.pp / J.cc   9
+  enum { PK_F = 0, PK_JFAC = 3, PK_Q = 6, PK_YOLD = 15, PK_JD = 18, PK_N = 27 };
+  int pk0;  // first parking slot
+  WT_DEV vd pk(int k) const { return lu->get(pk0 + k); }
+  WT_DEV void pkset(int k, vd x, vb m) { lu->put(pk0 + k, x, m); }
   // Per-plant decisions of the solver, one bit each in ONE register (as separate bools ptxas kept them in
   // byte lanes of several registers and spilled those to local memory, which misses L1 here: long_sb stalls)
   enum { F_RUNNING = 1, F_NEED_JAC = 2, F_CURRENT_JAC = 4, F_LU_VALID = 8, F_NEW_STEP = 16, F_HAVE_OLD = 32,
@@ -460,8 +467,6 @@ struct WtPlantStep {
   WT_DEV vb failed() const { return fget(F_FAILED); }      // TOO_SMALL_STEP
   WT_DEV vb worklimit() const { return fget(F_WORKLIMIT); }  // engine policy: attempt budget exhausted (not reference behaviour)
   vd W[3][3];     // W[k][var]
-  vd Q[3][3];     // dense output, Q[var][k]   (radau.py:547-553)
-  vd yold[3];
   // Per-plant step-control scalars live in the per-plant store (shared memory), not replicated in two
   // registers per lane for the whole step: they are touched a few times per attempt, never in the Newton loop.
   enum { PV_SELF_H = 0, PV_SELF_H_OLD, PV_SELF_ERR_OLD, PV_H_OLD, PV_ERR_OLD, PV_MIN_STEP, PV_SOL_TOLD, PV_SOL_H,
@@ -484,16 +489,19 @@ struct WtPlantStep {
     const vd mr = WT_MU_REAL * ih, gr = WT_MU_CRE * ih, gi = WT_MU_CIM * ih;
     vd a[3], b[3], c_[3];                         // real rows
     vd ar[3], ai[3], br[3], bi[3], cr[3], ci[3];  // complex rows
-    a[0] = -J.tt[0]; b[0] = mr - J.tt[1]; c_[0] = -J.tt[2];
-    a[1] = -J.pp[0]; b[1] = mr - J.pp[1]; c_[1] = -J.pp[2];
-    a[2] = -J.cc[0]; b[2] = mr - J.cc[1]; c_[2] = -J.cc[2];
+    vd jd[9];  // J.tt, J.pp, J.cc (parked by num_jac)
+    WT_UNROLL
+    for (int k = 0; k < 9; ++k) jd[k] = pk(PK_JD + k);
+    WT_UNROLL
+    for (int q = 0; q < 3; ++q) { a[q] = -jd[3 * q]; b[q] = mr - jd[3 * q + 1]; c_[q] = -jd[3 * q + 2]; }
     WT_UNROLL
     for (int q = 0; q < 3; ++q) {
       ar[q] = a[q]; ai[q] = vbroadcast(0.0);
       br[q] = b[q] - mr + gr; bi[q] = gi;
       cr[q] = c_[q]; ci[q] = vbroadcast(0.0);
     }
-    br[0] = gr - J.tt[1]; br[1] = gr - J.pp[1]; br[2] = gr - J.cc[1];
+    WT_UNROLL
+    for (int q = 0; q < 3; ++q) br[q] = gr - jd[3 * q + 1];
     int l = 0;
     const int s_last = 1 << (g.L - 1);
     WT_NOUNROLL
@@ -650,8 +658,12 @@ struct WtPlantStep {
     const double MINF = 1e3 * WT_EPS;
     lu->cadd(WTC_NJEV, seli(m, 1, 0));
 
+    vd f[3], jfac[3];
     WT_UNROLL
-    for (int v = 0; v < 3; ++v) jfac[v] = sel(m & !fget(F_HAVE_JFAC), 1.4901161193847656e-08, jfac[v]);  // EPS ** 0.5
+    for (int v = 0; v < 3; ++v) {
+      f[v] = pk(PK_F + v);
+      jfac[v] = sel(fget(F_HAVE_JFAC), pk(PK_JFAC + v), 1.4901161193847656e-08);  // EPS ** 0.5 on the first call of a step
+    }
     fset(F_HAVE_JFAC, m);
 
     // ---- base intermediates at y (identical bits to the evaluation that produced f)
@@ -848,23 +860,25 @@ struct WtPlantStep {
     for (int v = 0; v < 3; ++v) { hh[v] = wt_rcp(hh[v]); hdn[v] = shfl_up(hh[v], 1); hup[v] = shfl_down(hh[v], 1); }
     vb hasdn = !g.first, hasup = !g.last;
 #define WT_JSET(dst, val) dst = sel(m, (val), dst)
-    WT_JSET(J.pp[0], sel(hasdn, d_pp[0] * hdn[0], 0.0));
-    WT_JSET(J.pp[1], d_pp[1] * hh[0]);
-    WT_JSET(J.pp[2], sel(hasup, d_pp[2] * hup[0], 0.0));
+#define WT_JPARK(k, val) pkset(PK_JD + (k), (val), m)
+    WT_JPARK(3, sel(hasdn, d_pp[0] * hdn[0], 0.0));
+    WT_JPARK(4, d_pp[1] * hh[0]);
+    WT_JPARK(5, sel(hasup, d_pp[2] * hup[0], 0.0));
     WT_JSET(J.cp, d_cp * hh[0]);
-    WT_JSET(J.cc[0], sel(hasdn, d_cc[0] * hdn[1], 0.0));
-    WT_JSET(J.cc[1], d_cc[1] * hh[1]);
-    WT_JSET(J.cc[2], sel(hasup, d_cc[2] * hup[1], 0.0));
+    WT_JPARK(6, sel(hasdn, d_cc[0] * hdn[1], 0.0));
+    WT_JPARK(7, d_cc[1] * hh[1]);
+    WT_JPARK(8, sel(hasup, d_cc[2] * hup[1], 0.0));
     WT_JSET(J.pt[0], sel(hasdn, d_pt[0] * hdn[2], 0.0));
     WT_JSET(J.pt[1], d_pt[1] * hh[2]);
     WT_JSET(J.pt[2], sel(hasup, d_pt[2] * hup[2], 0.0));
     WT_JSET(J.ct[0], sel(hasdn, d_ct[0] * hdn[2], 0.0));
     WT_JSET(J.ct[1], d_ct[1] * hh[2]);
     WT_JSET(J.ct[2], sel(hasup, d_ct[2] * hup[2], 0.0));
-    WT_JSET(J.tt[0], sel(hasdn, d_tt[0] * hdn[2], 0.0));
-    WT_JSET(J.tt[1], d_tt[1] * hh[2]);
-    WT_JSET(J.tt[2], sel(hasup, d_tt[2] * hup[2], 0.0));
+    WT_JPARK(0, sel(hasdn, d_tt[0] * hdn[2], 0.0));
+    WT_JPARK(1, d_tt[1] * hh[2]);
+    WT_JPARK(2, sel(hasup, d_tt[2] * hup[2], 0.0));
 #undef WT_JSET
+#undef WT_JPARK
     // ---- factor adaptation (common.py:377-380)
     WT_UNROLL
     for (int v = 0; v < 3; ++v) {
@@ -872,7 +886,7 @@ struct WtPlantStep {
       fnew = sel(maxd[v] < SMALL * scl[v], fnew * 10.0, fnew);
       fnew = sel(maxd[v] > BIG * scl[v], fnew * 0.1, fnew);
       fnew = vmax(fnew, MINF);
-      jfac[v] = sel(m, fnew, jfac[v]);
+      pkset(PK_JFAC + v, fnew, m);
     }
   }
 
@@ -895,34 +909,50 @@ struct WtPlantStep {
   // -------------------------------------------------------------------------------------
   // the whole step: solve_ivp(Radau) over [t0, t0+dt] from (y) -> y at t0+dt
   // -------------------------------------------------------------------------------------
+  // The step is split in two so that the GPU can run it as two kernels (wt_kernels.cu):
+  //   begin()  once-per-step work with the same control flow for every plant: solver set-up, f0, the initial step
+  //            size and the first Jacobian (Radau.__init__, radau.py:295-347, 363-369);
+  //   run()    the attempt loop (_step_impl, radau.py:405-545), data-dependent.
+  // What crosses from one to the other: fl, J.pt / J.ct / J.cp, the parked f / jfac / J diagonal blocks and
+  // PV_SELF_H (everything else begin() leaves behind is rebuilt by reset()).
   WT_DEV void integrate(vd t0, vd dt, vb plant_on, int max_attempts) {
-    if (max_attempts <= 0 || max_attempts > WT_HARD_MAX_ATTEMPTS) max_attempts = WT_HARD_MAX_ATTEMPTS;
-    vd t = t0;
+    begin(t0, dt, plant_on);
+    run(t0, max_attempts);
+  }
+
+  // solver state at the start of a step (radau.py:295-347 minus f0 / h_abs / the Jacobian)
+  WT_DEV void reset(vd t0, vd dt, vb plant_on) {
     pvset(PV_T_BOUND, t0 + dt);
     pvset(PV_MAX_STEP, vmin(dt, 10.0));
     // running = plant_on; current_jac and new_step start true (radau.py:363-369, :413)
     fl = seli(plant_on, (int)F_RUNNING, 0) | (int)(F_CURRENT_JAC | F_NEW_STEP);
     pvset(PV_SOL_TOLD, vbroadcast(0.0));
     pvset(PV_SOL_H, vbroadcast(1.0));
+    const vb all = vbroadcast_b(true);
     WT_UNROLL
     for (int v = 0; v < 3; ++v) {
-      jfac[v] = vbroadcast(0.0);
-      yold[v] = y[v];
+      pkset(PK_YOLD + v, y[v], all);
       WT_UNROLL
-      for (int k = 0; k < 3; ++k) { W[k][v] = vbroadcast(0.0); Q[v][k] = vbroadcast(0.0); }
+      for (int k = 0; k < 3; ++k) { W[k][v] = vbroadcast(0.0); pkset(PK_Q + 3 * v + k, vbroadcast(0.0), all); }
     }
     J.cp = vbroadcast(0.0);
     WT_UNROLL
-    for (int k = 0; k < 3; ++k) {
-      J.tt[k] = vbroadcast(0.0); J.pp[k] = vbroadcast(0.0); J.pt[k] = vbroadcast(0.0);
-      J.cc[k] = vbroadcast(0.0); J.ct[k] = vbroadcast(0.0);
-    }
+    for (int k = 0; k < 3; ++k) { J.pt[k] = vbroadcast(0.0); J.ct[k] = vbroadcast(0.0); }
+    pvset(PV_SELF_H_OLD, vbroadcast(0.0));
+    pvset(PV_SELF_ERR_OLD, vbroadcast(0.0));
+    pvset(PV_H_OLD, vbroadcast(0.0));
+    pvset(PV_ERR_OLD, vbroadcast(0.0));
+    pvset(PV_MIN_STEP, vbroadcast(0.0));
+  }
 
+  WT_DEV void begin(vd t0, vd dt, vb plant_on) {
+    reset(t0, dt, plant_on);
+    const vb all = vbroadcast_b(true);
     // ---- Radau.__init__: f0 and select_initial_step (radau.py:303-311, common.py:68-134)
-    vd h_abs;
     {
+      vd h_abs;
       // f0 = f(y) and f1 = f(y + h0 f0) go through ONE rolled copy of the RHS (instruction-fetch bound kernel)
-      vd sc[3], yy[3], fo[3];  // sc = 1 / scale
+      vd sc[3], yy[3], fo[3], f[3];  // sc = 1 / scale
       vd d1 = vbroadcast(0.0), h0 = vbroadcast(0.0);
       const vd interval = vabs(pv(PV_T_BOUND) - t0);
       WT_UNROLL
@@ -948,16 +978,26 @@ struct WtPlantStep {
       vd h1 = sel((d1 <= 1e-15) & (d2 <= 1e-15), vmax(h0 * 1e-3, 1e-6), vsqrt(vsqrt(wt_div(0.01, vmax(d1, d2)))));
       h_abs = vmin(vmin(100.0 * h0, h1), vmin(interval, pv(PV_MAX_STEP)));
       pvset(PV_SELF_H, h_abs);
+      WT_UNROLL
+      for (int v = 0; v < 3; ++v) pkset(PK_F + v, f[v], all);
     }
     fclr(F_RUNNING, trange());
+    // first Jacobian (radau.py:363-369)
+    {
+      vb m = fget(F_RUNNING);
+      if (vany(m)) {
+        num_jac(m);
+        fset(F_CURRENT_JAC, m);
+        fclr(F_LU_VALID | F_NEED_JAC, m);
+        fclr(F_RUNNING, trange());
+      }
+    }
+  }
 
-    pvset(PV_SELF_H_OLD, vbroadcast(0.0));
-    pvset(PV_SELF_ERR_OLD, vbroadcast(0.0));
-    fset(F_NEED_JAC, fget(F_RUNNING));  // first Jacobian (radau.py:363-369)
-    pvset(PV_H_OLD, vbroadcast(0.0));
-    pvset(PV_ERR_OLD, vbroadcast(0.0));
-    pvset(PV_MIN_STEP, vbroadcast(0.0));
-
+  WT_DEV void run(vd t0, int max_attempts) {
+    if (max_attempts <= 0 || max_attempts > WT_HARD_MAX_ATTEMPTS) max_attempts = WT_HARD_MAX_ATTEMPTS;
+    vd t = t0;
+    vd h_abs = vbroadcast(0.0);  // set from PV_SELF_H on the first pass (F_NEW_STEP)
     vi attempts = vbroadcast_i(0);
     while (wt_cta_any(vany(fget(F_RUNNING)))) {
       // (1) Jacobian: first one, stale-J refresh (radau.py:467-473) or post-accept refresh (:519-521)
@@ -1016,9 +1056,10 @@ struct WtPlantStep {
         vd x2 = ((t + h * 1.0) - sol_told) * isolh;
         WT_UNROLL
         for (int v = 0; v < 3; ++v) {
-          vd z0 = (((Q[v][0] * x0 + Q[v][1] * (x0 * x0)) + Q[v][2] * ((x0 * x0) * x0)) + yold[v]) - y[v];
-          vd z1 = (((Q[v][0] * x1 + Q[v][1] * (x1 * x1)) + Q[v][2] * ((x1 * x1) * x1)) + yold[v]) - y[v];
-          vd z2 = (((Q[v][0] * x2 + Q[v][1] * (x2 * x2)) + Q[v][2] * ((x2 * x2) * x2)) + yold[v]) - y[v];
+          const vd q0 = pk(PK_Q + 3 * v), q1 = pk(PK_Q + 3 * v + 1), q2 = pk(PK_Q + 3 * v + 2), yo = pk(PK_YOLD + v);
+          vd z0 = (((q0 * x0 + q1 * (x0 * x0)) + q2 * ((x0 * x0) * x0)) + yo) - y[v];
+          vd z1 = (((q0 * x1 + q1 * (x1 * x1)) + q2 * ((x1 * x1) * x1)) + yo) - y[v];
+          vd z2 = (((q0 * x2 + q1 * (x2 * x2)) + q2 * ((x2 * x2) * x2)) + yo) - y[v];
           z0 = sel(hs, z0, 0.0);
           z1 = sel(hs, z1, 0.0);
           z2 = sel(hs, z2, 0.0);
@@ -1150,7 +1191,7 @@ struct WtPlantStep {
         Z[0][v] = zrow(0, v); Z[1][v] = zrow(1, v); Z[2][v] = zrow(2, v);
         y_new[v] = y[v] + Z[2][v];
         ZE[v] = ((Z[0][v] * WT_E0 + Z[1][v] * WT_E1) + Z[2][v] * WT_E2) * ih;
-        err[v] = f[v];
+        err[v] = vbroadcast(0.0);
         escale[v] = wt_rcp(WT_ATOL + vmax(vabs(y[v]), vabs(y_new[v])) * WT_RTOL);
       }
       const vd safety = wt_div(vbroadcast(0.9 * (2 * WT_NEWTON_MAXITER + 1)), vfromint(n_iter + 2 * WT_NEWTON_MAXITER));
@@ -1161,7 +1202,7 @@ struct WtPlantStep {
         vd F[3];
         if (pass == 0) {
           WT_UNROLL
-          for (int v = 0; v < 3; ++v) F[v] = f[v];
+          for (int v = 0; v < 3; ++v) F[v] = pk(PK_F + v);
         } else {
           vb m;
           vd pnt[3];
@@ -1218,12 +1259,12 @@ struct WtPlantStep {
           pvset(PV_SELF_H, h_abs * fct, acc);
           WT_UNROLL
           for (int v = 0; v < 3; ++v) {
-            Q[v][0] = sel(acc, (Z[0][v] * WT_P00 + Z[1][v] * WT_P10) + Z[2][v] * WT_P20, Q[v][0]);
-            Q[v][1] = sel(acc, (Z[0][v] * WT_P01 + Z[1][v] * WT_P11) + Z[2][v] * WT_P21, Q[v][1]);
-            Q[v][2] = sel(acc, (Z[0][v] * WT_P02 + Z[1][v] * WT_P12) + Z[2][v] * WT_P22, Q[v][2]);
-            yold[v] = sel(acc, y[v], yold[v]);
+            pkset(PK_Q + 3 * v + 0, (Z[0][v] * WT_P00 + Z[1][v] * WT_P10) + Z[2][v] * WT_P20, acc);
+            pkset(PK_Q + 3 * v + 1, (Z[0][v] * WT_P01 + Z[1][v] * WT_P11) + Z[2][v] * WT_P21, acc);
+            pkset(PK_Q + 3 * v + 2, (Z[0][v] * WT_P02 + Z[1][v] * WT_P12) + Z[2][v] * WT_P22, acc);
+            pkset(PK_YOLD + v, y[v], acc);
             y[v] = sel(acc, y_new[v], y[v]);
-            f[v] = sel(acc, F[v], f[v]);
+            pkset(PK_F + v, F[v], acc);
           }
           pvset(PV_SOL_TOLD, t, acc);
           pvset(PV_SOL_H, t_new - t, acc);

@@ -225,6 +225,8 @@ class PlantEnsemble:
             self._bnd_batch = None
             self._order = None
             self._cost = torch.zeros(P, dtype=torch.int32, device=self.device) if self.sort_every > 0 else None
+            # device workspace of the step (work queue + hand-off rows between its two launches), reused by every step
+            self._ws = torch.empty(int(_lib.lib().wt_step_workspace_bytes(P, n)), dtype=torch.uint8, device=self.device)
         self.state = EnsembleState(self._y, self._derived, self._time, self._flow)
         if init is not None:
             self.set_state(init.pH0, init.Cl0, init.T0)
@@ -310,7 +312,8 @@ class PlantEnsemble:
             rc = _lib.lib().wt_advance(self.n_plants, self.n_zones, int(n_steps), float(dt), _ptr(self._par),
                                        _ptr(bnd), stride, _ptr(self._time), _ptr(self._y), _ptr(self._flow),
                                        _ptr(self._derived), _ptr(self._status), _ptr(self._counters),
-                                       self.max_attempts, _ptr(self._order), _ptr(self._cost), C.c_void_p(stream))
+                                       self.max_attempts, _ptr(self._order), _ptr(self._cost), _ptr(self._ws),
+                                       C.c_void_p(stream))
         _lib.check(rc, "wt_advance")
         self._launches += 1
         return self.state

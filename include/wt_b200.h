@@ -23,13 +23,14 @@
 #ifndef WT_B200_H
 #define WT_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define WT_ABI_VERSION 2   /* 2: sensor state has 9 fields (power-on time); wt_sensors_maintain, wt_sensor_window_stats, wt_diagnostics, wt_register_image */
+#define WT_ABI_VERSION 3   /* 3: wt_step / wt_advance take a device workspace (wt_step_workspace_bytes); new entry points of round 2 */
 #define WT_MAX_ZONES 32
 
 /* derived per-plant constants; computed on the host exactly as the reference constructors do
@@ -79,8 +80,13 @@ const char *wt_last_error(void);
 /* ---------------------------------------------------------------------------------------
  * IntegratedCSTR.step(dt, boundary) for P plants          (reactor.py:450-541)
  *
- * One launch advances every non-halted plant by one step(dt): scipy-Radau solve over
+ * Advances every non-halted plant by one step(dt): scipy-Radau solve over
  * [time[p], time[p]+dt], derived-state update, bound clipping.  In place on y/time/flow_rate.
+ * A step is two launches on `stream`: the once-per-step solver set-up (f0, initial step size, first
+ * finite-difference Jacobian) and the attempt loop run by persistent warps that draw groups of plants from a queue.
+ *   workspace  device memory of wt_step_workspace_bytes(P, n_zones) bytes, owned by the caller and reusable by
+ *              every later call with the same or a smaller P (the queue counter and the hand-off rows between the
+ *              two launches); calls that may overlap on the device (different streams) need their own.
  *   derived    optional [3 * n_zones * P]: H_concentration, density, chlorine_decay_rate
  *              (ReactorState derived fields, reactor.py:136-147), may be NULL
  *   status     [P] in/out: plants whose word has a WT_ST_HALT_MASK bit are skipped
@@ -90,11 +96,12 @@ const char *wt_last_error(void);
 int wt_step(int P, int n_zones, double dt, const double *par_dev, const double *bnd_dev,
             int bnd_stride, double *time_dev, double *y_dev, double *flow_rate_dev,
             double *derived_dev, uint32_t *status_dev, int32_t *counters_dev, int max_attempts,
-            void *stream);
+            void *workspace_dev, void *stream);
+size_t wt_step_workspace_bytes(int P, int n_zones);
 
-/* Same, `n_steps` consecutive step(dt) calls fused in one launch (state stays in registers
- * between steps; plants are independent so no grid-wide synchronisation is needed).
- * Equivalent to calling wt_step n_steps times with unchanged boundary conditions.
+/* Same, `n_steps` consecutive step(dt) calls queued by one call (2 n_steps launches).
+ * Equivalent to calling wt_step n_steps times with unchanged boundary conditions, except that the non-halting
+ * status bits (clips, solver failure) of all n_steps steps are OR-ed into the final status word.
  *   order_dev  optional int32 [P]: permutation slot -> plant.  Results do not depend on it (plants
  *              are independent); it only decides which plants share a warp and which start first,
  *              e.g. plants sorted by the cost of their previous step (stragglers first, similar
@@ -105,7 +112,7 @@ int wt_advance(int P, int n_zones, int n_steps, double dt, const double *par_dev
                const double *bnd_dev, int bnd_stride, double *time_dev, double *y_dev,
                double *flow_rate_dev, double *derived_dev, uint32_t *status_dev,
                int32_t *counters_dev, int max_attempts, const int32_t *order_dev,
-               int32_t *cost_dev, void *stream);
+               int32_t *cost_dev, void *workspace_dev, void *stream);
 
 /* IntegratedCSTR.derivatives(t, y, boundary) for P plants (reactor.py:272-448).
  * dy has the layout of y; bad[p] != 0 where the reference would raise ValueError. */

@@ -43,6 +43,7 @@ void wt_emu_step_batch(int P, int n, int nsteps, double dt, const double *par, c
       WtPlantStep<EmuLu> ps;
       ps.g = wt_make_group(n);
       ps.lu = &lu;
+      ps.pk0 = 64;  // real LU slots end at 30, the lane constants sit at 110
       vd vpar[WTP_NPAR], vbnd[WTB_NBND], t0, vdt = vbroadcast(dt);
       vb on;
       vd yin[3];

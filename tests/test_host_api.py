@@ -74,7 +74,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for n in names:
         assert hasattr(L, n), n
-    assert L.wt_abi_version() == 2
+    assert L.wt_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_no_silent_cpu_path_without_a_gpu():
@@ -85,7 +85,7 @@ def test_no_silent_cpu_path_without_a_gpu():
         wt.PlantEnsemble(ens.config2(4))
     with pytest.raises(_lib.EngineError):
         wt.calculate_pH_batch([100.0], [2.0], [20.0], [7.0])
-    rc = L.wt_step(4, 10, 1.0, None, None, 0, None, None, None, None, None, None, 0, None)
+    rc = L.wt_step(4, 10, 1.0, None, None, 0, None, None, None, None, None, None, 0, None, None)
     assert rc == -2  # WT_ERR_NO_DEVICE
     out = C.c_double(0)
     assert L.wt_measure_fp64_peak(C.byref(out), 10) == -2
