@@ -414,17 +414,6 @@ WT_DEV int wt_pcr_levels(int n) { int L = 0; for (int s = 1; s < n; s <<= 1) ++L
 // partner lane of the last PCR level (clamped to the plant: a zone without partner has a zero multiplier)
 WT_DEV vi wt_src_last(const WtGroup &g, int s) { return seli(g.z >= s, g.lane - s, vmini(g.lane + s, g.last_lane)); }
 
-template <class LuStore>
-WT_DEV vd wt_pcr_solve_real(const WtGroup &g, LuStore &lu, int slot0, vd d) {
-  int l = 0;
-  const int s_last = 1 << (g.L - 1);
-  WT_NOUNROLL
-  for (int s = 1; s < s_last; s <<= 1, ++l)
-    d = d - shfl_idx(d, wt_src_dn(g, s)) * lu.get(slot0 + 2 * l) - shfl_idx(d, wt_src_up(g, s)) * lu.get(slot0 + 2 * l + 1);
-  d = d - shfl_idx(d, wt_src_last(g, s_last)) * lu.get(slot0 + 2 * l);
-  return d * lu.get(slot0 + 2 * l + 1);
-}
-
 // ----------------------------------------------------------------------------------------
 // finite-difference Jacobian rows of this lane's zone (index 0: column zone z-1, 1: z, 2: z+1)
 // ----------------------------------------------------------------------------------------
@@ -483,161 +472,136 @@ struct WtPlantStep {
   // -------------------------------------------------------------------------------------
   // All six factorizations (real + complex of T, pH, Cl) share one sweep over the PCR levels:
   // six independent dependency chains per level instead of six sweeps back to back.
+  // The three systems (T, pH, Cl) go through ONE rolled copy of the factorization (real and complex chains of a
+  // system interleaved): a third of the code of the all-systems-at-once version, which matters more than its
+  // extra instruction-level parallelism in a kernel bound by instruction fetch.
   WT_DEV void factor(vd h, vb mask, vb keep) {
     lu->begin_factor(keep);
     const vd ih = wt_rcp(h);
     const vd mr = WT_MU_REAL * ih, gr = WT_MU_CRE * ih, gi = WT_MU_CIM * ih;
-    vd a[3], b[3], c_[3];                         // real rows
-    vd ar[3], ai[3], br[3], bi[3], cr[3], ci[3];  // complex rows
-    vd jd[9];  // J.tt, J.pp, J.cc (parked by num_jac)
-    WT_UNROLL
-    for (int k = 0; k < 9; ++k) jd[k] = pk(PK_JD + k);
-    WT_UNROLL
-    for (int q = 0; q < 3; ++q) { a[q] = -jd[3 * q]; b[q] = mr - jd[3 * q + 1]; c_[q] = -jd[3 * q + 2]; }
-    WT_UNROLL
-    for (int q = 0; q < 3; ++q) {
-      ar[q] = a[q]; ai[q] = vbroadcast(0.0);
-      br[q] = b[q] - mr + gr; bi[q] = gi;
-      cr[q] = c_[q]; ci[q] = vbroadcast(0.0);
-    }
-    WT_UNROLL
-    for (int q = 0; q < 3; ++q) br[q] = gr - jd[3 * q + 1];
-    int l = 0;
     const int s_last = 1 << (g.L - 1);
     WT_NOUNROLL
-    for (int s = 1; s < s_last; s <<= 1, ++l) {
-      const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
-      // Written PHASE-major (all reciprocals, then all exchanges, then all updates) so that the six
-      // factorizations advance together: ptxas keeps the statement order when registers are tight, and
-      // system-major order ran the six reciprocal chains (MUFU + 3 dependent DFMAs each) back to back.
-      vd den[6], inv[6];  // 0..2 real pivots, 3..5 |complex pivot|^2
-      WT_UNROLL
-      for (int q = 0; q < 3; ++q) { den[q] = b[q]; den[3 + q] = br[q] * br[q] + bi[q] * bi[q]; }
-      wt_rcp_n<6>(den, inv);
-      vd rr[3], ri[3];  // 1 / complex pivot
-      WT_UNROLL
-      for (int q = 0; q < 3; ++q) { rr[q] = br[q] * inv[3 + q]; ri[q] = -(bi[q] * inv[3 + q]); }
-      vd k1[3], k2[3], kc[3][4];  // kc = k1r, k1i, k2r, k2i
-      WT_UNROLL
-      for (int q = 0; q < 3; ++q) {
-        k1[q] = a[q] * shfl_idx(inv[q], sd);
-        k2[q] = c_[q] * shfl_idx(inv[q], su);
-        const vd rdr = shfl_idx(rr[q], sd), rdi = shfl_idx(ri[q], sd);
-        const vd rur = shfl_idx(rr[q], su), rui = shfl_idx(ri[q], su);
-        kc[q][0] = ar[q] * rdr - ai[q] * rdi; kc[q][1] = ar[q] * rdi + ai[q] * rdr;
-        kc[q][2] = cr[q] * rur - ci[q] * rui; kc[q][3] = cr[q] * rui + ci[q] * rur;
+    for (int q = 0; q < 3; ++q) {
+      // rows of (mu/h I - J_qq): J.tt, J.pp, J.cc parked by num_jac
+      const vd jdg = pk(PK_JD + 3 * q + 1);
+      vd a = -pk(PK_JD + 3 * q), b = mr - jdg, c_ = -pk(PK_JD + 3 * q + 2);                 // real
+      vd ar = a, ai = vbroadcast(0.0), br = gr - jdg, bi = gi, cr = c_, ci = vbroadcast(0.0);  // complex
+      const int sr = slot_real(q), sc = slot_cplx(q);
+      int l = 0;
+      WT_NOUNROLL
+      for (int s = 1; s < s_last; s <<= 1, ++l) {
+        const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
+        vd den[2] = {b, br * br + bi * bi}, inv[2];  // real pivot, |complex pivot|^2
+        wt_rcp_n<2>(den, inv);
+        const vd rr = br * inv[1], ri = -(bi * inv[1]);  // 1 / complex pivot
+        const vd k1 = a * shfl_idx(inv[0], sd), k2 = c_ * shfl_idx(inv[0], su);
+        const vd rdr = shfl_idx(rr, sd), rdi = shfl_idx(ri, sd), rur = shfl_idx(rr, su), rui = shfl_idx(ri, su);
+        vd kc[4];  // k1r, k1i, k2r, k2i
+        kc[0] = ar * rdr - ai * rdi; kc[1] = ar * rdi + ai * rdr;
+        kc[2] = cr * rur - ci * rui; kc[3] = cr * rui + ci * rur;
+        const vd a_dn = shfl_idx(a, sd), c_dn = shfl_idx(c_, sd), a_up = shfl_idx(a, su), c_up = shfl_idx(c_, su);
+        b = b - c_dn * k1 - a_up * k2;
+        a = -(a_dn * k1);
+        c_ = -(c_up * k2);
+        const vd adr = shfl_idx(ar, sd), adi = shfl_idx(ai, sd), cdr = shfl_idx(cr, sd), cdi = shfl_idx(ci, sd);
+        const vd aur = shfl_idx(ar, su), aui = shfl_idx(ai, su), cur = shfl_idx(cr, su), cui = shfl_idx(ci, su);
+        br = br - (cdr * kc[0] - cdi * kc[1]) - (aur * kc[2] - aui * kc[3]);
+        bi = bi - (cdr * kc[1] + cdi * kc[0]) - (aur * kc[3] + aui * kc[2]);
+        ar = -(adr * kc[0] - adi * kc[1]);
+        ai = -(adr * kc[1] + adi * kc[0]);
+        cr = -(cur * kc[2] - cui * kc[3]);
+        ci = -(cur * kc[3] + cui * kc[2]);
+        lu->put(sr + 2 * l, k1, mask);
+        lu->put(sr + 2 * l + 1, k2, mask);
+        lu->cx_put4(sc + 4 * l, kc, mask);
       }
-      WT_UNROLL
-      for (int q = 0; q < 3; ++q) {
-        const vd a_dn = shfl_idx(a[q], sd), c_dn = shfl_idx(c_[q], sd);
-        const vd a_up = shfl_idx(a[q], su), c_up = shfl_idx(c_[q], su);
-        b[q] = b[q] - c_dn * k1[q] - a_up * k2[q];
-        a[q] = -(a_dn * k1[q]);
-        c_[q] = -(c_up * k2[q]);
-        const vd adr = shfl_idx(ar[q], sd), adi = shfl_idx(ai[q], sd), cdr = shfl_idx(cr[q], sd), cdi = shfl_idx(ci[q], sd);
-        const vd aur = shfl_idx(ar[q], su), aui = shfl_idx(ai[q], su), cur = shfl_idx(cr[q], su), cui = shfl_idx(ci[q], su);
-        br[q] = br[q] - (cdr * kc[q][0] - cdi * kc[q][1]) - (aur * kc[q][2] - aui * kc[q][3]);
-        bi[q] = bi[q] - (cdr * kc[q][1] + cdi * kc[q][0]) - (aur * kc[q][3] + aui * kc[q][2]);
-        ar[q] = -(adr * kc[q][0] - adi * kc[q][1]);
-        ai[q] = -(adr * kc[q][1] + adi * kc[q][0]);
-        cr[q] = -(cur * kc[q][2] - cui * kc[q][3]);
-        ci[q] = -(cur * kc[q][3] + cui * kc[q][2]);
-      }
-      WT_UNROLL
-      for (int q = 0; q < 3; ++q) {
-        lu->put(slot_real(q) + 2 * l, k1[q], mask);
-        lu->put(slot_real(q) + 2 * l + 1, k2[q], mask);
-        lu->cx_put4(slot_cplx(q) + 4 * l, kc[q], mask);
-      }
-    }
-    {
-      // last level: one partner per zone (z - s for the upper zones, z + s for the lower ones), then the pivots
-      const vb upper = g.z >= s_last;
-      const vi sl = wt_src_last(g, s_last);
-      vd den[6], inv[6];
-      WT_UNROLL
-      for (int q = 0; q < 3; ++q) { den[q] = b[q]; den[3 + q] = br[q] * br[q] + bi[q] * bi[q]; }
-      wt_rcp_n<6>(den, inv);
-      vd k[3], kc[3][4];  // kc = kr, ki, pivot re, pivot im
-      WT_UNROLL
-      for (int q = 0; q < 3; ++q) {
-        const vd rr = br[q] * inv[3 + q], ri = -(bi[q] * inv[3 + q]);
-        const vd e = sel(upper, a[q], c_[q]), er = sel(upper, ar[q], cr[q]), ei = sel(upper, ai[q], ci[q]);
-        k[q] = e * shfl_idx(inv[q], sl);
+      {
+        // last level: one partner per zone (z - s for the upper zones, z + s for the lower ones), then the pivots
+        const vb upper = g.z >= s_last;
+        const vi sl = wt_src_last(g, s_last);
+        vd den[2] = {b, br * br + bi * bi}, inv[2];
+        wt_rcp_n<2>(den, inv);
+        const vd rr = br * inv[1], ri = -(bi * inv[1]);
+        const vd e = sel(upper, a, c_), er = sel(upper, ar, cr), ei = sel(upper, ai, ci);
+        const vd k = e * shfl_idx(inv[0], sl);
         const vd rpr = shfl_idx(rr, sl), rpi = shfl_idx(ri, sl);
-        kc[q][0] = er * rpr - ei * rpi; kc[q][1] = er * rpi + ei * rpr;
+        vd kc[4];  // kr, ki, pivot re, pivot im
+        kc[0] = er * rpr - ei * rpi; kc[1] = er * rpi + ei * rpr;
         const vd ep = shfl_idx(e, sl), epr = shfl_idx(er, sl), epi = shfl_idx(ei, sl);
-        b[q] = b[q] - ep * k[q];
-        br[q] = br[q] - (epr * kc[q][0] - epi * kc[q][1]);
-        bi[q] = bi[q] - (epr * kc[q][1] + epi * kc[q][0]);
-      }
-      WT_UNROLL
-      for (int q = 0; q < 3; ++q) { den[q] = b[q]; den[3 + q] = br[q] * br[q] + bi[q] * bi[q]; }
-      wt_rcp_n<6>(den, inv);
-      WT_UNROLL
-      for (int q = 0; q < 3; ++q) {
-        kc[q][2] = br[q] * inv[3 + q];
-        kc[q][3] = -(bi[q] * inv[3 + q]);
-        lu->put(slot_real(q) + 2 * l, k[q], mask);
-        lu->put(slot_real(q) + 2 * l + 1, inv[q], mask);
-        lu->cx_put4(slot_cplx(q) + 4 * l, kc[q], mask);
+        b = b - ep * k;
+        br = br - (epr * kc[0] - epi * kc[1]);
+        bi = bi - (epr * kc[1] + epi * kc[0]);
+        den[0] = b; den[1] = br * br + bi * bi;
+        wt_rcp_n<2>(den, inv);
+        kc[2] = br * inv[1];
+        kc[3] = -(bi * inv[1]);
+        lu->put(sr + 2 * l, k, mask);
+        lu->put(sr + 2 * l + 1, inv[0], mask);
+        lu->cx_put4(sc + 4 * l, kc, mask);
       }
     }
     lu->end_factor();
   }
   WT_DEV vd tri_mv(const vd *row, vd xdn, vd x, vd xup) const { return (row[0] * xdn + row[1] * x) + row[2] * xup; }
-  // (mu/h I - J) x = b, b and x indexed [0 pH, 1 Cl, 2 T]
-  WT_DEV void solve_real(vd *b) {
-    vd xT = wt_pcr_solve_real(g, *lu, slot_real(0), b[2]);
-    vd xTd = wt_dnc(g, xT), xTu = wt_upc(g, xT);
-    vd xp = wt_pcr_solve_real(g, *lu, slot_real(1), b[0] + tri_mv(J.pt, xTd, xT, xTu));
-    vd xc = wt_pcr_solve_real(g, *lu, slot_real(2), b[1] + tri_mv(J.ct, xTd, xT, xTu) + J.cp * xp);
-    b[0] = xp; b[1] = xc; b[2] = xT;
-  }
-  // one system, real and complex right-hand sides in the same sweep (three independent chains)
-  WT_DEV void solve_sys3(int q, vd &d, vd &dr, vd &di) {
+  // one system, real and complex right-hand sides in the same sweep (three independent chains); `cplx` false
+  // (warp-uniform): the real one only (a closing pass)
+  WT_DEV void solve_sys3(int q, vd &d, vd &dr, vd &di, bool cplx) {
     const int sr = slot_real(q), sc = slot_cplx(q);
     int l = 0;
     const int s_last = 1 << (g.L - 1);
     WT_NOUNROLL
     for (int s = 1; s < s_last; s <<= 1, ++l) {
       const vi sd = wt_src_dn(g, s), su = wt_src_up(g, s);
-      vd kc[4];  // k1r, k1i, k2r, k2i
-      lu->cx_get4(sc + 4 * l, kc);
       vd k1 = lu->get(sr + 2 * l), k2 = lu->get(sr + 2 * l + 1);
       vd dd = shfl_idx(d, sd), du = shfl_idx(d, su);
-      vd ddr = shfl_idx(dr, sd), ddi = shfl_idx(di, sd), dur = shfl_idx(dr, su), dui = shfl_idx(di, su);
       d = d - dd * k1 - du * k2;
-      vd nr = dr - (ddr * kc[0] - ddi * kc[1]) - (dur * kc[2] - dui * kc[3]);
-      vd ni = di - (ddr * kc[1] + ddi * kc[0]) - (dur * kc[3] + dui * kc[2]);
-      dr = nr;
-      di = ni;
+      if (cplx) {
+        vd kc[4];  // k1r, k1i, k2r, k2i
+        lu->cx_get4(sc + 4 * l, kc);
+        vd ddr = shfl_idx(dr, sd), ddi = shfl_idx(di, sd), dur = shfl_idx(dr, su), dui = shfl_idx(di, su);
+        vd nr = dr - (ddr * kc[0] - ddi * kc[1]) - (dur * kc[2] - dui * kc[3]);
+        vd ni = di - (ddr * kc[1] + ddi * kc[0]) - (dur * kc[3] + dui * kc[2]);
+        dr = nr;
+        di = ni;
+      }
     }
     {
       const vi sl = wt_src_last(g, s_last);
-      vd kc[4];  // kr, ki, pivot re, pivot im
-      lu->cx_get4(sc + 4 * l, kc);
       vd k = lu->get(sr + 2 * l), piv = lu->get(sr + 2 * l + 1);
-      vd dp = shfl_idx(d, sl), dpr = shfl_idx(dr, sl), dpi = shfl_idx(di, sl);
+      vd dp = shfl_idx(d, sl);
       d = (d - dp * k) * piv;
-      vd nr = dr - (dpr * kc[0] - dpi * kc[1]);
-      vd ni = di - (dpr * kc[1] + dpi * kc[0]);
-      dr = nr * kc[2] - ni * kc[3];
-      di = nr * kc[3] + ni * kc[2];
+      if (cplx) {
+        vd kc[4];  // kr, ki, pivot re, pivot im
+        lu->cx_get4(sc + 4 * l, kc);
+        vd dpr = shfl_idx(dr, sl), dpi = shfl_idx(di, sl);
+        vd nr = dr - (dpr * kc[0] - dpi * kc[1]);
+        vd ni = di - (dpr * kc[1] + dpi * kc[0]);
+        dr = nr * kc[2] - ni * kc[3];
+        di = nr * kc[3] + ni * kc[2];
+      }
     }
   }
   // the real and the complex collocation systems of one Newton iteration together
-  WT_DEV void solve_newton(vd *b, vd *br, vd *bi) {
+  WT_DEV void solve_newton(vd *b, vd *br, vd *bi, bool cplx) {
     vd xT = b[2], tr = br[2], ti = bi[2];
-    solve_sys3(0, xT, tr, ti);
+    solve_sys3(0, xT, tr, ti, cplx);
     vd xTd = wt_dnc(g, xT), xTu = wt_upc(g, xT);
-    vd trd = wt_dnc(g, tr), tru = wt_upc(g, tr), tid = wt_dnc(g, ti), tiu = wt_upc(g, ti);
     vd xp = b[0] + tri_mv(J.pt, xTd, xT, xTu);
-    vd pr = br[0] + tri_mv(J.pt, trd, tr, tru), pi = bi[0] + tri_mv(J.pt, tid, ti, tiu);
-    solve_sys3(1, xp, pr, pi);
+    vd pr = br[0], pi = bi[0];
+    vd trd = tr, tru = tr, tid = ti, tiu = ti;
+    if (cplx) {
+      trd = wt_dnc(g, tr); tru = wt_upc(g, tr); tid = wt_dnc(g, ti); tiu = wt_upc(g, ti);
+      pr = pr + tri_mv(J.pt, trd, tr, tru);
+      pi = pi + tri_mv(J.pt, tid, ti, tiu);
+    }
+    solve_sys3(1, xp, pr, pi, cplx);
     vd xc = b[1] + tri_mv(J.ct, xTd, xT, xTu) + J.cp * xp;
-    vd qr = br[1] + tri_mv(J.ct, trd, tr, tru) + J.cp * pr, qi = bi[1] + tri_mv(J.ct, tid, ti, tiu) + J.cp * pi;
-    solve_sys3(2, xc, qr, qi);
+    vd qr = br[1], qi = bi[1];
+    if (cplx) {
+      qr = qr + tri_mv(J.ct, trd, tr, tru) + J.cp * pr;
+      qi = qi + tri_mv(J.ct, tid, ti, tiu) + J.cp * pi;
+    }
+    solve_sys3(2, xc, qr, qi, cplx);
     b[0] = xp; b[1] = xc; b[2] = xT;
     br[0] = pr; bi[0] = pi; br[1] = qr; bi[1] = qi; br[2] = tr; bi[2] = ti;
   }
@@ -1086,27 +1050,52 @@ struct WtPlantStep {
         fset(F_WORKLIMIT, over);
         fclr(F_RUNNING, over);
       }
-      // (5) simplified Newton (radau.py:48-136)
+      // (5)-(8) ONE pass loop for the simplified Newton iterations (radau.py:48-136), the error estimate
+      // (radau.py:483-512) and the acceptance evaluation (radau.py:514-545).  The kernel is bound by instruction
+      // fetch, so all of them go through ONE copy of "evaluate the RHS at three points -> solve -> scaled norm":
+      //   Newton pass of a plant   points y + Z_i; real + complex right-hand sides; dW and the convergence logic
+      //   closing pass 0 (cl0)     the pass after convergence: err = solve_real(f + ZE); the point y_new is evaluated
+      //                            speculatively (scipy evaluates f(y_new) only after accepting; the evaluation, its
+      //                            nfev count and its temperature check only take effect if the step is accepted)
+      //   closing pass 1 (cl1)     only where a rejected step is about to be rejected again (radau.py:493-495):
+      //                            err = solve_real(f(y + err) + ZE)
+      // The plants of a warp are in different passes at the same time: a plant that converges early closes while its
+      // neighbours still iterate.  In a closing pass the complex right-hand side is zero.
       const vd M_real = WT_MU_REAL * ih, Mc_re = WT_MU_CRE * ih, Mc_im = WT_MU_CIM * ih;
       vb converged = vbroadcast_b(false);
-      vb active = fget(F_RUNNING);
+      vb active = fget(F_RUNNING), cl0 = vbroadcast_b(false), cl1 = vbroadcast_b(false);
       vd dW_norm_old = vbroadcast(0.0), rate = vbroadcast(0.0);
       vb have_norm_old = vbroadcast_b(false), have_rate = vbroadcast_b(false);
       vi n_iter = vbroadcast_i(0);
+      vd y_new[3], ZE[3], escale[3], errv[3], f_new[3];
+      vb bad_new = vbroadcast_b(false);
+      vd err_norm = vbroadcast(0.0);
+      WT_UNROLL
+      for (int v = 0; v < 3; ++v) {
+        y_new[v] = y[v]; ZE[v] = vbroadcast(0.0); escale[v] = vbroadcast(0.0); errv[v] = vbroadcast(0.0);
+        f_new[v] = vbroadcast(0.0);
+      }
       WT_NOUNROLL
-      for (int k = 0; k < WT_NEWTON_MAXITER; ++k) {
-        if (!vany(active)) break;
+      for (int k = 0; k < WT_NEWTON_MAXITER + 2; ++k) {
+        const vb cl = cl0 | cl1;
+        if (!vany(active | cl)) break;
         n_iter = seli(active, k + 1, n_iter);
-        vd fr[3], cr[3], ci[3];
+        // A pass in which no plant iterates (all closing) needs ONE evaluation and no complex solve.
+        const bool newton_pass = vany(active);
+        vd fr[3], cr[3], ci[3], F[3], pc[3];
         WT_UNROLL
-        for (int v = 0; v < 3; ++v) { fr[v] = vbroadcast(0.0); cr[v] = vbroadcast(0.0); ci[v] = vbroadcast(0.0); }
-        vb finite = vbroadcast_b(true), bad_any = vbroadcast_b(false);
+        for (int v = 0; v < 3; ++v) {
+          fr[v] = vbroadcast(0.0); cr[v] = vbroadcast(0.0); ci[v] = vbroadcast(0.0); F[v] = vbroadcast(0.0);
+          pc[v] = sel(cl1, y[v] + errv[v], y_new[v]);  // the point a closing plant evaluates
+        }
+        vb finite = vbroadcast_b(true), bad_any = vbroadcast_b(false), bad = vbroadcast_b(false);
         WT_STAGE_UNROLL
-        for (int i = 0; i < 3; ++i) {  // three independent stage evaluations
-          vd F[3];
-          vb bad;
-          wt_rhs(g, c, y[0] + zrow(i, 0), y[1] + zrow(i, 1), y[2] + zrow(i, 2), F[0], F[1], F[2], bad);
-          bad_any = bad_any | bad;
+        for (int i = newton_pass ? 0 : 2; i < 3; ++i) {  // the three stages of a Newton pass; the LAST one is the closing evaluation
+          vd pnt[3];
+          WT_UNROLL
+          for (int v = 0; v < 3; ++v) pnt[v] = sel(active, y[v] + zrow(i, v), pc[v]);
+          wt_rhs(g, c, pnt[0], pnt[1], pnt[2], F[0], F[1], F[2], bad);
+          bad_any = bad_any | (bad & active);
           finite = finite & visfinite(F[0]) & visfinite(F[1]) & visfinite(F[2]);
           const double tr = wt_rk[14 + i], t1 = wt_rk[17 + i], t2 = wt_rk[20 + i];
           WT_UNROLL
@@ -1116,56 +1105,137 @@ struct WtPlantStep {
             ci[v] = ci[v] + F[v] * t2;
           }
         }
+        // F, bad: the last evaluation = f(y_new) of a cl0 plant (speculative), f(y + err) of a cl1 plant (it counts)
+        bad_any = bad_any | (bad & cl1);
         {
-          vb tb = active & wt_gany(g, bad_any);
+          vb tb = (active | cl1) & wt_gany(g, bad_any);
           fset(F_TRANGE, tb);
           fclr(F_RUNNING, tb);
           active = active & !tb;
+          cl1 = cl1 & !tb;
         }
         active = active & !wt_gany(g, !finite);  // radau.py:91-92: break, not converged
         WT_UNROLL
         for (int v = 0; v < 3; ++v) {
-          fr[v] = fr[v] - M_real * W[0][v];
-          vd re = cr[v] - (Mc_re * W[1][v] - Mc_im * W[2][v]);
-          vd im = ci[v] - (Mc_re * W[2][v] + Mc_im * W[1][v]);
-          cr[v] = re;
-          ci[v] = im;
+          // Newton: TI F - M W (radau.py:96-99); closing: f + ZE resp. f(y + err) + ZE, no complex part
+          const vd nr = fr[v] - M_real * W[0][v];
+          const vd re = cr[v] - (Mc_re * W[1][v] - Mc_im * W[2][v]);
+          const vd im = ci[v] - (Mc_re * W[2][v] + Mc_im * W[1][v]);
+          const vd er = sel(cl1, F[v], pk(PK_F + v)) + ZE[v];
+          fr[v] = sel(cl, er, nr);
+          cr[v] = sel(cl, 0.0, re);
+          ci[v] = sel(cl, 0.0, im);
         }
-        solve_newton(fr, cr, ci);
+        solve_newton(fr, cr, ci, newton_pass);
         vd q = vbroadcast(0.0);
         WT_UNROLL
         for (int v = 0; v < 3; ++v) {
-          vd a = fr[v] * scale[v], b = cr[v] * scale[v], d = ci[v] * scale[v];
+          const vd sr = sel(cl, escale[v], scale[v]);
+          vd a = fr[v] * sr, b = cr[v] * scale[v], d = ci[v] * scale[v];
           q = q + ((a * a + b * b) + d * d);
         }
-        vd dW_norm = vsqrt(wt_gsum(g, q)) * g.inv_sqrt3N;
-        vd new_rate = wt_div(dW_norm, dW_norm_old);
-        rate = sel(active & have_norm_old, new_rate, rate);
-        have_rate = have_rate | (active & have_norm_old);
-        // rate ** (NEWTON_MAXITER - k)
-        vd rp = rate;
-        WT_NOUNROLL
-        for (int e = 1; e < WT_NEWTON_MAXITER - k; ++e) rp = rp * rate;
-        const vd i1r = wt_rcp(1.0 - rate);
-        vb brk = active & have_rate & ((rate >= 1.0) | (rp * i1r * dW_norm > WT_NEWTON_TOL));
-        active = active & !brk;
-        WT_UNROLL
-        for (int v = 0; v < 3; ++v) {
-          W[0][v] = sel(active, W[0][v] + fr[v], W[0][v]);
-          W[1][v] = sel(active, W[1][v] + cr[v], W[1][v]);
-          W[2][v] = sel(active, W[2][v] + ci[v], W[2][v]);
+        // common.py:63-65 over the 3 n (closing) or 9 n (Newton) scaled unknowns
+        const vd nrm = vsqrt(wt_gsum(g, q)) * sel(cl, g.inv_sqrtN, g.inv_sqrt3N);
+        // ---- Newton pass: convergence control (radau.py:101-130)
+        {
+          const vd dW_norm = nrm;
+          vd new_rate = wt_div(dW_norm, dW_norm_old);
+          rate = sel(active & have_norm_old, new_rate, rate);
+          have_rate = have_rate | (active & have_norm_old);
+          // rate ** (NEWTON_MAXITER - k)
+          vd rp = rate;
+          WT_NOUNROLL
+          for (int e = 1; e < WT_NEWTON_MAXITER - k; ++e) rp = rp * rate;
+          const vd i1r = wt_rcp(1.0 - rate);
+          vb brk = active & have_rate & ((rate >= 1.0) | (rp * i1r * dW_norm > WT_NEWTON_TOL));
+          active = active & !brk;
+          WT_UNROLL
+          for (int v = 0; v < 3; ++v) {
+            W[0][v] = sel(active, W[0][v] + fr[v], W[0][v]);
+            W[1][v] = sel(active, W[1][v] + cr[v], W[1][v]);
+            W[2][v] = sel(active, W[2][v] + ci[v], W[2][v]);
+          }
+          const vb cvn = active & ((dW_norm == 0.0) | (have_rate & (rate * i1r * dW_norm < WT_NEWTON_TOL)));
+          converged = converged | cvn;
+          active = active & !cvn;
+          dW_norm_old = sel(cl, dW_norm_old, dW_norm);
+          have_norm_old = vbroadcast_b(true);
+          if (k + 1 >= WT_NEWTON_MAXITER) active = vbroadcast_b(false);  // radau.py:87: at most NEWTON_MAXITER iterations
+          // ---- closing pass: error norm, second estimate, accept / reject (radau.py:483-545)
+          if (vany(cl)) {
+            const vb clx = cl & fget(F_RUNNING);  // (not the plants whose evaluation at y + err just raised)
+            err_norm = sel(clx, nrm, err_norm);
+            const vb again = cl0 & fget(F_REJECTED) & (err_norm > 1.0);
+            WT_UNROLL
+            for (int v = 0; v < 3; ++v) {
+              errv[v] = sel(cl0, fr[v], errv[v]);
+              f_new[v] = sel(cl0, F[v], f_new[v]);
+            }
+            bad_new = selb(cl0, bad, bad_new);
+            lu->cadd(WTC_NFEV, seli(again, 1, 0));  // the evaluation at y + err of the next pass
+            const vb decide = clx & !again;
+            const vb rej = decide & (err_norm > 1.0);
+            vb acc = decide & !rej;
+            const vd safety = wt_div(vbroadcast(0.9 * (2 * WT_NEWTON_MAXITER + 1)), vfromint(n_iter + 2 * WT_NEWTON_MAXITER));
+            const vd pf = predict_factor(h_abs, pv(PV_H_OLD), err_norm, pv(PV_ERR_OLD), fget(F_HAVE_OLD));
+            h_abs = sel(rej, h_abs * vmax(safety * pf, 0.2), h_abs);
+            fclr(F_LU_VALID, rej);
+            fset(F_REJECTED, rej);
+            lu->cadd(WTC_NREJECT, seli(rej, 1, 0));
+            // f(y_new): now it counts (radau.py:514-516); a temperature outside [0, 100] C raises there
+            lu->cadd(WTC_NFEV, seli(acc, 1, 0));
+            {
+              const vb tb = acc & wt_gany(g, bad_new);
+              fset(F_TRANGE, tb);
+              fclr(F_RUNNING, tb);
+              acc = acc & !tb;
+            }
+            const vb recompute = (n_iter > 2) & (rate > 1e-3);
+            vd fct = vmin(safety * pf, 10.0);
+            const vb keep = (!recompute) & (fct < 1.2);
+            fct = sel(keep, 1.0, fct);
+            fclr(F_LU_VALID, acc & !keep);
+            fset(F_NEED_JAC, acc & recompute);
+            fclr(F_CURRENT_JAC, acc);  // set again by num_jac when recomputed
+            pvset(PV_SELF_H_OLD, pv(PV_SELF_H), acc);
+            pvset(PV_SELF_ERR_OLD, err_norm, acc);
+            pvset(PV_SELF_H, h_abs * fct, acc);
+            WT_UNROLL
+            for (int v = 0; v < 3; ++v) {
+              const vd Z0 = zrow(0, v), Z1 = zrow(1, v), Z2 = zrow(2, v);  // W is final once a plant has converged
+              pkset(PK_Q + 3 * v + 0, (Z0 * WT_P00 + Z1 * WT_P10) + Z2 * WT_P20, acc);
+              pkset(PK_Q + 3 * v + 1, (Z0 * WT_P01 + Z1 * WT_P11) + Z2 * WT_P21, acc);
+              pkset(PK_Q + 3 * v + 2, (Z0 * WT_P02 + Z1 * WT_P12) + Z2 * WT_P22, acc);
+              pkset(PK_YOLD + v, y[v], acc);
+              y[v] = sel(acc, y_new[v], y[v]);
+              pkset(PK_F + v, f_new[v], acc);
+            }
+            pvset(PV_SOL_TOLD, t, acc);
+            pvset(PV_SOL_H, t_new - t, acc);
+            fset(F_SELF_HAVE_OLD | F_HAVE_SOL | F_NEW_STEP, acc);
+            t = sel(acc, t_new, t);
+            lu->cadd(WTC_NSTEPS, seli(acc, 1, 0));
+            cl1 = again;
+          }
+          // ---- a plant that converged in this pass closes in the next one
+          cl0 = cvn;
+          if (vany(cvn)) {
+            WT_UNROLL
+            for (int v = 0; v < 3; ++v) {
+              const vd Z0 = zrow(0, v), Z1 = zrow(1, v), Z2 = zrow(2, v);
+              const vd yn = y[v] + Z2;
+              y_new[v] = sel(cvn, yn, y_new[v]);
+              ZE[v] = sel(cvn, ((Z0 * WT_E0 + Z1 * WT_E1) + Z2 * WT_E2) * ih, ZE[v]);
+              escale[v] = sel(cvn, wt_rcp(WT_ATOL + vmax(vabs(y[v]), vabs(yn)) * WT_RTOL), escale[v]);
+            }
+          }
         }
-        vb cv = active & ((dW_norm == 0.0) | (have_rate & (rate * i1r * dW_norm < WT_NEWTON_TOL)));
-        converged = converged | cv;
-        active = active & !cv;
-        dW_norm_old = dW_norm;
-        have_norm_old = vbroadcast_b(true);
       }
       // path counters of this attempt: n_iter Newton iterations with three RHS evaluations each (one update here
       // instead of two shared-memory read-modify-writes per iteration)
       lu->cadd(WTC_NNEWTON, n_iter);
       lu->cadd(WTC_NFEV, n_iter * 3);
-      // (6) outcome of the collocation solve (radau.py:464-481)
+      // (6) outcome of a collocation solve that did not converge (radau.py:464-481)
       {
         vb nc = fget(F_RUNNING) & !converged;
         lu->cadd(WTC_NNEWTON_FAIL, seli(nc, 1, 0));
@@ -1174,104 +1244,6 @@ struct WtPlantStep {
         vb halve = nc & fget(F_CURRENT_JAC);
         h_abs = sel(halve, h_abs * 0.5, h_abs);
         fclr(F_LU_VALID, halve);
-      }
-      vb cv = fget(F_RUNNING) & converged;
-      if (!vany(cv)) continue;
-
-      // (7) error estimate and step control (radau.py:483-512), (8) acceptance (radau.py:514-545).
-      // Three passes through ONE copy of "evaluate the RHS, solve with the real LU, take the scaled norm"
-      // (the kernel is bound by instruction fetch, so the three call sites share their code):
-      //   pass 0  err = solve(f + ZE)                               for the converged plants
-      //   pass 1  err = solve(f(y + err) + ZE)                      only where a rejected step is about to be
-      //                                                             rejected again (radau.py:493-495)
-      //   pass 2  f(y_new) and the bookkeeping of an accepted step  (radau.py:514-545)
-      vd Z[3][3], y_new[3], ZE[3], err[3], escale[3];
-      WT_UNROLL
-      for (int v = 0; v < 3; ++v) {
-        Z[0][v] = zrow(0, v); Z[1][v] = zrow(1, v); Z[2][v] = zrow(2, v);
-        y_new[v] = y[v] + Z[2][v];
-        ZE[v] = ((Z[0][v] * WT_E0 + Z[1][v] * WT_E1) + Z[2][v] * WT_E2) * ih;
-        err[v] = vbroadcast(0.0);
-        escale[v] = wt_rcp(WT_ATOL + vmax(vabs(y[v]), vabs(y_new[v])) * WT_RTOL);
-      }
-      const vd safety = wt_div(vbroadcast(0.9 * (2 * WT_NEWTON_MAXITER + 1)), vfromint(n_iter + 2 * WT_NEWTON_MAXITER));
-      vd err_norm = vbroadcast(0.0), pf = vbroadcast(0.0);
-      vb again = vbroadcast_b(false), acc = vbroadcast_b(false);
-      WT_NOUNROLL
-      for (int pass = 0; pass < 3; ++pass) {
-        vd F[3];
-        if (pass == 0) {
-          WT_UNROLL
-          for (int v = 0; v < 3; ++v) F[v] = pk(PK_F + v);
-        } else {
-          vb m;
-          vd pnt[3];
-          if (pass == 1) {
-            m = again;
-            WT_UNROLL
-            for (int v = 0; v < 3; ++v) pnt[v] = y[v] + err[v];
-          } else {
-            const vb rej = cv & (err_norm > 1.0);
-            acc = cv & !rej;
-            pf = predict_factor(h_abs, pv(PV_H_OLD), err_norm, pv(PV_ERR_OLD), fget(F_HAVE_OLD));
-            h_abs = sel(rej, h_abs * vmax(safety * pf, 0.2), h_abs);
-            fclr(F_LU_VALID, rej);
-            fset(F_REJECTED, rej);
-            lu->cadd(WTC_NREJECT, seli(rej, 1, 0));
-            m = acc;
-            WT_UNROLL
-            for (int v = 0; v < 3; ++v) pnt[v] = y_new[v];
-          }
-          if (!vany(m)) continue;
-          vb bad;
-          wt_rhs(g, c, pnt[0], pnt[1], pnt[2], F[0], F[1], F[2], bad);
-          lu->cadd(WTC_NFEV, seli(m, 1, 0));
-          const vb tb = m & wt_gany(g, bad);
-          fset(F_TRANGE, tb);
-          fclr(F_RUNNING, tb);
-          cv = cv & !tb;
-          acc = acc & !tb;
-        }
-        if (pass < 2) {
-          vd e[3];
-          WT_UNROLL
-          for (int v = 0; v < 3; ++v) e[v] = F[v] + ZE[v];
-          solve_real(e);
-          const vd en = rms3(e[0] * escale[0], e[1] * escale[1], e[2] * escale[2]);
-          if (pass == 0) {
-            WT_UNROLL
-            for (int v = 0; v < 3; ++v) err[v] = e[v];
-            err_norm = en;
-            again = cv & fget(F_REJECTED) & (err_norm > 1.0);
-          } else {
-            err_norm = sel(again, en, err_norm);
-          }
-        } else {  // radau.py:514-545
-          const vb recompute = (n_iter > 2) & (rate > 1e-3);
-          vd fct = vmin(safety * pf, 10.0);
-          const vb keep = (!recompute) & (fct < 1.2);
-          fct = sel(keep, 1.0, fct);
-          fclr(F_LU_VALID, acc & !keep);
-          fset(F_NEED_JAC, acc & recompute);
-          fclr(F_CURRENT_JAC, acc);  // set again by num_jac when recomputed
-          pvset(PV_SELF_H_OLD, pv(PV_SELF_H), acc);
-          pvset(PV_SELF_ERR_OLD, err_norm, acc);
-          pvset(PV_SELF_H, h_abs * fct, acc);
-          WT_UNROLL
-          for (int v = 0; v < 3; ++v) {
-            pkset(PK_Q + 3 * v + 0, (Z[0][v] * WT_P00 + Z[1][v] * WT_P10) + Z[2][v] * WT_P20, acc);
-            pkset(PK_Q + 3 * v + 1, (Z[0][v] * WT_P01 + Z[1][v] * WT_P11) + Z[2][v] * WT_P21, acc);
-            pkset(PK_Q + 3 * v + 2, (Z[0][v] * WT_P02 + Z[1][v] * WT_P12) + Z[2][v] * WT_P22, acc);
-            pkset(PK_YOLD + v, y[v], acc);
-            y[v] = sel(acc, y_new[v], y[v]);
-            pkset(PK_F + v, F[v], acc);
-          }
-          pvset(PV_SOL_TOLD, t, acc);
-          pvset(PV_SOL_H, t_new - t, acc);
-          fset(F_SELF_HAVE_OLD | F_HAVE_SOL | F_NEW_STEP, acc);
-          t = sel(acc, t_new, t);
-          lu->cadd(WTC_NSTEPS, seli(acc, 1, 0));
-        }
       }
     }
   }
