@@ -34,7 +34,8 @@ EXPORTS = (
     "wt_abi_version", "wt_device_count", "wt_last_error", "wt_step", "wt_advance", "wt_derivatives",
     "wt_step_host", "wt_step_workspace_bytes", "wt_calc_ph", "wt_measure_fp64_peak", "wt_stats", "wt_stats_size", "wt_stats_scratch_doubles",
     "wt_sensors_init", "wt_sensors_calibrate", "wt_sensors_read", "wt_diagnostics", "wt_register_image",
-    "wt_sensors_maintain", "wt_sensor_window_stats",
+    "wt_sensors_maintain", "wt_sensor_window_stats", "wt_sensors_reset", "wt_clock_tick", "wt_sensor_stats_size",
+    "wt_sensor_stats_scratch_doubles", "wt_sensor_stats", "wt_cost_order",
 )
 
 
@@ -87,8 +88,18 @@ def lib() -> C.CDLL:
     L.wt_sensors_calibrate.argtypes = [C.c_int, C.c_int, C.c_double, dp, C.c_double, dp, ip, vp]
     L.wt_sensors_calibrate.restype = C.c_int
     L.wt_sensors_read.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_uint, C.c_double, C.c_double, dp, dp, dp, dp, dp, dp, ip,
-                                  dp, ip, dp, ip, ip, C.POINTER(C.c_double), C.c_uint64, vp]
+                                  dp, ip, dp, ip, ip, C.POINTER(C.c_double), C.c_uint64, dp, vp]
     L.wt_sensors_read.restype = C.c_int
+    L.wt_sensors_reset.argtypes = [C.c_int, C.c_int, C.c_double, dp, dp, ip, ip, vp]
+    L.wt_sensors_reset.restype = C.c_int
+    L.wt_clock_tick.argtypes = [dp, vp]
+    L.wt_clock_tick.restype = C.c_int
+    L.wt_sensor_stats_size.restype = C.c_int
+    L.wt_sensor_stats_scratch_doubles.restype = C.c_int
+    L.wt_sensor_stats.argtypes = [C.c_int, dp, ip, ip, up, dp, dp, dp, C.c_int, vp]
+    L.wt_sensor_stats.restype = C.c_int
+    L.wt_cost_order.argtypes = [C.c_int, ip, ip, ip, vp]
+    L.wt_cost_order.restype = C.c_int
     L.wt_diagnostics.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, ip, vp]
     L.wt_diagnostics.restype = C.c_int
     L.wt_register_image.argtypes = [C.c_int, ip, C.c_int, dp, ip, C.c_double, vp, vp, vp, vp]

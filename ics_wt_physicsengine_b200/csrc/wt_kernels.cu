@@ -910,7 +910,114 @@ __global__ void wt_sensors_calibrate_kernel(int P, int sensor, double t, const d
   S[(size_t)WT_SF_TCAL * WT_NSENS * Pz] = t;
   S[(size_t)WT_SF_TPOWER * WT_NSENS * Pz] = t;
   sens_i[(size_t)sensor * Pz + p] = SS_NORMAL;
-  sens_i[((size_t)WT_NSENS + sensor) * Pz + p] = SFLT_NONE;
+  sens_i[((size_t)WT_SI_FAULT * WT_NSENS + sensor) * Pz + p] = SFLT_NONE;
+  sens_i[((size_t)WT_SI_FLAGS * WT_NSENS + sensor) * Pz + p] &= ~1;   // calibration_history.append(record)
+}
+
+// BaseSensor.reset (base_sensor.py:858-878) for sensor `sensor` of every plant, with the simulated time t where the
+// reference stamps time.monotonic(): value to mid-range, offset 0, histories cleared (every later read reports
+// CALIBRATION_EXPIRED until calibrate()), status / fault cleared, warm-up restarted, the sensor's sample line emptied
+// (the pH and temperature sensors of one side share the line object, sensors/__init__.py:62-67).
+__global__ void wt_sensors_reset_kernel(int P, int sensor, double t, const double *cfg_flow, double *sens, int *sens_i, int *ring_i) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const size_t Pz = (size_t)P;
+  const int type = wt_sensor_type(sensor);
+  double *S = sens + (size_t)sensor * Pz + p;
+  const double lo = type == ST_TEMP_RTD ? -10.0 : 0.0;
+  const double hi = type == ST_PH ? 14.0 : (type == ST_TEMP_RTD ? 110.0 : (type == ST_FLOW_MAG ? cfg_flow[p] * 2.0 : 10.0));
+  S[(size_t)WT_SF_CUR * WT_NSENS * Pz] = (lo + hi) / 2.0;
+  S[(size_t)WT_SF_CALOFF * WT_NSENS * Pz] = 0.0;
+  S[(size_t)WT_SF_TCAL * WT_NSENS * Pz] = t;
+  S[(size_t)WT_SF_TPOWER * WT_NSENS * Pz] = t;
+  S[(size_t)WT_SF_LASTVAL * WT_NSENS * Pz] = nan("");
+  sens_i[(size_t)sensor * Pz + p] = SS_NORMAL;
+  sens_i[((size_t)WT_SI_FAULT * WT_NSENS + sensor) * Pz + p] = SFLT_NONE;
+  sens_i[((size_t)WT_SI_HIST * WT_NSENS + sensor) * Pz + p] = 0;
+  sens_i[((size_t)WT_SI_FLAGS * WT_NSENS + sensor) * Pz + p] |= 1;
+  const int line = (sensor == 0 || sensor == 5) ? 0 : ((sensor == 1 || sensor == 6) ? 1 : -1);
+  if (line >= 0) { ring_i[((size_t)line * 2 + 0) * Pz + p] = 0; ring_i[((size_t)line * 2 + 1) * Pz + p] = 0; }
+}
+
+// device clock of a sensor suite {t, t_prev, read_index, t0, dt}: advanced in stream order after every read of a
+// captured (CUDA graph) step, so that replays need no new launch arguments.  t = t0 + k dt, as the host loop computes it.
+__global__ void wt_clock_tick_kernel(double *clock) {
+  const double k = clock[2] + 1.0;
+  clock[1] = clock[0];
+  clock[2] = k;
+  clock[0] = clock[3] + k * clock[4];
+}
+
+// Per-sensor ensemble statistics of the LAST suite read (the sensor half of the all-reduce payload, SURVEY.md 8e;
+// reference analogue BaseSensor.get_statistics, base_sensor.py:809-856, here across plants instead of across time):
+//   out[s * WT_SSTAT_N + 0] readings with a finite value   [1] sum (value - shift_s)   [2] sum (value - shift_s)^2
+//   [3 .. 14] SensorStatus histogram   [15 .. 21] SensorFault histogram          (s = sensor 0..6; halted plants skipped)
+// One block per (sensor, slab) -> partials summed in a fixed order by the final kernel: bitwise reproducible.
+#define WT_SSTAT_N 22
+__global__ void __launch_bounds__(WT_STATS_TPB) wt_sensor_stats_partial_kernel(int P, const double *value, const int32_t *st,
+                                                                                 const int32_t *ft, const uint32_t *plant_status,
+                                                                                 const double *shift7, double *partial) {
+  __shared__ double sh[WT_STATS_TPB / 32];
+  __shared__ int hist[12 + 7];
+  const int s = blockIdx.y;
+  const int per_block = (P + gridDim.x - 1) / gridDim.x;
+  const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
+  if (threadIdx.x < 19) hist[threadIdx.x] = 0;
+  __syncthreads();
+  const double c = shift7[s];
+  double nv = 0, s1 = 0, s2 = 0;
+  for (int p = lo + threadIdx.x; p < hi; p += WT_STATS_TPB) {
+    if (plant_status[p] & WTS_HALT_MASK) continue;
+    const double v = value[(size_t)s * P + p];
+    if (isfinite(v)) { const double d = v - c; nv += 1.0; s1 += d; s2 += d * d; }
+    const int a = st[(size_t)s * P + p], b = ft[(size_t)s * P + p];
+    if (a >= 0 && a < 12) atomicAdd(&hist[a], 1);
+    if (b >= 0 && b < 7) atomicAdd(&hist[12 + b], 1);
+  }
+  double *out = partial + ((size_t)blockIdx.x * WT_NSENS + s) * WT_SSTAT_N;
+  double r;
+  r = block_sum(nv, sh); if (threadIdx.x == 0) out[0] = r;
+  r = block_sum(s1, sh); if (threadIdx.x == 0) out[1] = r;
+  r = block_sum(s2, sh); if (threadIdx.x == 0) out[2] = r;
+  if (threadIdx.x < 19) out[3 + threadIdx.x] = (double)hist[threadIdx.x];
+}
+
+// Counting sort of the plants by the work of their last step, most expensive first (scheduling only: stragglers
+// start first and plants with similar solver paths share a warp).  Keys are small integers (collocation solves +
+// Newton iterations), so three tiny kernels replace a general radix sort: histogram, exclusive scan over the
+// descending keys, scatter.  The order inside a key is whatever the atomics give -- results never depend on it.
+#define WT_COST_BINS 1024
+__global__ void wt_cost_hist_kernel(int P, const int32_t *cost, int32_t *bins) {
+  __shared__ int sh[WT_COST_BINS];
+  for (int i = threadIdx.x; i < WT_COST_BINS; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+    int c = cost[p];
+    c = c < 0 ? 0 : (c >= WT_COST_BINS ? WT_COST_BINS - 1 : c);
+    atomicAdd(&sh[c], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < WT_COST_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&bins[i], sh[i]);
+}
+__global__ void wt_cost_scan_kernel(int32_t *bins) {  // one block of WT_COST_BINS threads: bins[c] <- first slot of key c, keys descending
+  __shared__ int sh[WT_COST_BINS];
+  const int i = threadIdx.x;
+  sh[i] = bins[WT_COST_BINS - 1 - i];  // descending
+  __syncthreads();
+  for (int o = 1; o < WT_COST_BINS; o <<= 1) {
+    const int v = i >= o ? sh[i - o] : 0;
+    __syncthreads();
+    sh[i] += v;
+    __syncthreads();
+  }
+  bins[WT_COST_BINS - 1 - i] = sh[i] - (i == 0 ? sh[0] : sh[i] - sh[i - 1]);  // exclusive
+}
+__global__ void wt_cost_scatter_kernel(int P, const int32_t *cost, int32_t *cursor, int32_t *order) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  int c = cost[p];
+  c = c < 0 ? 0 : (c >= WT_COST_BINS ? WT_COST_BINS - 1 : c);
+  order[atomicAdd(&cursor[c], 1)] = p;
 }
 
 // Maintenance operations of the reference sensors, for sensor `sensor` of every plant:
@@ -950,7 +1057,8 @@ __global__ void wt_sensors_maintain_kernel(int P, int sensor, int op, double t, 
     MF(WT_SF_TCAL) = t;
     MF(WT_SF_TPOWER) = t;
     sens_i[(size_t)sensor * Pz + p] = SS_NORMAL;
-    sens_i[((size_t)WT_NSENS + sensor) * Pz + p] = SFLT_NONE;
+    sens_i[((size_t)WT_SI_FAULT * WT_NSENS + sensor) * Pz + p] = SFLT_NONE;
+    sens_i[((size_t)WT_SI_FLAGS * WT_NSENS + sensor) * Pz + p] &= ~1;
   }
 #undef MF
 }
@@ -991,14 +1099,18 @@ int wt_sensors_calibrate(int P, int sensor, double t, const double *ref_dev, dou
 int wt_sensors_read(int P, int n, long long plant0, unsigned read_index, double t, double t_prev, const double *y,
                     const double *flow, const double *cfg_flow, const double *cfg_cl, const double *cfg_T, double *sens,
                     int32_t *sens_i, double *ring, int32_t *ring_i, double *out, int32_t *out_status, int32_t *out_fault,
-                    const double *suite6, uint64_t seed, void *stream) {
+                    const double *suite8, uint64_t seed, const double *clock_dev, void *stream) {
   int rc = check_common(P, n);
   if (rc) return rc;
   if (!y || !flow || !cfg_flow || !cfg_cl || !cfg_T || !sens || !sens_i || !ring || !ring_i || !out || !out_status ||
-      !out_fault || !suite6)
+      !out_fault || !suite8)
     return set_err(WT_ERR_BAD_ARG, "null pointer");
+  const double *suite6 = suite8;
+  if (!(suite8[6] >= 0.0 && suite8[6] <= 3.0) || !(suite8[7] == 0.0 || suite8[7] == 1.0))
+    return set_err(WT_ERR_BAD_ARG, "unknown temperature / flow sensor type");
   SensorArgs a;
-  a.P = P; a.n = n; a.plant0 = plant0; a.read_index = read_index; a.t = t; a.t_prev = t_prev;
+  a.P = P; a.n = n; a.plant0 = plant0; a.read_index = read_index; a.t = t; a.t_prev = t_prev; a.clock = clock_dev;
+  a.s.temp_kind = (int)suite8[6]; a.s.flow_kind = (int)suite8[7];
   a.y = y; a.flow = flow; a.cfg_flow = cfg_flow; a.cfg_cl = cfg_cl; a.cfg_T = cfg_T;
   a.sens = sens; a.sens_i = sens_i; a.ring = ring; a.ring_i = ring_i; a.out = out; a.out_status = out_status;
   a.out_fault = out_fault;
@@ -1007,6 +1119,55 @@ int wt_sensors_read(int P, int n, long long plant0, unsigned read_index, double 
   a.s.seed_lo = (uint32_t)seed; a.s.seed_hi = (uint32_t)(seed >> 32);
   wt_sensors_read_kernel<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
   return cuda_err(cudaGetLastError(), "wt_sensors_read_kernel launch");
+}
+
+int wt_sensors_reset(int P, int sensor, double t, const double *cfg_flow, double *sens, int32_t *sens_i, int32_t *ring_i,
+                     void *stream) {
+  if (P <= 0 || sensor < 0 || sensor >= WT_NSENS) return set_err(WT_ERR_BAD_ARG, "bad P or sensor index");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (!cfg_flow || !sens || !sens_i || !ring_i) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  wt_sensors_reset_kernel<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, sensor, t, cfg_flow, sens, sens_i, ring_i);
+  return cuda_err(cudaGetLastError(), "wt_sensors_reset_kernel launch");
+}
+
+int wt_clock_tick(double *clock_dev, void *stream) {
+  if (!clock_dev) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  wt_clock_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(clock_dev);
+  return cuda_err(cudaGetLastError(), "wt_clock_tick_kernel launch");
+}
+
+int wt_sensor_stats_size(void) { return WT_NSENS * WT_SSTAT_N; }
+int wt_sensor_stats_scratch_doubles(void) { return 256 * WT_NSENS * WT_SSTAT_N; }
+int wt_sensor_stats(int P, const double *out_value, const int32_t *out_status, const int32_t *out_fault,
+                    const uint32_t *plant_status, const double *shift7, double *stats, double *scratch, int accumulate,
+                    void *stream) {
+  if (P <= 0) return set_err(WT_ERR_BAD_ARG, "P must be positive");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (!out_value || !out_status || !out_fault || !plant_status || !shift7 || !stats || !scratch)
+    return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  int blocks = (P + 8 * WT_STATS_TPB - 1) / (8 * WT_STATS_TPB);
+  if (blocks > 256) blocks = 256;
+  const int nstat = WT_NSENS * WT_SSTAT_N;
+  wt_sensor_stats_partial_kernel<<<dim3(blocks, WT_NSENS), WT_STATS_TPB, 0, (cudaStream_t)stream>>>(P, out_value, out_status, out_fault,
+                                                                                              plant_status, shift7, scratch);
+  wt_stats_final_kernel<<<(nstat + 127) / 128, 128, 0, (cudaStream_t)stream>>>(blocks, nstat, scratch, stats, accumulate);
+  return cuda_err(cudaGetLastError(), "wt_sensor_stats launch");
+}
+
+int wt_cost_order(int P, const int32_t *cost_dev, int32_t *order_dev, int32_t *bins_dev, void *stream) {
+  if (P <= 0) return set_err(WT_ERR_BAD_ARG, "P must be positive");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (!cost_dev || !order_dev || !bins_dev) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(bins_dev, 0, WT_COST_BINS * sizeof(int32_t), s);
+  if (e != cudaSuccess) return cuda_err(e, "cudaMemsetAsync");
+  int blocks = (P + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  wt_cost_hist_kernel<<<blocks, 256, 0, s>>>(P, cost_dev, bins_dev);
+  wt_cost_scan_kernel<<<1, WT_COST_BINS, 0, s>>>(bins_dev);
+  wt_cost_scatter_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, cost_dev, bins_dev, order_dev);
+  return cuda_err(cudaGetLastError(), "wt_cost_order launch");
 }
 
 // Host-buffer path: per device, one workspace grown on demand, three copy/compute streams, one event, and the

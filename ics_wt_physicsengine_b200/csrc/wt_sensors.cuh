@@ -3,7 +3,8 @@
 // One thread per plant reads the 7 sensors of create_realistic_sensor_suite (reference
 // src/wt_simulator/sensors/__init__.py:41-120) in the reference's dict order:
 //   0 pH_inlet (zone 0, line A)   1 pH_outlet (zone n-1, line B)   2 chlorine_inlet (amperometric, zone 0)
-//   3 chlorine_outlet (DPD, zone n-1)   4 flow_main (magnetic)   5 temp_inlet (RTD, line A)   6 temp_outlet (RTD, line B)
+//   3 chlorine_outlet (DPD, zone n-1)   4 flow_main (magnetic | turbine)   5 temp_inlet (line A)   6 temp_outlet (line B)
+//   (temperature sensors: RTD PT100 as in the factory, or PT1000 / thermocouple K / J -- the suite configuration word)
 // and runs, per sensor, BaseSensor.read (base_sensor.py:509-699) followed by the subclass
 // post-processing (ph_sensor.py:216-336, chlorine_sensor.py:345-484, temperature_sensor.py:110-171,
 // flow_sensor.py:125-219).  The reference's emergent behaviour is kept on purpose (SURVEY.md
@@ -17,8 +18,8 @@
 // secrets.randbits (base_sensor.py:331), so only distributional parity with it is meaningful.
 //
 // State layout in HBM (fp64 / int32, plant index fastest):
-//   sens[(field * 7 + sensor) * P + p]      field: WT_SF_*  (WT_NSF = 9 fields)
-//   sens_i[(field * 7 + sensor) * P + p]    field: 0 status, 1 fault
+//   sens[(field * 7 + sensor) * P + p]      field: WT_SF_*  (WT_NSF = 10 fields)
+//   sens_i[(field * 7 + sensor) * P + p]    field: WT_SI_* (status, fault, len(reading_history), flags)
 //   ring[((line * WT_RING + slot) * 2 + f) * P + p]   f: 0 timestamp, 1 value   (the stored sample
 //       temperature of SampleLine.transport_sample is never used by read(): base_sensor.py:610-614)
 //   ring_i[(line * 2 + f) * P + p]          f: 0 head (next write slot), 1 count
@@ -34,11 +35,17 @@
 #define WT_SF_CALOFF 2    // calibration_offset
 #define WT_SF_TCAL 3      // last_calibration_time == calibration record timestamp
 #define WT_SF_LASTVAL 4   // reading_history[-1].value
-#define WT_SF_AUX0 5      // pH: membrane_fouling | Cl amp: membrane_fouling | DPD: reagent_potency | flow: electrode_fouling
+#define WT_SF_AUX0 5      // pH: membrane_fouling | Cl amp: membrane_fouling | DPD: reagent_potency | flow: electrode_fouling (magnetic) / bearing_wear_days (turbine) | thermocouple: cold_junction_drift
 #define WT_SF_AUX1 6      // pH: reference_contamination | Cl amp: membrane_age_days | DPD: light_exposure_hours
 #define WT_SF_AUX2 7      // pH: days_since_cleaning | DPD: reagent_age_days
 #define WT_SF_TPOWER 8   // power_on_time (differs from WT_SF_TCAL only after clean_electrode)
-#define WT_NSF 9
+#define WT_SF_AUX3 9     // pH: slope_percentage (only refreshed while a calibration record exists, ph_sensor.py:274-279)
+#define WT_NSF 10
+#define WT_SI_STATUS 0
+#define WT_SI_FAULT 1
+#define WT_SI_HIST 2      // len(reading_history): reads since construction / reset()
+#define WT_SI_FLAGS 3     // bit 0: calibration_history is empty (after reset(), until the next calibrate())
+#define WT_NSI 4
 #define WT_SO_VALUE 0     // outputs: out[(field * 7 + sensor) * P + p]
 #define WT_SO_RAW 1
 #define WT_SO_NOISE 2
@@ -52,8 +59,11 @@ enum { SS_NORMAL = 0, SS_CALIBRATING, SS_WARMING_UP, SS_FAILED, SS_SATURATED, SS
 enum { SFLT_NONE = 0, SFLT_OPEN, SFLT_SHORT, SFLT_RANGE, SFLT_RATE, SFLT_POWER_LOW, SFLT_POWER_HIGH };
 enum { ST_PH = 0, ST_CL_AMP, ST_CL_DPD, ST_FLOW_MAG, ST_TEMP_RTD };
 
-struct WtSuiteCfg {   // InstallationQuality of the suite (sensors/__init__.py:53-59) + line delay
+enum { WT_TEMP_RTD_PT100 = 0, WT_TEMP_RTD_PT1000 = 1, WT_TEMP_TC_K = 2, WT_TEMP_TC_J = 3 };  // TemperatureSensorType, temperature_sensor.py:29-35
+enum { WT_FLOW_MAGNETIC = 0, WT_FLOW_TURBINE = 1 };                                           // FlowSensorType, flow_sensor.py:33-37
+struct WtSuiteCfg {   // InstallationQuality of the suite (sensors/__init__.py:53-59) + line delay + sensor variants
   double flow_velocity, bubble_per_min, grounding, vibration_g, ambient_temp, line_delay_s;
+  int temp_kind, flow_kind;
   uint32_t seed_lo, seed_hi;
 };
 
@@ -62,6 +72,8 @@ struct SensorArgs {
   long long plant0;      // global id of this shard's first plant (RNG counter)
   unsigned read_index;   // k: number of suite reads done before this one
   double t, t_prev;      // current_time of this read, of the previous read
+  const double *clock;   // optional device clock {t, t_prev, read_index, t0, dt} overriding the three values above
+                         // (CUDA-graph replays: the launch arguments are frozen, the clock is advanced by wt_clock_tick)
   const double *y;       // plant state [3][n][P]
   const double *flow;    // state.flow_rate [P]
   const double *cfg_flow, *cfg_cl, *cfg_T;  // per-plant configuration values (full scale, calibration references)
@@ -142,9 +154,9 @@ __global__ void __launch_bounds__(128) wt_sensors_read_kernel(SensorArgs a) {
   if (p >= a.P) return;
   const size_t P = (size_t)a.P;
   const int n = a.n;
-  const double t = a.t;
-  const double dt_read = t - a.t_prev;            // reading.timestamp - reading_history[-2].timestamp
-  const bool have_prev = a.read_index > 0;        // len(reading_history) >= 1 before this read
+  const double t = a.clock ? a.clock[0] : a.t;
+  const double dt_read = t - (a.clock ? a.clock[1] : a.t_prev);   // reading.timestamp - reading_history[-2].timestamp
+  const unsigned read_index = a.clock ? (unsigned)a.clock[2] : a.read_index;
   const double FS = a.cfg_flow[p] * 2.0;          // sensors/__init__.py:104
   const unsigned long long gid = (unsigned long long)(a.plant0 + p);
 
@@ -154,11 +166,12 @@ __global__ void __launch_bounds__(128) wt_sensors_read_kernel(SensorArgs a) {
     const int line = (s == 0 || s == 5) ? 0 : ((s == 1 || s == 6) ? 1 : -1);
     // static descriptor (ph_sensor.py:73-96, chlorine_sensor.py:84-117, temperature_sensor.py:57-85, flow_sensor.py:52-78)
     double vmin = 0.0, vmax, prec, drift_rate, warmup, max_rate, validity_h;
+    const bool turbine = a.s.flow_kind == WT_FLOW_TURBINE, thermocouple = a.s.temp_kind >= WT_TEMP_TC_K;
     if (type == ST_PH) { vmax = 14.0; prec = 0.01; drift_rate = 0.01 / 24.0; warmup = 1800.0; max_rate = 0.5; validity_h = 24.0; }
     else if (type == ST_CL_AMP) { vmax = 10.0; prec = 0.01; drift_rate = 0.02 / 24.0; warmup = 300.0; max_rate = 1.0; validity_h = 24.0; }
     else if (type == ST_CL_DPD) { vmax = 10.0; prec = 0.02; drift_rate = 0.02 / 24.0; warmup = 60.0; max_rate = 1.0; validity_h = 24.0; }
-    else if (type == ST_FLOW_MAG) { vmax = FS; prec = 0.005 * FS; drift_rate = 0.0; warmup = 10.0; max_rate = FS; validity_h = 8760.0; }
-    else { vmin = -10.0; vmax = 110.0; prec = 0.1; drift_rate = 0.0; warmup = 30.0; max_rate = 10.0; validity_h = 8760.0; }
+    else if (type == ST_FLOW_MAG) { vmax = FS; prec = (turbine ? 0.01 : 0.005) * FS; drift_rate = 0.0; warmup = 10.0; max_rate = FS; validity_h = 8760.0; }
+    else { vmin = -10.0; vmax = 110.0; prec = thermocouple ? 0.5 : 0.1; drift_rate = 0.0; warmup = 30.0; max_rate = 10.0; validity_h = 8760.0; }
 
     double *S = a.sens + (size_t)s * P + p;      // + field * 7 * P
 #define SF(f) S[(size_t)(f) * WT_NSENS * P]
@@ -166,12 +179,17 @@ __global__ void __launch_bounds__(128) wt_sensors_read_kernel(SensorArgs a) {
     double *O = a.out + (size_t)s * P + p;
 #define OUT(f) O[(size_t)(f) * WT_NSENS * P]
     WtRng rng;
-    rng.c0 = (uint32_t)gid; rng.c1 = a.read_index ^ ((uint32_t)(gid >> 32) << 24); rng.sens = (uint32_t)s;
+    rng.c0 = (uint32_t)gid; rng.c1 = read_index ^ ((uint32_t)(gid >> 32) << 24); rng.sens = (uint32_t)s;
     rng.k0 = a.s.seed_lo; rng.k1 = a.s.seed_hi;
 
     double cur = SF(WT_SF_CUR);
     const double volt0 = SF(WT_SF_VOLT);
-    int status = SI[0], fault = SI[(size_t)WT_NSENS * P];
+    int status = SI[0], fault = SI[(size_t)WT_SI_FAULT * WT_NSENS * P];
+    // every read appends to reading_history, also the early returns below (base_sensor.py:570-595)
+    const int hist = SI[(size_t)WT_SI_HIST * WT_NSENS * P];
+    SI[(size_t)WT_SI_HIST * WT_NSENS * P] = hist + 1;
+    const bool have_prev = hist > 0;               // len(reading_history) >= 1 before this read
+    const bool has_cal = !(SI[(size_t)WT_SI_FLAGS * WT_NSENS * P] & 1);
 
     // base_sensor.py:556-577: the voltage drawn by the PREVIOUS read is checked first; a sensor that
     // ever drew V outside (20, 28) never redraws it -> absorbing
@@ -194,7 +212,8 @@ __global__ void __launch_bounds__(128) wt_sensors_read_kernel(SensorArgs a) {
       SF(WT_SF_LASTVAL) = nan("");
       continue;
     }
-    const bool cal_expired = ((t - tcal) / 3600.0) > validity_h;   // :598-600, CalibrationRecord.is_expired
+    // :598-600, _check_calibration_valid :432-436 (no record -> invalid), CalibrationRecord.is_expired
+    const bool cal_expired = !has_cal || ((t - tcal) / 3600.0) > validity_h;
     if (cal_expired) status = SS_CAL_EXPIRED;
 
     // _get_true_value
@@ -273,8 +292,12 @@ __global__ void __launch_bounds__(128) wt_sensors_read_kernel(SensorArgs a) {
         }
         const double en = n0 * (0.002 * (1.0 + 0.1 * fabs(value - 7.0)));                  // :242-246
         const double jn = n1 * (0.005 * (1.0 + contam));                                   // :249-253
-        const double days = (t - tcal) / 86400.0;                                           // :256-262
-        const double slope_pct = fmax(90.0, 100.0 - 0.001 * days);
+        double days = 0.0, slope_pct = SF(WT_SF_AUX3);                                      // :274-279
+        if (has_cal) {
+          days = (t - tcal) / 86400.0;
+          slope_pct = fmax(90.0, 100.0 - 0.001 * days);
+          SF(WT_SF_AUX3) = slope_pct;
+        }
         double slope_err = 0.0;                                                             // :265-273
         if (!(4.0 < value && value < 7.0)) slope_err = fmin(fabs(value - 4.0), fabs(value - 7.0)) * (100.0 - slope_pct) / 100.0;
         const double foul_off = foul * 0.2;                                                 // :276-277
@@ -313,9 +336,16 @@ __global__ void __launch_bounds__(128) wt_sensors_read_kernel(SensorArgs a) {
         value = fmin(fmax(fin, vmin), vmax);
         SF(WT_SF_AUX0) = pot; SF(WT_SF_AUX1) = light;
       } else if (type == ST_FLOW_MAG) {                                                     // flow_sensor.py:131-178, 201-219
-        double foul = SF(WT_SF_AUX0);
-        if (have_prev) foul += 0.001 * (dt_read / 86400.0);
-        double fin = value * fmax(0.9, 1.0 - 0.005 * foul) * 1.0 + n0 * (0.001 * FS);
+        double foul = SF(WT_SF_AUX0), fin;   // electrode_fouling (magnetic) or bearing_wear_days (turbine)
+        if (turbine) {                                                                     // :138-141, 180-199
+          if (have_prev) foul += (dt_read / 86400.0) * (1.0 + a.s.vibration_g * 5.0);
+          const double friction_loss = (0.01 * (1.0 + 0.01 * (foul / 365.0))) * FS;
+          const double eff = value < friction_loss ? 0.0 : value - friction_loss;
+          fin = eff + n0 * (a.s.vibration_g * 0.01 * FS);
+        } else {
+          if (have_prev) foul += 0.001 * (dt_read / 86400.0);
+          fin = value * fmax(0.9, 1.0 - 0.005 * foul) * 1.0 + n0 * (0.001 * FS);
+        }
         if (a.s.bubble_per_min > 0.0) {
           double ub, ub2;
           rng.uniform2(7, &ub, &ub2);
@@ -325,11 +355,21 @@ __global__ void __launch_bounds__(128) wt_sensors_read_kernel(SensorArgs a) {
         value = fmin(fmax(fin, 0.0), vmax);
         SF(WT_SF_AUX0) = foul;
       } else {                                                                              // temperature_sensor.py:116-171
-        const double R_true = 100.0 * (1.0 + 0.00385 * value);
-        const double R_meas = R_true + 2.0 * 0.5;
-        const double I_A = 1.0 / 1000.0;
-        const double she = 0.001 * (((I_A * I_A) * R_meas) * 1000.0);
-        double fin = (R_meas / 100.0 - 1.0) / 0.00385 + she + n0 * 0.001;
+        double fin;
+        if (thermocouple) {                                                                 // :173-194
+          const double v_seebeck = 40.0 * (value - 25.0);
+          const double cjd = SF(WT_SF_AUX0) + n0 * 0.01;
+          SF(WT_SF_AUX0) = cjd;
+          const double v_total = v_seebeck + n1 * 0.5;
+          fin = (v_total / 40.0) + 25.0 + cjd;
+        } else {                                                                            // RTD :150-171
+          const double R0 = a.s.temp_kind == WT_TEMP_RTD_PT1000 ? 1000.0 : 100.0;
+          const double R_true = R0 * (1.0 + 0.00385 * value);
+          const double R_meas = R_true + 2.0 * 0.5;
+          const double I_A = 1.0 / 1000.0;
+          const double she = 0.001 * (((I_A * I_A) * R_meas) * 1000.0);
+          fin = (R_meas / R0 - 1.0) / 0.00385 + she + n0 * 0.001;
+        }
         const double stem = 0.01 * (value - a.s.ambient_temp);
         fin += stem;
         o_drift = drift + stem;
@@ -340,7 +380,7 @@ __global__ void __launch_bounds__(128) wt_sensors_read_kernel(SensorArgs a) {
     SF(WT_SF_CUR) = cur;
     SF(WT_SF_LASTVAL) = value;
     SI[0] = status;
-    SI[(size_t)WT_NSENS * P] = fault;
+    SI[(size_t)WT_SI_FAULT * WT_NSENS * P] = fault;
     OUT(WT_SO_VALUE) = value; OUT(WT_SO_RAW) = truev; OUT(WT_SO_NOISE) = o_noise; OUT(WT_SO_DRIFT) = o_drift; OUT(WT_SO_UNC) = unc;
     a.out_status[(size_t)s * P + p] = status;
     a.out_fault[(size_t)s * P + p] = fault;
@@ -371,8 +411,11 @@ __global__ void wt_sensors_init_kernel(int P, double t0, const double *cfg_flow,
     S[(size_t)WT_SF_AUX0 * WT_NSENS * Pz] = type == ST_CL_DPD ? 1.0 : 0.0;  // reagent_potency = 1
     S[(size_t)WT_SF_AUX1 * WT_NSENS * Pz] = 0.0;
     S[(size_t)WT_SF_AUX2 * WT_NSENS * Pz] = 0.0;
+    S[(size_t)WT_SF_AUX3 * WT_NSENS * Pz] = 100.0;                          // slope_percentage, ph_sensor.py:137
     sens_i[(size_t)s * Pz + p] = SS_NORMAL;
-    sens_i[((size_t)WT_NSENS + s) * Pz + p] = SFLT_NONE;
+    sens_i[((size_t)WT_SI_FAULT * WT_NSENS + s) * Pz + p] = SFLT_NONE;
+    sens_i[((size_t)WT_SI_HIST * WT_NSENS + s) * Pz + p] = 0;
+    sens_i[((size_t)WT_SI_FLAGS * WT_NSENS + s) * Pz + p] = 0;
   }
   for (int k = 0; k < 4; ++k) ring_i[(size_t)k * Pz + p] = 0;
 }

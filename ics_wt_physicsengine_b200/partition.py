@@ -21,6 +21,8 @@ from .ensembles import Ensemble
 
 STATS_HDR = 8
 VARS = ("pH", "chlorine", "temperature")
+SENSOR_STATS = 22   # per sensor: valid count, shifted sum, shifted sum of squares, 12 status bins, 7 fault bins
+N_SENSORS = 7
 
 
 def shard_bounds(total: int, rank: int, world: int) -> Tuple[int, int]:
@@ -37,8 +39,8 @@ def shard_ensemble(e: Ensemble, rank: int, world: int) -> Ensemble:
     return e.slice(slice(lo, hi))
 
 
-def stats_size(n_zones: int) -> int:
-    return STATS_HDR + 6 * n_zones
+def stats_size(n_zones: int, sensors: bool = False) -> int:
+    return STATS_HDR + 6 * n_zones + (N_SENSORS * SENSOR_STATS if sensors else 0)
 
 
 @dataclass
@@ -52,6 +54,8 @@ class StatsSpec:
     pH_low: float = 6.5
     pH_high: float = 8.5
     temperature_max: float = 30.0
+    # shifts of the per-sensor moments (pH, pH, chlorine, chlorine, flow, temperature, temperature)
+    sensor_shifts: Tuple[float, ...] = (7.0, 7.0, 2.0, 2.0, 10.0, 20.0, 20.0)
 
     def as_row(self) -> np.ndarray:
         return np.array([self.shift_pH, self.shift_chlorine, self.shift_temperature, self.chlorine_min,
@@ -73,22 +77,45 @@ def finalize_stats(vec: np.ndarray, n_zones: int, spec: StatsSpec) -> Dict[str, 
         m1 = body[v, :, 0] / denom
         out[f"mean_{name}"] = shifts[v] + m1
         out[f"var_{name}"] = np.maximum(body[v, :, 1] / denom - m1 * m1, 0.0)  # population variance
+    off = STATS_HDR + 6 * n_zones
+    if vec.size >= off + N_SENSORS * SENSOR_STATS:
+        # per-sensor statistics of the last suite read over the live plants (reference analogue across time:
+        # BaseSensor.get_statistics, base_sensor.py:809-856): valid fraction, mean / variance of the finite readings,
+        # SensorStatus and SensorFault histograms (fractions of the live plants)
+        sb = vec[off:off + N_SENSORS * SENSOR_STATS].reshape(N_SENSORS, SENSOR_STATS)
+        nv = sb[:, 0]
+        dv = np.where(nv > 0, nv, np.nan)
+        m1 = sb[:, 1] / dv
+        out["sensor_valid_count"] = nv
+        out["sensor_valid_fraction"] = nv / denom
+        out["sensor_mean"] = np.asarray(spec.sensor_shifts) + m1
+        out["sensor_var"] = np.maximum(sb[:, 2] / dv - m1 * m1, 0.0)
+        out["sensor_status_hist"] = sb[:, 3:15] / denom
+        out["sensor_fault_hist"] = sb[:, 15:22] / denom
     return out
 
 
 class EnsembleStatistics:
     """Device-side accumulation + all-reduce of the ensemble statistics of one PlantEnsemble shard."""
 
-    def __init__(self, ensemble, spec: Optional[StatsSpec] = None):
+    def __init__(self, ensemble, spec: Optional[StatsSpec] = None, suite=None):
+        """``suite``: the ensemble's SensorSuite; its per-sensor statistics then follow the plant statistics in the
+        vector (valid count, sum, sum of squares, status and fault histograms per sensor)."""
         self.ens = ensemble
         self.spec = spec or StatsSpec()
+        self.suite = suite
         L = _lib.lib()
         n = ensemble.n_zones
-        self.size = L.wt_stats_size(n)
+        self.size_plants = L.wt_stats_size(n)
+        self.size = self.size_plants + (L.wt_sensor_stats_size() if suite is not None else 0)
+        assert self.size == stats_size(n, suite is not None)
         dev = ensemble.device
         self._spec_dev = torch.from_numpy(self.spec.as_row()).to(dev)
         self._out = torch.zeros(self.size, dtype=torch.float64, device=dev)
         self._scratch = torch.empty(L.wt_stats_scratch_doubles(n), dtype=torch.float64, device=dev)
+        if suite is not None:
+            self._shift7 = torch.tensor(self.spec.sensor_shifts, dtype=torch.float64, device=dev)
+            self._scratch_s = torch.empty(L.wt_sensor_stats_scratch_doubles(), dtype=torch.float64, device=dev)
 
     def local(self) -> torch.Tensor:
         """Statistics vector of this shard (device tensor, overwritten on every call)."""
@@ -98,7 +125,13 @@ class EnsembleStatistics:
             stream = torch.cuda.current_stream().cuda_stream
             rc = _lib.lib().wt_stats(e.n_plants, e.n_zones, p(e._y), p(e._status), p(self._spec_dev), p(self._out),
                                      p(self._scratch), 0, C.c_void_p(stream))
-        _lib.check(rc, "wt_stats")
+            _lib.check(rc, "wt_stats")
+            if self.suite is not None:
+                su = self.suite
+                rc = _lib.lib().wt_sensor_stats(e.n_plants, p(su._out[0]), p(su._out_status), p(su._out_fault), p(e._status),
+                                                p(self._shift7), p(self._out[self.size_plants:]), p(self._scratch_s), 0,
+                                                C.c_void_p(stream))
+                _lib.check(rc, "wt_sensor_stats")
         return self._out
 
     def allreduce(self, group=None) -> torch.Tensor:
@@ -143,8 +176,11 @@ class PipelinedShard:
             from .sensors import create_realistic_sensor_suite
             self.suites = [create_realistic_sensor_suite(e, seed=sensor_seed, plant0=plant0 + lo)
                            for e, (lo, _) in zip(self.engines, self.bounds)]
-        self.stats_parts = [EnsembleStatistics(e, spec) for e in self.engines]
+        self.stats_parts = [EnsembleStatistics(e, spec, None if self.suites is None else self.suites[i])
+                            for i, e in enumerate(self.engines)]
         self._sum = torch.zeros(self.stats_parts[0].size, dtype=torch.float64, device=self.device)
+        self._stack = torch.zeros((len(self.engines), self.stats_parts[0].size), dtype=torch.float64, device=self.device)
+        self._graph = None
         self.fork()
 
     def fork(self) -> None:
@@ -178,17 +214,65 @@ class PipelinedShard:
             with torch.cuda.stream(s):
                 e.advance(n_steps, dt, self.bnd[i])
 
+    def local_stats(self) -> torch.Tensor:
+        """Statistics vector of this rank's shard (device tensor): the parts' kernels on their own streams, joined,
+        summed in a fixed order."""
+        for i, (sp, s) in enumerate(zip(self.stats_parts, self.streams)):
+            with torch.cuda.stream(s):
+                self._stack[i].copy_(sp.local())
+        self.synchronize()
+        torch.sum(self._stack, dim=0, out=self._sum)
+        self.fork()  # the statistics buffers are reused by the next call
+        return self._sum
+
     def stats(self, group=None) -> torch.Tensor:
         """Statistics vector of the whole shard, summed over the ranks of ``group`` (one all-reduce)."""
-        for sp, s in zip(self.stats_parts, self.streams):
-            with torch.cuda.stream(s):
-                sp.local()
-        self.synchronize()
-        torch.sum(torch.stack([sp._out for sp in self.stats_parts]), dim=0, out=self._sum)
+        v = self.local_stats()
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+        return v
+
+    # ---- one CUDA graph per rank for a block of steps (SURVEY.md 8e) ------------------------------------------
+    def capture(self, n_steps: int, dt: float, t_next: float, with_stats: bool = True) -> None:
+        """Capture ``n_steps`` x (step + sensor read [+ cost order]) of every sub-ensemble, followed by the local
+        statistics, into ONE CUDA graph: a replay is a single launch from the host instead of ~10 per part and step.
+        The time of the sensor reads lives in a device clock (SensorSuite.start_clock) that the captured kernels
+        advance themselves; the next read happens at ``t_next``.  Warm up (run at least one eager step) first: the
+        first launch of a kernel sets its attributes, which cannot be captured."""
+        if self.suites is not None:
+            for su in self.suites:
+                su.start_clock(t_next, dt)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=self.device)
+        cap.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(cap):
+            with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
+                self.fork()
+                for _ in range(n_steps):
+                    for i, (e, s) in enumerate(zip(self.engines, self.streams)):
+                        with torch.cuda.stream(s):
+                            e.step(dt, self.bnd[i])
+                            if self.suites is not None:
+                                self.suites[i].read_clocked()
+                if with_stats:
+                    self.local_stats()
+                self.synchronize()
+        self._graph, self._graph_steps, self._graph_stats = g, int(n_steps), bool(with_stats)
+
+    def replay(self, group=None) -> Optional[torch.Tensor]:
+        """Replay the captured block of steps on the current stream; returns the (all-reduced) statistics vector when the
+        block was captured with statistics."""
+        self._graph.replay()
+        if self.suites is not None:
+            for su in self.suites:
+                su.account_reads(self._graph_steps)
+        if not self._graph_stats:
+            return None
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self._sum, op=dist.ReduceOp.SUM, group=group)
-        self.fork()  # the statistics buffers are reused by the next call
         return self._sum
 
     # aggregate views (they join the streams first)

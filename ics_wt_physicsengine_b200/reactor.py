@@ -223,8 +223,10 @@ class PlantEnsemble:
             self._counters = torch.zeros((_lib.NCNT, P), dtype=torch.int32, device=self.device)
             self._bnd_bcast = torch.zeros(NBND, dtype=torch.float64, device=self.device)
             self._bnd_batch = None
-            self._order = None
+            # cost order (scheduling only): a static buffer so that captured (CUDA graph) steps keep their pointers
+            self._order = torch.arange(P, dtype=torch.int32, device=self.device) if self.sort_every > 0 else None
             self._cost = torch.zeros(P, dtype=torch.int32, device=self.device) if self.sort_every > 0 else None
+            self._bins = torch.zeros(1024, dtype=torch.int32, device=self.device) if self.sort_every > 0 else None
             # device workspace of the step (work queue + hand-off rows between its two launches), reused by every step
             self._ws = torch.empty(int(_lib.lib().wt_step_workspace_bytes(P, n)), dtype=torch.uint8, device=self.device)
         self.state = EnsembleState(self._y, self._derived, self._time, self._flow)
@@ -306,9 +308,10 @@ class PlantEnsemble:
         """``n_steps`` consecutive ``step(dt, boundary)`` calls fused into one kernel launch."""
         bnd, stride = self._boundary(boundary)
         with torch.cuda.device(self.device):
-            if self.sort_every > 0 and self._launches > 0 and self._launches % self.sort_every == 0:
-                self._order = torch.argsort(self._cost, descending=True).to(torch.int32)
             stream = torch.cuda.current_stream().cuda_stream
+            if self.sort_every > 0 and self._launches > 0 and self._launches % self.sort_every == 0:
+                _lib.check(_lib.lib().wt_cost_order(self.n_plants, _ptr(self._cost), _ptr(self._order), _ptr(self._bins),
+                                                    C.c_void_p(stream)), "wt_cost_order")
             rc = _lib.lib().wt_advance(self.n_plants, self.n_zones, int(n_steps), float(dt), _ptr(self._par),
                                        _ptr(bnd), stride, _ptr(self._time), _ptr(self._y), _ptr(self._flow),
                                        _ptr(self._derived), _ptr(self._status), _ptr(self._counters),

@@ -48,6 +48,22 @@ class SensorFault(Enum):  # base_sensor.py:66-75
     POWER_HIGH = "power_high"
 
 
+class TemperatureSensorType(Enum):  # temperature_sensor.py:29-35
+    RTD_PT100 = "rtd_pt100"
+    RTD_PT1000 = "rtd_pt1000"
+    THERMOCOUPLE_K = "thermocouple_k"
+    THERMOCOUPLE_J = "thermocouple_j"
+
+
+class FlowSensorType(Enum):  # flow_sensor.py:33-37
+    TURBINE = "turbine"
+    MAGNETIC = "magnetic"
+
+
+_TEMP_CODE = {TemperatureSensorType.RTD_PT100: 0, TemperatureSensorType.RTD_PT1000: 1,
+              TemperatureSensorType.THERMOCOUPLE_K: 2, TemperatureSensorType.THERMOCOUPLE_J: 3}
+_FLOW_CODE = {FlowSensorType.MAGNETIC: 0, FlowSensorType.TURBINE: 1}
+
 STATUS_BY_CODE = tuple(SensorStatus)   # device codes are the enum declaration order
 FAULT_BY_CODE = tuple(SensorFault)
 SENSOR_NAMES = ("pH_inlet", "pH_outlet", "chlorine_inlet", "chlorine_outlet", "flow_main", "temp_inlet", "temp_outlet")
@@ -107,7 +123,9 @@ class SensorSuite:
     """The 7-sensor suite of every plant of one ensemble shard, state resident in HBM."""
 
     def __init__(self, ensemble, seed: int = 0, plant0: int = 0, installation: Optional[InstallationQuality] = None,
-                 sample_line: Optional[SampleLine] = None, history: int = 0):
+                 sample_line: Optional[SampleLine] = None, history: int = 0,
+                 temperature_sensor_type: TemperatureSensorType = TemperatureSensorType.RTD_PT100,
+                 flow_sensor_type: FlowSensorType = FlowSensorType.MAGNETIC):
         _lib.require_device()
         self.ens = ensemble
         self.seed, self.plant0 = int(seed) & (2 ** 64 - 1), int(plant0)
@@ -117,15 +135,21 @@ class SensorSuite:
         if int(line.transport_delay_s) + 10 > 100:
             raise ValueError("sample-line delay needs a deque longer than the 100 slots the engine keeps")
         i = self.installation
+        # the factory builds RTD PT100 and magnetic sensors (sensors/__init__.py:100-118); the other variants of
+        # TemperatureSensor / FlowSensor are selected for the whole suite
+        self.temperature_sensor_type = TemperatureSensorType(temperature_sensor_type)
+        self.flow_sensor_type = FlowSensorType(flow_sensor_type)
         self._suite6 = np.array([i.flow_velocity, i.air_bubble_frequency, i.grounding_quality, i.pipe_vibration_g,
-                                 i.ambient_temperature, line.transport_delay_s], dtype=np.float64)
+                                 i.ambient_temperature, line.transport_delay_s,
+                                 _TEMP_CODE[self.temperature_sensor_type], _FLOW_CODE[self.flow_sensor_type]], dtype=np.float64)
         P, dev = ensemble.n_plants, ensemble.device
         cfg = ensemble.cfg
         col = lambda k: torch.from_numpy(np.ascontiguousarray(cfg[:, CFG_FIELDS.index(k)])).to(dev)
         self._cfg_flow, self._cfg_cl, self._cfg_T = col("flow_rate"), col("initial_chlorine"), col("temperature")
         f64, i32 = torch.float64, torch.int32
-        self._sens = torch.zeros((9, 7, P), dtype=f64, device=dev)   # WT_NSF fields
-        self._sens_i = torch.zeros((2, 7, P), dtype=i32, device=dev)
+        self._sens = torch.zeros((10, 7, P), dtype=f64, device=dev)   # WT_NSF fields
+        self._sens_i = torch.zeros((4, 7, P), dtype=i32, device=dev)   # WT_NSI: status, fault, len(history), flags
+        self._clock = None   # device clock {t, t_prev, read_index, t0, dt} of captured (CUDA graph) reads
         self._ring = torch.zeros((2, 100, 2, P), dtype=f64, device=dev)
         self._ring_i = torch.zeros((2, 2, P), dtype=i32, device=dev)
         self._out = torch.zeros((5, 7, P), dtype=f64, device=dev)
@@ -188,7 +212,7 @@ class SensorSuite:
                 e.n_plants, e.n_zones, self.plant0, self.read_index, float(current_time), float(t_prev), p(e._y), p(e._flow),
                 p(self._cfg_flow), p(self._cfg_cl), p(self._cfg_T), p(self._sens), p(self._sens_i), p(self._ring),
                 p(self._ring_i), p(self._out), p(self._out_status), p(self._out_fault),
-                self._suite6.ctypes.data_as(C.POINTER(C.c_double)), C.c_uint64(self.seed), self._stream())
+                self._suite6.ctypes.data_as(C.POINTER(C.c_double)), C.c_uint64(self.seed), C.c_void_p(0), self._stream())
         _lib.check(rc, "wt_sensors_read")
         if self._hist is not None:
             self._hist[self.read_index % self.history].copy_(self._out[0])
@@ -201,6 +225,60 @@ class SensorSuite:
         return {name: BatchReading(float(current_time), o[0, s], o[1, s], o[2, s], o[3, s], self._out_status[s], o[4, s],
                                    self._out_fault[s]) for s, name in enumerate(SENSOR_NAMES)}
 
+
+    # ---- captured reads: the time of the read lives on the device so that a CUDA graph can be replayed ----
+    def start_clock(self, t_next: float, dt: float) -> None:
+        """Device clock for ``read_clocked``: the next read happens at ``t_next``, every following one ``dt`` later."""
+        if not self._initialized:
+            raise RuntimeError("call initialize(t0) first")
+        k = float(self.read_index)
+        t_prev = self.last_time if self.last_time is not None else float(t_next)
+        self._clock_host = (float(t_next), float(dt))
+        row = torch.tensor([float(t_next), float(t_prev), k, float(t_next) - k * float(dt), float(dt)], dtype=torch.float64)
+        if self._clock is None:
+            self._clock = torch.empty(5, dtype=torch.float64, device=self.ens.device)
+        self._clock.copy_(row)
+
+    def read_clocked(self) -> None:
+        """One suite read at the device clock's time followed by a clock tick (two launches, no host scalars:
+        capturable).  The caller accounts for the reads with ``account_reads`` after the (re)play."""
+        e = self.ens
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(e.device):
+            L = _lib.lib()
+            rc = L.wt_sensors_read(
+                e.n_plants, e.n_zones, self.plant0, 0, 0.0, 0.0, p(e._y), p(e._flow),
+                p(self._cfg_flow), p(self._cfg_cl), p(self._cfg_T), p(self._sens), p(self._sens_i), p(self._ring),
+                p(self._ring_i), p(self._out), p(self._out_status), p(self._out_fault),
+                self._suite6.ctypes.data_as(C.POINTER(C.c_double)), C.c_uint64(self.seed), p(self._clock), self._stream())
+            _lib.check(rc, "wt_sensors_read")
+            _lib.check(L.wt_clock_tick(p(self._clock), self._stream()), "wt_clock_tick")
+
+    def account_reads(self, n_reads: int) -> None:
+        """Host-side bookkeeping of ``n_reads`` clocked reads (read index, last read time)."""
+        t_next, dt = self._clock_host
+        self.read_index += int(n_reads)
+        self.last_time = t_next + (int(n_reads) - 1) * dt
+        self._clock_host = (t_next + int(n_reads) * dt, dt)
+
+    def readings(self) -> Dict[str, BatchReading]:
+        """The readings of the last read (views of the device output buffers)."""
+        o = self._out
+        t = self.last_time if self.last_time is not None else float("nan")
+        return {name: BatchReading(t, o[0, s], o[1, s], o[2, s], o[3, s], self._out_status[s], o[4, s], self._out_fault[s])
+                for s, name in enumerate(SENSOR_NAMES)}
+
+    def reset(self, name: str, current_time: float) -> None:
+        """BaseSensor.reset() (base_sensor.py:858-878) for sensor `name` of every plant; the reference stamps
+        time.monotonic() into the calibration / power-on times, the ensemble runs on simulated time, so the time is
+        an argument.  Every later read reports CALIBRATION_EXPIRED until ``calibrate`` (the reference clears its
+        calibration history, base_sensor.py:432-436, 870)."""
+        s = SENSOR_NAMES.index(name)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.ens.device):
+            rc = _lib.lib().wt_sensors_reset(self.ens.n_plants, s, float(current_time), p(self._cfg_flow), p(self._sens),
+                                             p(self._sens_i), p(self._ring_i), self._stream())
+        _lib.check(rc, "wt_sensors_reset")
 
     # ---- maintenance (SURVEY 8f rank 2): the reference's per-sensor methods, for that sensor of every plant ----
     def _maintain(self, name: str, op: int, t: float, a0: float = 0.0, a1: float = 0.0) -> None:
@@ -276,6 +354,6 @@ class SensorSuite:
         return ir, di, ok
 
 
-def create_realistic_sensor_suite(ensemble, seed: int = 0, plant0: int = 0, history: int = 0) -> SensorSuite:
+def create_realistic_sensor_suite(ensemble, seed: int = 0, plant0: int = 0, history: int = 0, **suite_kw) -> SensorSuite:
     """Batched counterpart of sensors/__init__.py:41-120 for a PlantEnsemble (same 7 keys)."""
-    return SensorSuite(ensemble, seed=seed, plant0=plant0, history=history)
+    return SensorSuite(ensemble, seed=seed, plant0=plant0, history=history, **suite_kw)

@@ -223,9 +223,11 @@ int wt_stats(int P, int n_zones, const double *y_dev, const uint32_t *status_dev
  * pH_x and temp_x share one SampleLine, as in the reference.
  *
  * Device buffers (plant index fastest; shapes in elements):
- *   sens     double [9][7][P]      per-sensor state (WT_SF_*: current_value, supply_voltage,
- *                                  calibration_offset, calibration time, last history value, 3 aux, power-on time)
- *   sens_i   int32  [2][7][P]      sticky SensorStatus, SensorFault (enum order of base_sensor.py:49-75)
+ *   sens     double [10][7][P]     per-sensor state (WT_SF_*: current_value, supply_voltage,
+ *                                  calibration_offset, calibration time, last history value, 3 aux, power-on time,
+ *                                  pH slope_percentage)
+ *   sens_i   int32  [4][7][P]      sticky SensorStatus, SensorFault (enum order of base_sensor.py:49-75),
+ *                                  len(reading_history), flags (bit 0: calibration_history is empty)
  *   ring     double [2][100][2][P] delay lines: (timestamp, value) per slot
  *   ring_i   int32  [2][2][P]      per line: head, count
  *   out      double [5][7][P]      SensorReading.value, raw_value, noise, drift, uncertainty
@@ -241,8 +243,16 @@ int wt_stats(int P, int n_zones, const double *y_dev, const uint32_t *status_dev
  *                       (base_sensor.py:543-549 raises; the Python facade checks it).
  *     plant0      global id of the shard's first plant; read_index = number of earlier suite reads
  *                 (both only feed the counter-based Philox4x32-10 RNG: results are independent of sharding)
- *     suite6      HOST array {flow_velocity, air_bubble_frequency, grounding_quality, pipe_vibration_g,
- *                 ambient_temperature, sample-line transport delay [s]}
+ *     suite8      HOST array {flow_velocity, air_bubble_frequency, grounding_quality, pipe_vibration_g,
+ *                 ambient_temperature, sample-line transport delay [s], TemperatureSensorType of temp_inlet /
+ *                 temp_outlet (0 rtd_pt100 = the factory's, 1 rtd_pt1000, 2 thermocouple_k, 3 thermocouple_j;
+ *                 temperature_sensor.py:29-35, 150-194), FlowSensorType of flow_main (0 magnetic = the factory's,
+ *                 1 turbine; flow_sensor.py:33-37, 180-219)}
+ *     clock_dev   NULL, or a device array {t, t_prev, read_index, t0, dt} that overrides the t / t_prev / read_index
+ *                 arguments: a captured (CUDA graph) step replays with frozen launch arguments and advances the
+ *                 clock with wt_clock_tick after every read (t = t0 + read_index * dt)
+ * wt_sensors_reset    = BaseSensor.reset() (base_sensor.py:858-878) for one sensor of every plant, with the
+ *                       simulated time t where the reference stamps time.monotonic()
  * ------------------------------------------------------------------------------------- */
 int wt_sensors_init(int P, double t0, const double *cfg_flow_dev, const double *cfg_chlorine_dev,
                     const double *cfg_temperature_dev, double *sens_dev, int32_t *sens_i_dev,
@@ -265,8 +275,27 @@ int wt_sensors_read(int P, int n_zones, long long plant0, unsigned read_index, d
                     const double *y_dev, const double *flow_rate_dev, const double *cfg_flow_dev,
                     const double *cfg_chlorine_dev, const double *cfg_temperature_dev, double *sens_dev,
                     int32_t *sens_i_dev, double *ring_dev, int32_t *ring_i_dev, double *out_dev,
-                    int32_t *out_status_dev, int32_t *out_fault_dev, const double *suite6,
-                    uint64_t seed, void *stream);
+                    int32_t *out_status_dev, int32_t *out_fault_dev, const double *suite8,
+                    uint64_t seed, const double *clock_dev, void *stream);
+int wt_sensors_reset(int P, int sensor, double t, const double *cfg_flow_dev, double *sens_dev,
+                     int32_t *sens_i_dev, int32_t *ring_i_dev, void *stream);
+int wt_clock_tick(double *clock_dev, void *stream);
+
+/* Per-sensor ensemble statistics of the last suite read: the sensor half of the all-reduce payload of SURVEY.md
+ * section 8(e) / BASELINE configs[4] (reference analogue: BaseSensor.get_statistics, base_sensor.py:809-856,
+ * taken across plants instead of across time).  Halted plants are skipped.
+ *   stats[s * 22 + 0] readings with a finite value, [1] sum (value - shift7[s]), [2] sum (value - shift7[s])^2,
+ *   [3 .. 14] SensorStatus histogram, [15 .. 21] SensorFault histogram        (s = sensor 0..6)
+ *   scratch: wt_sensor_stats_scratch_doubles() doubles.  Deterministic (fixed summation order). */
+int wt_sensor_stats_size(void);
+int wt_sensor_stats_scratch_doubles(void);
+int wt_sensor_stats(int P, const double *out_value_dev, const int32_t *out_status_dev,
+                    const int32_t *out_fault_dev, const uint32_t *plant_status_dev, const double *shift7_dev,
+                    double *stats_dev, double *scratch_dev, int accumulate, void *stream);
+
+/* Scheduling helper: order_dev <- plants sorted by cost_dev (the per-plant work wt_advance reports), most expensive
+ * first (counting sort; bins_dev: 1024 int32 of device scratch).  Results of wt_advance never depend on the order. */
+int wt_cost_order(int P, const int32_t *cost_dev, int32_t *order_dev, int32_t *bins_dev, void *stream);
 
 /* Measured-peak helper for the roofline denominator: runs a dependent-chain-free DFMA loop on
  * every SM and returns the sustained FP64 rate in TFLOP/s (2 flops per DFMA). */

@@ -80,8 +80,10 @@ def lib():
         L.wt_oracle_calc_ph_batch.argtypes = [C.c_int, dp, dp, dp, dp, dp, ip, ip, C.c_int]
         L.wt_oracle_calc_ph_batch.restype = None
         L.wt_oracle_suite_bytes.restype = C.c_int
-        L.wt_oracle_sensors_init.argtypes = [C.c_int, C.c_double, dp, dp, dp, C.c_void_p]
+        L.wt_oracle_sensors_init.argtypes = [C.c_int, C.c_double, dp, dp, dp, C.c_void_p, C.c_int, C.c_int]
         L.wt_oracle_sensors_init.restype = None
+        L.wt_oracle_sensors_reset.argtypes = [C.c_int, C.c_int, C.c_double, C.c_void_p]
+        L.wt_oracle_sensors_reset.restype = None
         L.wt_oracle_sensors_calibrate.argtypes = [C.c_int, C.c_int, C.c_double, dp, C.c_void_p]
         L.wt_oracle_sensors_calibrate.restype = None
         L.wt_oracle_sensors_read.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_uint, C.c_double, C.c_double, dp, dp,
@@ -178,19 +180,24 @@ STANDARD_SUITE6 = np.array([0.5, 0.0, 0.9, 0.1, 30.0, (250 / 1000.0) / (500 / 10
 class SensorSuiteOracle:
     """P instances of the reference sensor suite (CPU port), calibrated at t0 as __main__.initialize_sensors does."""
 
-    def __init__(self, cfg_flow, cfg_cl, cfg_T, t0, seed=0, plant0=0, suite6=None, nthreads=1):
+    def __init__(self, cfg_flow, cfg_cl, cfg_T, t0, seed=0, plant0=0, suite6=None, nthreads=1, temp_kind=0, flow_kind=0):
         self.P = len(cfg_flow)
         self.t0, self.seed, self.plant0, self.nthreads = float(t0), int(seed), int(plant0), nthreads
         self.suite6 = np.ascontiguousarray(STANDARD_SUITE6 if suite6 is None else suite6, dtype=np.float64)
         self._buf = np.zeros(self.P * lib().wt_oracle_suite_bytes(), dtype=np.uint8)
         f, c, t = (np.ascontiguousarray(a, dtype=np.float64) for a in (cfg_flow, cfg_cl, cfg_T))
-        lib().wt_oracle_sensors_init(self.P, self.t0, _dp(f), _dp(c), _dp(t), self._buf.ctypes.data)
+        lib().wt_oracle_sensors_init(self.P, self.t0, _dp(f), _dp(c), _dp(t), self._buf.ctypes.data, int(temp_kind),
+                                     int(flow_kind))
         self.k = 0
         self.t_prev = self.t0
 
     def calibrate(self, sensor: int, reference, t: float):
         ref = np.ascontiguousarray(np.broadcast_to(np.asarray(reference, dtype=np.float64), (self.P,)))
         lib().wt_oracle_sensors_calibrate(self.P, sensor, float(t), _dp(ref), self._buf.ctypes.data)
+
+    def reset(self, sensor: int, t: float):
+        """BaseSensor.reset() with the simulated time t in place of time.monotonic()."""
+        lib().wt_oracle_sensors_reset(self.P, sensor, float(t), self._buf.ctypes.data)
 
     FIELDS = ("current_value", "calibration_offset", "last_calibration_time", "power_on_time", "membrane_fouling",
               "reference_contamination", "days_since_cleaning", "membrane_age_days", "reagent_potency",

@@ -5,7 +5,8 @@
  * Follows the reference class by class, one plant at a time, plain structs:
  *   BaseSensor.read / calibrate / _check_for_faults / _apply_installation_effects   base_sensor.py:357-755
  *   SampleLine.transport_sample                                                     base_sensor.py:177-216
- *   pHSensor, ChlorineSensor (amperometric, DPD), TemperatureSensor (RTD), FlowSensor (magnetic)
+ *   pHSensor, ChlorineSensor (amperometric, DPD), TemperatureSensor (RTD PT100 / PT1000, thermocouple K / J),
+ *   FlowSensor (magnetic, turbine), BaseSensor.reset
  *   create_realistic_sensor_suite + __main__.initialize_sensors                     sensors/__init__.py:41-120, __main__.py:84-118
  *
  * Parity pin: the reference seeds each sensor from secrets.randbits (base_sensor.py:331), so no
@@ -38,7 +39,13 @@ typedef struct {
   double membrane_fouling, reference_contamination, days_since_cleaning; /* pH */
   double membrane_age_days;                                             /* amperometric */
   double reagent_potency, light_exposure_hours, reagent_age_days;       /* DPD */
-  double electrode_fouling, full_scale;                                 /* flow */
+  double electrode_fouling, full_scale;                                 /* flow (magnetic) */
+  double bearing_wear_days;                                             /* flow (turbine), flow_sensor.py:90-92 */
+  double cold_junction_drift;                                           /* temperature (thermocouple), temperature_sensor.py:96-99 */
+  int variant;                       /* temperature: 0 RTD_PT100, 1 RTD_PT1000, 2 THERMOCOUPLE_K, 3 THERMOCOUPLE_J; flow: 0 MAGNETIC, 1 TURBINE */
+  int hist_count;                    /* len(reading_history) */
+  int has_cal_record;                /* bool(calibration_history): reset() clears the list, calibrate() appends */
+  double slope_percentage;           /* pH: only refreshed by a read while a calibration record exists (ph_sensor.py:274-279) */
 } sensor_t;
 
 typedef struct {
@@ -89,6 +96,7 @@ static void base_init(sensor_t *s, int kind, int zone_first, int line, double lo
   s->status = SS_NORMAL; s->fault = F_NONE;
   s->supply_voltage = 24.0;               /* :309 */
   s->last_value = NAN;
+  s->slope_percentage = 100.0;            /* ph_sensor.py:118 */
 }
 static void calibrate(sensor_t *s, double reference, double t) { /* base_sensor.py:701-755 */
   double offset = reference - s->current_value;
@@ -98,8 +106,9 @@ static void calibrate(sensor_t *s, double reference, double t) { /* base_sensor.
   s->fault = F_NONE;
   s->power_on_time = t;
   s->cal_timestamp = t;
+  s->has_cal_record = 1;
 }
-static void suite_init(suite_t *u, double t0, double cfg_flow, double cfg_cl, double cfg_T) {
+static void suite_init(suite_t *u, double t0, double cfg_flow, double cfg_cl, double cfg_T, int temp_kind, int flow_kind) {
   memset(u, 0, sizeof(*u));
   /* sensors/__init__.py:69-118 */
   base_init(&u->s[0], K_PH, 1, 0, 0.0, 14.0, 0.01, 0.01 / 24.0, 1800.0, 0.5, 24.0);   u->s[0].current_value = 7.0;
@@ -108,10 +117,15 @@ static void suite_init(suite_t *u, double t0, double cfg_flow, double cfg_cl, do
   base_init(&u->s[3], K_CL_DPD, 0, -1, 0.0, 10.0, 0.02, 0.02 / 24.0, 60.0, 1.0, 24.0);  u->s[3].current_value = 0.0;
   u->s[3].reagent_potency = 1.0;
   double FS = cfg_flow * 2.0;
-  base_init(&u->s[4], K_FLOW, 1, -1, 0.0, FS, 0.005 * FS, 0.0, 10.0, FS, 8760.0);       u->s[4].current_value = 0.0;
+  /* flow_sensor.py:66-69: turbine precision 1 % of full scale, magnetic 0.5 % */
+  base_init(&u->s[4], K_FLOW, 1, -1, 0.0, FS, (flow_kind == 1 ? 0.01 : 0.005) * FS, 0.0, 10.0, FS, 8760.0); u->s[4].current_value = 0.0;
   u->s[4].full_scale = FS;
-  base_init(&u->s[5], K_TEMP, 1, 0, -10.0, 110.0, 0.1, 0.0, 30.0, 10.0, 8760.0);        u->s[5].current_value = 20.0;
-  base_init(&u->s[6], K_TEMP, 0, 1, -10.0, 110.0, 0.1, 0.0, 30.0, 10.0, 8760.0);        u->s[6].current_value = 20.0;
+  u->s[4].variant = flow_kind;
+  /* temperature_sensor.py:65-68: RTD precision 0.1 C, thermocouple 0.5 C */
+  const double tprec = temp_kind >= 2 ? 0.5 : 0.1;
+  base_init(&u->s[5], K_TEMP, 1, 0, -10.0, 110.0, tprec, 0.0, 30.0, 10.0, 8760.0);      u->s[5].current_value = 20.0;
+  base_init(&u->s[6], K_TEMP, 0, 1, -10.0, 110.0, tprec, 0.0, 30.0, 10.0, 8760.0);      u->s[6].current_value = 20.0;
+  u->s[5].variant = u->s[6].variant = temp_kind;
   /* __main__.py:96-105 */
   calibrate(&u->s[0], 7.0, t0);
   calibrate(&u->s[1], 7.0, t0);
@@ -162,7 +176,8 @@ static reading_t base_read(sensor_t *s, suite_t *u, const rng_t *g, const double
     s->last_value = NAN;
     return r;
   }
-  int cal_expired = ((t - s->cal_timestamp) / 3600.0) > s->validity_hours;   /* :598-600 */
+  /* :598-600, _check_calibration_valid :432-436: no record -> not valid */
+  int cal_expired = !s->has_cal_record || ((t - s->cal_timestamp) / 3600.0) > s->validity_hours;
   if (cal_expired) s->status = SS_CAL_EXPIRED;
   if (s->line >= 0) true_value = transport_sample(&u->line[s->line], true_value, t, inst[5]);   /* :603-614 */
   double drift_hours = (t - s->last_calibration_time) / 3600.0;
@@ -259,11 +274,14 @@ static reading_t sensor_read(sensor_t *s, suite_t *u, const rng_t *g, const doub
     }
     double electrical_noise = n0 * (0.002 * (1.0 + 0.1 * fabs(r.value - 7.0)));
     double junction_noise = n1 * (0.005 * (1.0 + s->reference_contamination));
-    double days = (t - s->cal_timestamp) / 86400.0;
-    double slope_percentage = fmax(90.0, 100.0 - 0.001 * days);
+    double days = 0.0;                                                                    /* :274-279 */
+    if (s->has_cal_record) {
+      days = (t - s->cal_timestamp) / 86400.0;
+      s->slope_percentage = fmax(90.0, 100.0 - 0.001 * days);
+    }
     double slope_error = 0.0;
     if (!(4.0 < r.value && r.value < 7.0))
-      slope_error = fmin(fabs(r.value - 4.0), fabs(r.value - 7.0)) * (100.0 - slope_percentage) / 100.0;
+      slope_error = fmin(fabs(r.value - 4.0), fabs(r.value - 7.0)) * (100.0 - s->slope_percentage) / 100.0;
     double fouling_offset = s->membrane_fouling * 0.2;
     double f0, f1;
     normal2(g, 3, &f0, &f1);
@@ -298,9 +316,17 @@ static reading_t sensor_read(sensor_t *s, suite_t *u, const rng_t *g, const doub
     }
     final_value = clip(r.value * s->reagent_potency * 0.95 + n0 * 0.005, s->min_value, s->max_value);
   } else if (s->kind == K_FLOW) {                                                         /* flow_sensor.py:125-219 */
-    if (have_prev) s->electrode_fouling += 0.001 * (dt / 86400.0);
-    double fouling_factor = fmax(0.9, 1.0 - 0.005 * s->electrode_fouling);
-    final_value = r.value * fouling_factor * 1.0 + n0 * (0.001 * s->full_scale);
+    if (s->variant == 1) {                                                                /* turbine :138-141, 180-199 */
+      if (have_prev) s->bearing_wear_days += (dt / 86400.0) * (1.0 + inst[3] * 5.0);
+      double friction_increase = 1.0 + 0.01 * (s->bearing_wear_days / 365.0);
+      double friction_loss = (0.01 * friction_increase) * s->full_scale;
+      double effective_value = r.value < friction_loss ? 0.0 : r.value - friction_loss;
+      final_value = effective_value + n0 * (inst[3] * 0.01 * s->full_scale);
+    } else {
+      if (have_prev) s->electrode_fouling += 0.001 * (dt / 86400.0);
+      double fouling_factor = fmax(0.9, 1.0 - 0.005 * s->electrode_fouling);
+      final_value = r.value * fouling_factor * 1.0 + n0 * (0.001 * s->full_scale);
+    }
     if (inst[1] > 0.0) {
       double ub, ub2;
       uniform2(g, 7, &ub, &ub2);
@@ -309,12 +335,21 @@ static reading_t sensor_read(sensor_t *s, suite_t *u, const rng_t *g, const doub
     if (final_value < 0.01 * s->full_scale) final_value = 0.0;
     final_value = clip(final_value, 0.0, s->max_value);
   } else {                                                                                /* temperature_sensor.py:110-171 */
-    double R_true = 100.0 * (1.0 + 0.00385 * r.value);
-    double R_measured = R_true + 2.0 * 0.5;
-    double I_A = 1.0 / 1000.0;
-    double self_heating_error = 0.001 * ((I_A * I_A) * R_measured * 1000.0);
-    double T_measured = (R_measured / 100.0 - 1.0) / 0.00385;
-    final_value = T_measured + self_heating_error + n0 * 0.001;
+    if (s->variant >= 2) {                                                                /* thermocouple :173-194 */
+      double V_seebeck = 40.0 * (r.value - 25.0);
+      s->cold_junction_drift += n0 * 0.01;
+      double emf_noise = n1 * 0.5;
+      double V_total = V_seebeck + emf_noise;
+      final_value = (V_total / 40.0) + 25.0 + s->cold_junction_drift;
+    } else {                                                                              /* RTD :150-171 */
+      double R0 = s->variant == 1 ? 1000.0 : 100.0;
+      double R_true = R0 * (1.0 + 0.00385 * r.value);
+      double R_measured = R_true + 2.0 * 0.5;
+      double I_A = 1.0 / 1000.0;
+      double self_heating_error = 0.001 * ((I_A * I_A) * R_measured * 1000.0);
+      double T_measured = (R_measured / R0 - 1.0) / 0.00385;
+      final_value = T_measured + self_heating_error + n0 * 0.001;
+    }
     double stem_error = 0.01 * (r.value - inst[4]);
     final_value += stem_error;
     final_value = clip(final_value, s->min_value, s->max_value);
@@ -328,8 +363,25 @@ static reading_t sensor_read(sensor_t *s, suite_t *u, const rng_t *g, const doub
 
 /* ---- batched drivers (AoS per plant): y [P][3n] species-major ---- */
 void wt_oracle_sensors_init(int P, double t0, const double *cfg_flow, const double *cfg_cl, const double *cfg_T,
-                            suite_t *st) {
-  for (int p = 0; p < P; ++p) suite_init(&st[p], t0, cfg_flow[p], cfg_cl[p], cfg_T[p]);
+                            suite_t *st, int temp_kind, int flow_kind) {
+  for (int p = 0; p < P; ++p) suite_init(&st[p], t0, cfg_flow[p], cfg_cl[p], cfg_T[p], temp_kind, flow_kind);
+}
+
+/* BaseSensor.reset (base_sensor.py:858-878) with the simulated time t in place of time.monotonic() */
+void wt_oracle_sensors_reset(int P, int sensor, double t, suite_t *st) {
+  for (int p = 0; p < P; ++p) {
+    sensor_t *s = &st[p].s[sensor];
+    s->current_value = (s->min_value + s->max_value) / 2.0;
+    s->calibration_offset = 0.0;
+    s->hist_count = 0;            /* reading_history.clear() */
+    s->last_value = NAN;
+    s->status = SS_NORMAL;
+    s->fault = F_NONE;
+    s->last_calibration_time = t;
+    s->power_on_time = t;
+    s->has_cal_record = 0;        /* calibration_history.clear(): every read reports CALIBRATION_EXPIRED until calibrate() */
+    if (s->line >= 0) { st[p].line[s->line].head = 0; st[p].line[s->line].count = 0; }  /* delay_buffer.clear() */
+  }
 }
 
 void wt_oracle_sensors_calibrate(int P, int sensor, double t, const double *ref, suite_t *st) {
@@ -426,8 +478,10 @@ static void *worker(void *arg) {
     unsigned long long gid = (unsigned long long)(j->plant0 + p);
     for (int s = 0; s < NSENS; ++s) {
       rng_t g = {(uint32_t)gid, j->k ^ ((uint32_t)(gid >> 32) << 24), (uint32_t)s, (uint32_t)j->seed, (uint32_t)(j->seed >> 32)};
-      reading_t r = sensor_read(&j->st[p].s[s], &j->st[p], &g, j->inst, yy, yy + j->n, yy + 2 * j->n, j->n, j->flow[p],
-                                j->t, j->t_prev, j->k > 0);
+      sensor_t *ss = &j->st[p].s[s];
+      reading_t r = sensor_read(ss, &j->st[p], &g, j->inst, yy, yy + j->n, yy + 2 * j->n, j->n, j->flow[p],
+                                j->t, j->t_prev, ss->hist_count > 0);
+      ss->hist_count++;   /* every read appends to reading_history, also the warm-up / power-fault early returns */
       double *o = j->out + ((size_t)p * NSENS + s) * 5;
       o[0] = r.value; o[1] = r.raw_value; o[2] = r.noise; o[3] = r.drift; o[4] = r.uncertainty;
       j->status[(size_t)p * NSENS + s] = r.status;

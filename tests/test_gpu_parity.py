@@ -299,6 +299,37 @@ def test_stats_kernel_matches_numpy_and_is_deterministic():
     assert np.all(r["var_pH"] >= 0) and np.all((r["mean_temperature"] > 0) & (r["mean_temperature"] < 45))
 
 
+def test_sensor_statistics_kernel_matches_numpy():
+    """The sensor half of the all-reduce payload (valid count, sum, sum of squares, status and fault histograms per
+    sensor) against its numpy restatement, on a stepped ensemble with warm and warming-up sensors."""
+    from ics_wt_physicsengine_b200.partition import EnsembleStatistics, StatsSpec, finalize_stats, stats_size
+    from ics_wt_physicsengine_b200.sensors import SENSOR_NAMES, create_realistic_sensor_suite
+    from tests.test_partition_gloo import local_stats_numpy, sensor_stats_numpy
+    P = 100003
+    e = ens.config5(P, 10)
+    eng = PlantEnsemble(e)
+    suite = create_realistic_sensor_suite(eng, seed=3)
+    suite.initialize(-400.0)   # warm: chlorine, flow, temperature; the pH pair still warms up
+    eng._status[5:500:7] = 2   # some halted plants: excluded
+    for k in range(40):
+        eng.step(1.0, e.bnd)
+        r = suite.read(eng.state, float(k))
+    st = EnsembleStatistics(eng, StatsSpec(), suite)
+    a = st.local().cpu().numpy().copy()
+    assert a.size == stats_size(10, sensors=True) and np.array_equal(a, st.local().cpu().numpy())
+    ps = eng.status.cpu().numpy().astype(np.uint32)
+    val = np.stack([r[k].value.cpu().numpy() for k in SENSOR_NAMES])
+    sst = np.stack([r[k].status.cpu().numpy() for k in SENSOR_NAMES])
+    sft = np.stack([r[k].fault.cpu().numpy() for k in SENSOR_NAMES])
+    want = np.concatenate([local_stats_numpy(eng.state_numpy(), ps, 10, StatsSpec()), sensor_stats_numpy(val, sst, sft, ps, StatsSpec())])
+    sb, wb = a[68:].reshape(7, 22), want[68:].reshape(7, 22)
+    assert np.array_equal(sb[:, 0], wb[:, 0]) and np.array_equal(sb[:, 3:], wb[:, 3:])   # counts and histograms: exact
+    assert np.allclose(sb[:, 1:3], wb[:, 1:3], rtol=1e-11, atol=1e-7)
+    f = finalize_stats(a, 10, StatsSpec())
+    assert f["sensor_valid_fraction"][0] == 0.0 and f["sensor_valid_fraction"][2] > 0.95   # pH warming up, chlorine reads
+    assert f["sensor_status_hist"][0, 2] > 0.99                                            # WARMING_UP (a few power faults)
+
+
 def test_sorted_scheduling_does_not_change_results():
     """sort_every only permutes which plants share a warp / start first: bitwise identical results."""
     e = ens.config5(30011, 10)
@@ -311,6 +342,16 @@ def test_sorted_scheduling_does_not_change_results():
     assert torch.equal(a.state.temperature, b.state.temperature) and torch.equal(a.status, b.status)
     assert torch.equal(a.counters, b.counters) and torch.equal(a.state.time, b.state.time)
     assert b._order is not None and sorted(b._order.cpu().tolist()) == list(range(30011))
+    # the counting sort itself: a permutation, most expensive plants first
+    import ctypes as C
+    from ics_wt_physicsengine_b200 import _lib
+    order = torch.empty(30011, dtype=torch.int32, device=b.device)
+    pp = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(_lib.lib().wt_cost_order(30011, pp(b._cost), pp(order), pp(b._bins), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "wt_cost_order")
+    o = order.cpu().numpy().astype(np.int64)
+    assert sorted(o.tolist()) == list(range(30011))
+    assert np.all(np.diff(np.minimum(b._cost.cpu().numpy()[o], 1023)) <= 0)
 
 
 @pytest.mark.parametrize("P,bcast", [(33, False), (70001, False), (70001, True), (131072 + 77, False)])
@@ -365,6 +406,7 @@ def test_pipelined_shard_equals_one_ensemble():
         sh.step(1.0, read_time=float(k))
     v = sh.stats().clone()
     torch.cuda.synchronize()
+    st = EnsembleStatistics(one, None, suite)
     got = np.concatenate([x.state_numpy() for x in sh.engines])
     assert np.array_equal(got, one.state_numpy())
     assert np.array_equal(np.concatenate([x.status.cpu().numpy() for x in sh.engines]), one.status.cpu().numpy())
@@ -373,3 +415,33 @@ def test_pipelined_shard_equals_one_ensemble():
     assert torch.equal(torch.cat([s._out_status for s in sh.suites], dim=1), suite._out_status)
     w = st.local()
     assert torch.allclose(v, w, rtol=1e-13, atol=1e-9)  # additive vector; only the summation order differs
+
+
+def test_captured_graph_replay_equals_eager_steps():
+    """One CUDA graph per rank for a block of steps (step + sensor read + cost order of every sub-ensemble + local
+    statistics): replays give bit-identical plant states, sensor readings and statistics to the same steps
+    launched eagerly."""
+    from ics_wt_physicsengine_b200.partition import PipelinedShard
+    P, n, G = 6007, 10, 4
+    e = ens.config5(P, n)
+    mk = lambda: PipelinedShard(e, parts=2, plant0=500, sensor_seed=11, max_attempts=CAP, sort_every=2)
+    a, b = mk(), mk()
+    for sh in (a, b):
+        sh.initialize_sensors(-100.0)
+    k = 0
+    for _ in range(2):          # warm-up, eager on both (a captured launch cannot set kernel attributes)
+        a.step(1.0, read_time=float(k)); b.step(1.0, read_time=float(k)); k += 1
+    b.capture(G, 1.0, t_next=float(k), with_stats=True)
+    for rep in range(3):
+        for _ in range(G):
+            a.step(1.0, read_time=float(k)); k += 1
+        va = a.stats().clone()
+        vb = b.replay().clone()
+        torch.cuda.synchronize()
+        for ea, eb in zip(a.engines, b.engines):
+            assert torch.equal(ea._y, eb._y) and torch.equal(ea._status, eb._status) and torch.equal(ea._time, eb._time)
+            assert torch.equal(ea._counters, eb._counters)
+        for sa, sb in zip(a.suites, b.suites):
+            assert torch.equal(torch.nan_to_num(sa._out, nan=-1.0), torch.nan_to_num(sb._out, nan=-1.0))
+            assert torch.equal(sa._out_status, sb._out_status) and sa.read_index == sb.read_index and sa.last_time == sb.last_time
+        assert torch.equal(va, vb), rep

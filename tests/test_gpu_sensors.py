@@ -280,3 +280,88 @@ def test_get_statistics_matches_the_oracle(golden_dir):
     assert float(s2["count"][0]) == 6 and float(s2["fault_rate"].min()) == 1.0 and bool(torch.isnan(s2["mean"]).all())
     f2 = suite2.get_statistics("flow_main", 100.0)                          # flow warms up in 10 s: finite values by now
     assert float(f2["count"][0]) == 8 and bool(torch.isfinite(f2["mean"]).any())
+
+
+def test_variants_and_reset_value_for_value_on_random_plants(oracle, golden_dir):
+    """Thermocouple temperature sensors, turbine flow meter, reset() + calibrate() of the flow meter, on 4,096
+    random config-5 plants over the golden schedule: every field equals the CPU port, which is pinned in
+    distribution against the unmodified reference on the same plants (tests/test_sensors_oracle.py)."""
+    from ics_wt_physicsengine_b200.sensors import FlowSensorType, TemperatureSensorType
+    g = np.load(os.path.join(golden_dir, "sensors_random_plants.npz"))
+    P, n, t0, t_first = 4096, 10, float(g["t0"]), float(g["t_first"])
+    e = ens.config5(int(g["n"]), n, seed=int(g["seed"])).slice(slice(0, P))
+    eng = PlantEnsemble(e)
+    suite = create_realistic_sensor_suite(eng, seed=777, temperature_sensor_type=TemperatureSensorType.THERMOCOUPLE_K,
+                                          flow_sensor_type=FlowSensorType.TURBINE)
+    suite.initialize(t0)
+    osu = oracle.SensorSuiteOracle(e.cfg[:, 3], e.cfg[:, 12], e.cfg[:, 13], t0, seed=777, nthreads=8, temp_kind=2, flow_kind=1)
+    y = eng.state_numpy()
+    flow = eng.state.flow_rate.cpu().numpy()
+    for k in range(int(g["checks"].max()) + 1):
+        t = t_first + k
+        if k == int(g["k_reset"]):
+            suite.reset("flow_main", t)
+            osu.reset(4, t)
+        if k == int(g["k_recal"]):
+            suite.calibrate("flow_main", e.cfg[:, 3], t)
+            osu.calibrate(4, e.cfg[:, 3], t)
+        out_g, st_g, ft_g = _gpu_read(suite, t)
+        out_o, st_o, ft_o = osu.read(y, flow, t, n)
+        assert np.array_equal(st_g.T, st_o) and np.array_equal(ft_g.T, ft_o), k
+        assert _close(np.transpose(out_g, (1, 0, 2)), out_o), k
+    # ... and directly against the reference's samples of the same plants, in distribution
+    ci = list(g["checks"]).index(130)
+    for s in (4, 5, 6):
+        a = g["var_values"][ci, s].astype(np.float64)
+        b = out_g[s, :, 0]
+        assert compare_distributions(a[np.isfinite(a)], b[np.isfinite(b)], ("var", s))
+
+
+def test_standard_suite_on_random_plants_against_reference_samples(golden_dir):
+    """The factory's suite on 10,240 random config-5 plants against the unmodified reference on the same plants."""
+    g = np.load(os.path.join(golden_dir, "sensors_random_plants.npz"))
+    P, n = int(g["n"]), 10
+    e = ens.config5(P, n, seed=int(g["seed"]))
+    eng = PlantEnsemble(e)
+    suite = create_realistic_sensor_suite(eng, seed=31)
+    suite.initialize(float(g["t0"]))
+    checks, ci, n_tested = list(g["checks"]), 0, 0
+    for k in range(max(checks) + 1):
+        r = suite.read(None, float(g["t_first"]) + k)
+        if ci < len(checks) and k == checks[ci]:
+            for s, name in enumerate(SENSOR_NAMES):
+                a, ar = g["std_values"][ci, s].astype(np.float64), g["std_raw"][ci, s].astype(np.float64)
+                b, br = r[name].value.cpu().numpy(), r[name].raw_value.cpu().numpy()
+                pa, pb = np.isnan(a).mean(), np.isnan(b).mean()
+                assert abs(pa - pb) < 5 * np.sqrt(max(pa * (1 - pa), 1e-4) * 2 / P) + 1e-3, (k, name, pa, pb)
+                ha = np.bincount(g["std_status"][ci, s].astype(int), minlength=12) / P
+                hb = np.bincount(r[name].status.cpu().numpy(), minlength=12) / P
+                assert np.abs(ha - hb).max() < 0.02, (k, name)
+                ma, mb = np.isfinite(a), np.isfinite(b)
+                if ma.sum() >= 500:
+                    n_tested += bool(compare_distributions(a[ma], b[mb], (k, name)))
+                    compare_distributions((a - ar)[ma], (b - br)[mb], (k, name, "value - raw"))
+            ci += 1
+    assert n_tested >= 20
+
+
+def test_clocked_reads_equal_host_timed_reads():
+    """read_clocked() (time, previous time and read index from the device clock; what a CUDA graph replays) gives
+    the same readings as read(state, t) with host scalars."""
+    P, n, t0, dt = 768, 10, 10.0, 0.5
+    e = ens.config2(P, n, seed=8)
+    a, b = PlantEnsemble(e), PlantEnsemble(e)
+    sa, sb = create_realistic_sensor_suite(a, seed=9), create_realistic_sensor_suite(b, seed=9)
+    sa.initialize(t0); sb.initialize(t0)
+    for k in range(5):
+        sa.read(None, t0 + k * dt); sb.read(None, t0 + k * dt)
+    sb.start_clock(t0 + 5 * dt, dt)
+    for k in range(5, 80):
+        sa.read(None, t0 + k * dt)
+        sb.read_clocked()
+    sb.account_reads(75)
+    assert sb.read_index == sa.read_index and sb.last_time == sa.last_time
+    assert torch.equal(torch.nan_to_num(sa._out, nan=-1.0), torch.nan_to_num(sb._out, nan=-1.0))
+    assert torch.equal(sa._out_status, sb._out_status) and torch.equal(sa._sens_i, sb._sens_i)
+    sa.read(None, t0 + 80 * dt); sb.read(None, t0 + 80 * dt)   # and host-timed reads continue from there
+    assert torch.equal(torch.nan_to_num(sa._out, nan=-1.0), torch.nan_to_num(sb._out, nan=-1.0))

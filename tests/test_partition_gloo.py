@@ -30,6 +30,21 @@ def local_stats_numpy(y_pn, status, n, spec: StatsSpec) -> np.ndarray:
     return v
 
 
+def sensor_stats_numpy(value_7p, status_7p, fault_7p, plant_status, spec: StatsSpec) -> np.ndarray:
+    """Numpy restatement of the wt_sensor_stats layout (include/wt_b200.h): per sensor valid count, shifted sum,
+    shifted sum of squares over the finite readings, SensorStatus (12) and SensorFault (7) histograms; live plants."""
+    live = (plant_status & (2 | 128)) == 0
+    out = np.zeros((7, 22))
+    for s in range(7):
+        v = value_7p[s][live]
+        ok = np.isfinite(v)
+        d = v[ok] - spec.sensor_shifts[s]
+        out[s, 0], out[s, 1], out[s, 2] = ok.sum(), d.sum(), (d * d).sum()
+        out[s, 3:15] = np.bincount(status_7p[s][live], minlength=12)[:12]
+        out[s, 15:22] = np.bincount(fault_7p[s][live], minlength=7)[:7]
+    return out.reshape(-1)
+
+
 def test_shard_bounds_cover_the_ensemble_exactly():
     for total in (1, 7, 64, 1000, 1048576):
         for world in (1, 2, 3, 4, 8):
@@ -47,6 +62,14 @@ def test_shard_bounds_cover_the_ensemble_exactly():
         shard_bounds(10, 2, 2)
 
 
+def _fake_readings(P):
+    """Deterministic stand-in for the last suite read of P plants (values with NaNs, status and fault codes)."""
+    rng = np.random.default_rng(5)
+    val = rng.normal([[7.2], [7.4], [1.9], [1.5], [11.0], [21.0], [22.0]], 0.3, size=(7, P))
+    val[rng.random((7, P)) < 0.1] = np.nan
+    return val, rng.integers(0, 12, size=(7, P)), rng.integers(0, 7, size=(7, P))
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -58,7 +81,10 @@ def _worker(rank, world, port, q):
     status = np.zeros(e.n_plants, dtype=np.uint32)
     if rank == 0:
         status[3] = 2    # a halted plant is excluded from the moments and counted as halted
-    v = torch.from_numpy(local_stats_numpy(y, status, 10, spec))
+    val, st, ft = _fake_readings(full.n_plants)
+    lo, hi = shard_bounds(full.n_plants, rank, world)
+    v = torch.from_numpy(np.concatenate([local_stats_numpy(y, status, 10, spec),
+                                         sensor_stats_numpy(val[:, lo:hi], st[:, lo:hi], ft[:, lo:hi], status, spec)]))
     dist.all_reduce(v, op=dist.ReduceOp.SUM)
     if rank == 0:
         q.put(v.numpy().copy())
@@ -83,9 +109,16 @@ def test_gloo_allreduce_of_statistics_world2():
     status = np.zeros(257, dtype=np.uint32)
     status[3] = 2
     spec = StatsSpec()
-    want = local_stats_numpy(y, status, 10, spec)
+    val, st, ft = _fake_readings(257)
+    want = np.concatenate([local_stats_numpy(y, status, 10, spec), sensor_stats_numpy(val, st, ft, status, spec)])
+    assert got.size == stats_size(10, sensors=True)
     assert np.allclose(got, want, rtol=1e-13, atol=1e-9)
     r = finalize_stats(got, 10, spec)
+    lv = status == 0
+    assert np.array_equal(r["sensor_valid_count"], np.isfinite(val[:, lv]).sum(axis=1))
+    assert np.allclose(r["sensor_mean"], np.nanmean(val[:, lv], axis=1), rtol=1e-12)
+    assert np.allclose(r["sensor_var"], np.nanvar(val[:, lv], axis=1), rtol=1e-9)
+    assert np.allclose(r["sensor_status_hist"].sum(axis=1), 1.0) and np.allclose(r["sensor_fault_hist"].sum(axis=1), 1.0)
     live = status == 0
     assert r["live"] == 256 and r["halted"] == 1
     assert np.allclose(r["mean_pH"], full.pH0[live].mean(axis=0), rtol=1e-12)

@@ -146,3 +146,68 @@ def test_maintenance_operations_match_the_reference(oracle, golden_dir):
             if kind_has or f in ("status", "fault"):
                 assert got[f][0] == after[i], (si, op, f, got[f][0], after[i])
     assert n_raise == 120  # replace_membrane on the DPD sensor and replace_reagent on the amperometric one
+
+
+# ---- random config-5 plants, both variant sets, reset() (tests/golden/sensors_random_plants.npz) -----------------
+@pytest.fixture(scope="module")
+def golden_random(golden_dir):
+    return np.load(os.path.join(golden_dir, "sensors_random_plants.npz"))
+
+
+def _oracle_random_run(oracle, g, variants):
+    from ics_wt_physicsengine_b200 import ensembles
+    from ics_wt_physicsengine_b200.ensembles import CFG_FIELDS
+    N, checks = int(g["n"]), list(g["checks"])
+    e = ensembles.config5(N, 10, seed=int(g["seed"]))
+    col = lambda k: np.ascontiguousarray(e.cfg[:, CFG_FIELDS.index(k)])
+    suite = oracle.SensorSuiteOracle(col("flow_rate"), col("initial_chlorine"), col("temperature"), float(g["t0"]), seed=777,
+                                     nthreads=8, temp_kind=2 if variants else 0, flow_kind=1 if variants else 0)
+    y = np.concatenate([e.pH0, e.Cl0, e.T0], axis=1)
+    vals = np.zeros((len(checks), 7, N)); raw = np.zeros_like(vals)
+    stat = np.zeros((len(checks), 7, N), dtype=np.int32); flt = np.zeros_like(stat)
+    ci = 0
+    for k in range(max(checks) + 1):
+        t = float(g["t_first"]) + k
+        if variants and k == int(g["k_reset"]):
+            suite.reset(4, t)
+        if variants and k == int(g["k_recal"]):
+            suite.calibrate(4, col("flow_rate"), t)
+        out, st, ft = suite.read(y, col("flow_rate"), t, 10)
+        if ci < len(checks) and k == checks[ci]:
+            vals[ci], raw[ci], stat[ci], flt[ci] = out[:, :, 0].T, out[:, :, 1].T, st.T, ft.T
+            ci += 1
+    return vals, raw, stat, flt
+
+
+@pytest.mark.parametrize("tag", ["std", "var"])
+def test_random_plants_match_the_reference_in_distribution(oracle, golden_random, tag):
+    """10,240 RANDOM config-5 plants (own full scale, calibration references, temperatures, zone profiles): the port
+    against the unmodified reference, for the factory's suite ("std") and for thermocouple + turbine sensors with a
+    reset() / calibrate() of the flow meter on the way ("var")."""
+    g = golden_random
+    vals, raw, stat, flt = _oracle_random_run(oracle, g, tag == "var")
+    gv, gr, gs, gf = g[f"{tag}_values"].astype(np.float64), g[f"{tag}_raw"].astype(np.float64), g[f"{tag}_status"], g[f"{tag}_fault"]
+    N = gv.shape[2]
+    n_tested = 0
+    for ci, k in enumerate(g["checks"]):
+        for s in range(7):
+            pa, pb = np.isnan(gv[ci, s]).mean(), np.isnan(vals[ci, s]).mean()
+            se = np.sqrt(max(pa * (1 - pa), 1e-4) * (2.0 / N))
+            assert abs(pa - pb) < 5 * se + 1e-3, (tag, int(k), s, pa, pb)
+            ha = np.bincount(gs[ci, s].astype(int), minlength=12) / N
+            hb = np.bincount(stat[ci, s], minlength=12) / N
+            assert np.abs(ha - hb).max() < 0.02, (tag, int(k), s, ha, hb)
+            fa = np.bincount(gf[ci, s].astype(int), minlength=7) / N
+            fb = np.bincount(flt[ci, s], minlength=7) / N
+            assert np.abs(fa - fb).max() < 0.02, (tag, int(k), s, fa, fb)
+            ma, mb = np.isfinite(gv[ci, s]), np.isfinite(vals[ci, s])
+            if ma.sum() < 500:
+                continue
+            # same plant population on both sides: the value and the residual value - raw_value are comparable pooled
+            n_tested += bool(compare_distributions(gv[ci, s][ma], vals[ci, s][mb], (tag, int(k), s, "value")))
+            compare_distributions((gv[ci, s] - gr[ci, s])[ma], (vals[ci, s] - raw[ci, s])[mb], (tag, int(k), s, "value - raw"))
+    assert n_tested >= 20
+    if tag == "var":   # reset(): warming up, then CALIBRATION_EXPIRED (6) while the calibration history is empty
+        c = list(g["checks"])
+        assert (stat[c.index(45), 4] == 2).mean() > 0.97 and (stat[c.index(62), 4] == 2).mean() > 0.97
+        assert (stat[c.index(55), 4] == 6).mean() > 0.9 and (gs[c.index(55), 4] == 6).mean() > 0.9
