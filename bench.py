@@ -111,7 +111,7 @@ def run_reference(args, rank, world):
 
     cores = os.cpu_count() or 1
     sample = args.cpu_plants
-    e = ensembles.config5(TOTAL_PLANTS if sample > 65536 else 65536, N_ZONES).slice(slice(0, sample))
+    e = ensembles.config5(args.plants, N_ZONES).slice(slice(0, sample))   # the first plants of the GPU arm's ensemble
     par = wo.derive_params(e.cfg, N_ZONES)
     bnd = np.ascontiguousarray(e.bnd)
     y = np.concatenate([e.pH0, e.Cl0, e.T0], axis=1).copy()
@@ -125,8 +125,9 @@ def run_reference(args, rank, world):
         ya, ta = y[idx].copy(), t[idx].copy()
         st, _, _ = wo.step_batch(par[idx].copy(), bnd[idx].copy(), N_ZONES, ta, ya, dt=DT, nthreads=cores)
         y[idx], t[idx] = ya, ta
-        halted[idx[(st & wo.ST_HALT_MASK) != 0]] = True
-        return idx.size
+        bad = (st & wo.ST_HALT_MASK) != 0
+        halted[idx[bad]] = True
+        return int((~bad).sum())   # completed plant-steps only
 
     for _ in range(args.warmup):
         one_step()
@@ -162,10 +163,11 @@ def main():
     ap.add_argument("--cpu-plants", type=int, default=16384)
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fused", action="store_true", help="time one fused wt_advance(K) launch instead of K launches")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying one CUDA graph per block of steps")
     ap.add_argument("--sort-every", type=int, default=2, help="re-order plants by last-step work every k launches (scheduling only)")
     ap.add_argument("--no-sensors", action="store_true", help="physics only (BASELINE configs[1]-style step)")
-    ap.add_argument("--streams", type=int, default=4, help="independent sub-ensembles (CUDA streams) per GPU")
+    ap.add_argument("--streams", type=int, default=0, help="independent sub-ensembles (CUDA streams) per GPU; 0 = by shard size")
+    ap.add_argument("--stats-every", type=int, default=10)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -188,34 +190,50 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     P_total = args.plants
-    from ics_wt_physicsengine_b200.partition import shard_bounds
+    from ics_wt_physicsengine_b200.partition import PipelinedShard, shard_bounds
     lo, hi = shard_bounds(P_total, rank, world)
     full = ensembles.config5(P_total, N_ZONES)
     e = full.slice(slice(lo, hi))
     P = e.n_plants
-    from ics_wt_physicsengine_b200.partition import PipelinedShard
-    # the rank's shard as `--streams` independent sub-ensembles on their own CUDA streams (plants never
-    # interact): the drain of one launch is filled by the next launch of another sub-ensemble
-    shard = PipelinedShard(e, parts=args.streams, device=dev, plant0=lo,
-                           sensor_seed=None if (args.no_sensors or args.fused) else 20260004,
+    # the rank's shard as independent sub-ensembles on their own CUDA streams (plants never interact): the drain of one
+    # launch is filled by the next launch of another sub-ensemble.  No sub-ensemble below ~64k plants.
+    parts = args.streams if args.streams > 0 else max(1, min(4, P // 65536))
+    sensors_on = not args.no_sensors
+    shard = PipelinedShard(e, parts=parts, device=dev, plant0=lo, sensor_seed=20260004 if sensors_on else None,
                            max_attempts=args.max_attempts, sort_every=args.sort_every)
-    eng = shard.engines[0]
     fp64_peak = _lib.measure_fp64_peak() if rank == 0 else 0.0
-    if shard.suites is not None:
-        shard.initialize_sensors(0.0)
+    # Sensors: calibrated at t = -2000 s, then 100 reads of the initial state at t = -100 .. -1 s: when the timed region
+    # starts every sensor is past its warm-up (10 / 30 / 60 / 300 / 1800 s) and the four 100-slot delay rings per plant
+    # are full, i.e. the read kernel does its steady-state work (ring scans included).
     sim = {"k": 0}
+    if sensors_on:
+        shard.initialize_sensors(-2000.0)
+        for j in range(100):
+            for su, s in zip(shard.suites, shard.streams):
+                with torch.cuda.stream(s):
+                    su.read(None, float(j - 100))
+    block = max(1, args.stats_every)
 
-    def do_steps(k, timed=False):
-        if args.fused:
-            shard.advance(k, DT)
-            return
+    def eager_steps(k):
         for i in range(k):
-            shard.step(DT, read_time=float(sim["k"]))   # step + sensor read (__main__.py:403-410), per sub-ensemble stream
+            shard.step(DT, read_time=float(sim["k"]) if sensors_on else None)   # step + sensor read (__main__.py:403-410)
             sim["k"] += 1
-            if (i + 1) % 10 == 0:
-                shard.stats()   # wt_stats kernels + one NCCL sum all-reduce of the statistics vector
+            if sim["k"] % block == 0:
+                shard.stats()   # wt_stats + wt_sensor_stats kernels, one NCCL sum all-reduce
 
-    do_steps(args.warmup)
+    eager_steps(args.warmup)
+    use_graph = not args.no_graph and args.steps >= block
+    n_blocks = args.steps // block if use_graph else 0
+    rem = args.steps - n_blocks * block
+    if use_graph:
+        # align the block boundary with the statistics interval, then capture one block: `block` x (step, sensor read,
+        # cost order) of every sub-ensemble + the local statistics kernels = ONE launch from the host per block
+        while sim["k"] % block:
+            eager_steps(1)
+        shard.synchronize()
+        shard.capture(block, DT, t_next=float(sim["k"]), with_stats=True)
+        shard.replay()            # one untimed replay (graph upload)
+        sim["k"] += block
     shard.reset_counters()
     torch.cuda.synchronize()
     if world > 1:
@@ -226,9 +244,13 @@ def main():
     with ClockSampler(local_rank) as clk:
         torch.cuda.synchronize()
         ev0.record()
-        shard.fork()
-        do_steps(args.steps, timed=True)
-        shard.synchronize()
+        for _ in range(n_blocks):
+            shard.replay()        # + the NCCL all-reduce of the statistics vector
+            sim["k"] += block
+        if rem or not use_graph:
+            shard.fork()
+            eager_steps(rem if use_graph else args.steps)
+            shard.synchronize()
         ev1.record()
         torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
@@ -246,9 +268,10 @@ def main():
     timed_plant_steps = float(agg[8])
     halted_after = shard.halted()
     value = timed_plant_steps * N_ZONES / (ms * 1e-3)
+    stats_vec = shard._sum.cpu().numpy().copy()
 
-    # ---- the dominant kernel alone: the sub-ensembles' launches overlap on the device inside the timed region, so one
-    # launch is timed here with CUDA events on the stream it is launched on, streams joined between launches
+    # ---- the kernels alone: the sub-ensembles' launches overlap on the device inside the timed region, so single launches
+    # are timed here with CUDA events on the stream they are launched on, streams joined between launches
     # (3 more steps of every sub-ensemble, after the timed region; rank 0 only)
     def kernel_alone(rounds=3):
         shard.reset_counters()
@@ -274,7 +297,8 @@ def main():
         done_cal = float((shard.time_sum() - t0_sum) / DT)
         return step_t, sens_t, n_launch, done_cal, shard.counters_sum().to(torch.float64).cpu().numpy()
 
-    cal = kernel_alone() if (rank == 0 and not args.fused) else None
+    cal = kernel_alone() if rank == 0 else None
+    k2 = calc_ph_roofline(dev, fp64_peak) if rank == 0 else None
 
     # ---- e2e: the C-ABI host-buffer call (H2D + step + D2H inside the timed region) on EVERY rank's
     # shard at the same time; whole-job value = all plants / slowest rank
@@ -288,8 +312,9 @@ def main():
         dist.all_reduce(e2e_max, op=dist.ReduceOp.MAX)
     e2e = {"value": float(e2e_agg[0]) * N_ZONES * k_e2e / float(e2e_max[1]), "unit": UNIT,
            "h2d_bytes_per_step": int(e2e_agg[2]), "d2h_bytes_per_step": int(e2e_agg[3]), "steps": k_e2e,
+           "work": "physics step only (IntegratedCSTR.step of every plant); the sensor suite is not part of this call",
            "api": "wt_step_host (C ABI, pinned host buffers: H2D of state+boundary, step, D2H of state+time+flow+status per call, "
-                  "pipelined over column slabs on three streams; per-plant constants resident after the first call)", "n_gpus": world}
+                  "pipelined over >= 12 column slabs on three streams; per-plant constants resident after the first call)", "n_gpus": world}
 
     if rank != 0:
         if world > 1:
@@ -297,32 +322,49 @@ def main():
         return
 
     # Headline roofline: the whole job's algorithmic flops over the whole timed region (conservative: the region also
-    # holds the sensor and statistics kernels, and the sub-ensembles' launches overlap).  Beside it: the step kernel
-    # alone, one launch at a time, from the calibration steps above with their own path counters.
+    # holds the sensor and statistics kernels, and the sub-ensembles' launches overlap).  Beside it: the step kernels
+    # alone, one step at a time, from the calibration steps above with their own path counters.
     F = flops_alg(cnt_sum, timed_plant_steps, N_ZONES)
-    parts = len(shard.engines)
-    kernel_region_ms = ms
-    achieved_tf = F / world / (kernel_region_ms * 1e-3) / 1e12  # per GPU
-    alone = None
-    if cal is not None:
-        step_t, sens_t, n_launch, done_cal, cnt_cal = cal
-        f_cal = flops_alg(cnt_cal, done_cal, N_ZONES)
-        alone = {"ms_per_launch": step_t / n_launch, "plants_per_launch": P // parts, "launches_timed": n_launch,
-                 "achieved": f_cal / (step_t * 1e-3) / 1e12, "frac": f_cal / (step_t * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
-                 "sensor_kernel_ms_per_launch": sens_t / n_launch, "step_share_of_gpu_time": step_t / (step_t + sens_t),
-                 "basis": "CUDA events on the launching stream, launches serialised (3 extra steps after the timed region)"}
+    nparts = len(shard.engines)
+    achieved_tf = F / world / (ms * 1e-3) / 1e12  # per GPU
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_ach = bytes_alg(timed_plant_steps, N_ZONES) / world / (kernel_region_ms * 1e-3) / 1e9
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    alone = sensors_rf = None
+    if cal is not None:
+        step_t, sens_t, n_launch, done_cal, cnt_cal = cal
+        f_cal = flops_alg(cnt_cal, done_cal, N_ZONES)
+        ppl = P // nparts
+        alone = {"ms_per_step_launch_pair": step_t / n_launch, "plants_per_launch": ppl, "launches_timed": n_launch,
+                 "achieved": f_cal / (step_t * 1e-3) / 1e12, "frac": f_cal / (step_t * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
+                 "step_share_of_gpu_time": step_t / (step_t + sens_t),
+                 "basis": "CUDA events on the launching stream around wt_step_begin_kernel + wt_step_run_kernel, launches "
+                          "serialised (3 extra steps after the timed region)"}
+        if shard.suites is not None:
+            # K3: algorithmic bytes of one suite read per plant: 7 sensors x (10 state doubles r/w + 4 ints r/w
+            # + 5 outputs + 2 ints) + 4 delay-ring scans x 100 slots x 8 B + 4 ring appends x 16 B + 6 state doubles
+            b_read = 7 * (10 * 8 * 2 + 4 * 4 * 2 + 5 * 8 + 2 * 4) + 4 * 100 * 8 + 4 * 16 + 6 * 8
+            ach = b_read * ppl / (sens_t / n_launch * 1e-3) / 1e9
+            sensors_rf = {"kernel": "wt_sensors_read_kernel", "bound": "hbm", "ms_per_launch": sens_t / n_launch,
+                          "algorithmic_bytes_per_plant_read": b_read, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": ach / hbm_peak, "peak_source": hbm_src,
+                          "state": "all sensors warm, delay rings full (100 of 100 slots scanned per line)",
+                          "traffic": 5030.0 * ppl, "traffic_source": "ncu dram bytes per plant-read of the same launch shape (profiles/r2_sensor_kernel.txt)"}
+    hbm_ach = bytes_alg(timed_plant_steps, N_ZONES) / world / (ms * 1e-3) / 1e9
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:   # rank 0 at N=1 only
         cpu = cpu_baseline(args)
 
+    from ics_wt_physicsengine_b200.partition import StatsSpec, finalize_stats
+    fin = finalize_stats(stats_vec, N_ZONES, StatsSpec())
+    per_part_step = 2 + (2 if sensors_on else 0)                                  # begin, run, sensor read, clock tick
+    per_part_sort = 4 * (args.steps // max(1, args.sort_every)) if args.sort_every > 0 else 0   # memset-free: hist, scan, scatter (+memset node)
+    per_part_stats = (2 + (2 if sensors_on else 0) + 1) * (args.steps // block)   # wt_stats (2), wt_sensor_stats (2), row copy
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -330,38 +372,83 @@ def main():
         "config": {
             "workload": f"BASELINE configs[4] physics: {P_total} plants x {N_ZONES} zones (ensembles.config5 seed 20260004), "
                         f"IntegratedCSTR.step(dt=1s) + 7-sensor suite read per plant per step, sharded over {world} GPU(s)",
-            "launch_mode": "fused wt_advance(K)" if args.fused else "one wt_step launch per sub-ensemble per step",
+            "launch_mode": (f"one CUDA graph per rank per {block} steps (step begin + run kernels, sensor read, clock tick, cost "
+                            f"order of every sub-ensemble, local statistics), then one NCCL all-reduce") if use_graph
+                           else "every kernel launched from the host",
             "l2": "state+params per GPU >> 126 MB L2 at N<=4; inputs larger than L2 (no flush needed)",
-            "sensor_suite": shard.suites is not None, "sort_every": args.sort_every,
-            "sub_ensembles_per_gpu": len(shard.engines),
+            "sensor_suite": shard.suites is not None,
+            "sensor_state": "warm (calibrated at t=-2000 s), delay rings full" if sensors_on else None,
+            "sort_every": args.sort_every, "sub_ensembles_per_gpu": nparts,
             "max_attempts": args.max_attempts, "plants_halted_at_end_rank0": halted_after,
-            "stats_allreduce_every": 10,
+            "halted_fraction_rank0": halted_after / P,
+            "stats_allreduce_every": block, "stats_vector_doubles": int(stats_vec.size),
         },
         "roofline": {
             "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": achieved_tf / fp64_peak if fp64_peak else None,
-            # dram__bytes_read+write of one wt_step launch: 81.1 B per plant-zone-step measured by ncu --set full on
-            # the 262,144-plant launch (profiles/r1_step_kernel_v5_session2_final.txt), scaled to this launch's units
-            "traffic": 81.1 * (timed_plant_steps / max(1, args.steps)) * N_ZONES / world,
-            "traffic_source": "ncu capture of the 262144-plant launch scaled by units (profiles/r1_step_kernel_v5_session2_final.txt)",
+            # dram__bytes_read+write of one step (begin + run kernels): per plant-zone-step from the ncu --set full capture of
+            # the 262,144-plant launches, scaled to this run's units
+            "traffic": TRAFFIC_B_PER_UNIT * (timed_plant_steps / max(1, args.steps)) * N_ZONES / world,
+            "traffic_source": f"modelled: {TRAFFIC_B_PER_UNIT} B per plant-zone-step measured by ncu on the 262144-plant launches "
+                              "(profiles/r2_step_kernels.txt) x this run's units; it includes the begin -> run hand-off rows "
+                              "(2 x 614 B per plant-zone-step written and read back through L2 / HBM)",
             "peak_source": "measured in this run by wt_measure_fp64_peak (8 independent DFMA chains/thread); "
-                           "MEASURED_PEAKS.json carries no FP64 figure",
+                           "MEASURED_PEAKS.json carries no FP64 figure (nominal 37.2 TFLOP/s at 1965 MHz)",
             "flops_model": "SURVEY 8(d): 310(nfev+9njev)+950(nlu/2)+740 newton+240 steps+900 per zone, from emitted counters",
             "hbm": {"achieved_gbs": hbm_ach, "peak_gbs": hbm_peak, "frac": hbm_ach / hbm_peak},
-            "kernel": "wt_step_kernel", "kernel_ms_per_launch": alone["ms_per_launch"] if alone else None,
+            "kernel": "wt_step_begin_kernel + wt_step_run_kernel",
+            "kernel_ms_per_launch": alone["ms_per_step_launch_pair"] if alone else None,
             "achieved_basis": "whole timed region (overlapping launches of the sub-ensembles; includes sensor/stats kernels)",
             "kernel_alone": alone,
             "counters_per_plant_step": {k: float(cnt_sum[i]) / timed_plant_steps for i, k in enumerate(_lib.CNT_NAMES)},
+            "sensors": sensors_rf,
+            "calc_ph": k2,
+        },
+        "ensemble_statistics": {
+            "live": float(fin["live"]), "halted": float(fin["halted"]),
+            "mean_outlet_pH": float(fin["mean_pH"][-1]), "mean_outlet_chlorine": float(fin["mean_chlorine"][-1]),
+            "sensor_valid_fraction": [float(x) for x in fin.get("sensor_valid_fraction", [])],
         },
         "cpu_baseline": cpu,
         "e2e": e2e,
-        "gpu_launches": len(shard.engines) * (1 if args.fused else args.steps * (2 if shard.suites is not None else 1)
-                                                 + 2 * (args.steps // 10)),
+        "gpu_launches": nparts * (per_part_step * args.steps + per_part_sort + per_part_stats),
+        "host_launches": (n_blocks + (nparts * (per_part_step * rem)) if use_graph else None),
         "clocks": clk.summary(),
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# dram__bytes_read + dram__bytes_write of one step per plant-zone-step (ncu --set full, 262,144 x 10 launches)
+TRAFFIC_B_PER_UNIT = 400.0
+
+
+def calc_ph_roofline(dev, fp64_peak):
+    """K2 alone: 262,144 calculate_pH solves of BASELINE configs[3] (ensembles.config4), CUDA events, best of 5."""
+    import torch
+
+    from ics_wt_physicsengine_b200 import ensembles
+    from ics_wt_physicsengine_b200.chemistry import calculate_pH_batch
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    alk, ct, temp, guess = (t(a) for a in ensembles.config4(262144))
+    best, iters = None, None
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ph, it, st = calculate_pH_batch(alk, ct, temp, guess)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+        iters = float(it.sum())
+    # per Newton iteration (chemistry.py:193-269): exp10 (35) + 9 divisions (20 each) + ~40 mul/add = ~255 flops
+    flops = 255.0 * iters
+    ach = flops / (best * 1e-3) / 1e12
+    return {"kernel": "wt_calc_ph_kernel", "bound": "fp64", "iterations_total": iters, "ms_per_launch": best,
+            "solves": int(alk.numel()), "flops_per_iteration": 255.0, "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": ach / fp64_peak if fp64_peak else None,
+            "note": "one thread per buffer system; iteration counts 1..100 diverge inside a warp, so the bound is the slowest lane"}
 
 
 def e2e_measure(e, shard, args):
@@ -399,24 +486,30 @@ def e2e_measure(e, shard, args):
 
 
 def cpu_baseline(args):
+    """The oracle port on the host cores, on the FIRST `cpu_plants` plants of the GPU arm's own ensemble; only
+    plant-steps that completed (time advanced) are credited."""
     from ics_wt_physicsengine_b200 import ensembles
     from oracle import wt_oracle as wo
 
     cores = os.cpu_count() or 1
     sample = args.cpu_plants
-    e = ensembles.config5(65536, N_ZONES).slice(slice(0, sample))
+    e = ensembles.config5(args.plants, N_ZONES).slice(slice(0, sample))
     par = wo.derive_params(e.cfg, N_ZONES)
     bnd = np.ascontiguousarray(e.bnd)
     y = np.concatenate([e.pH0, e.Cl0, e.T0], axis=1).copy()
     t = np.zeros(sample)
     wo.set_max_attempts(args.max_attempts)
     wo.step_batch(par, bnd, N_ZONES, t, y, dt=DT, nsteps=1, nthreads=cores)
+    t_start = t.copy()
     t0 = time.perf_counter()
     wo.step_batch(par, bnd, N_ZONES, t, y, dt=DT, nsteps=args.cpu_steps, nthreads=cores)
     el = time.perf_counter() - t0
-    return {"value": sample * N_ZONES * args.cpu_steps / el, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {sample} plants of config5(65536) x {args.cpu_steps} steps on {cores} host threads "
-                      "(oracle C port of reactor.py + scipy Radau; the Python reference runs ~1e3 zone-steps/s/core, BASELINE.md)"}
+    done = float(((t - t_start) / DT).sum())
+    return {"value": done * N_ZONES / el, "unit": UNIT, "cores": cores, "kind": "port", "same_plants_as_gpu_arm": True,
+            "plant_steps_completed": done, "plant_steps_attempted": float(sample * args.cpu_steps),
+            "sample": f"first {sample} plants of the GPU arm's ensemble (config5({args.plants})) x {args.cpu_steps} steps on {cores} "
+                      "host threads (oracle C port of reactor.py + scipy Radau; the Python reference itself runs ~1e3 "
+                      "zone-steps/s/core, BASELINE.md)"}
 
 
 if __name__ == "__main__":

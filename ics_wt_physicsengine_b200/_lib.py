@@ -35,7 +35,7 @@ EXPORTS = (
     "wt_step_host", "wt_step_workspace_bytes", "wt_calc_ph", "wt_measure_fp64_peak", "wt_stats", "wt_stats_size", "wt_stats_scratch_doubles",
     "wt_sensors_init", "wt_sensors_calibrate", "wt_sensors_read", "wt_diagnostics", "wt_register_image",
     "wt_sensors_maintain", "wt_sensor_window_stats", "wt_sensors_reset", "wt_clock_tick", "wt_sensor_stats_size",
-    "wt_sensor_stats_scratch_doubles", "wt_sensor_stats", "wt_cost_order",
+    "wt_sensor_stats_scratch_doubles", "wt_sensor_stats", "wt_cost_order", "wt_apply_commands", "wt_scenario_commands",
 )
 
 
@@ -100,6 +100,10 @@ def lib() -> C.CDLL:
     L.wt_sensor_stats.restype = C.c_int
     L.wt_cost_order.argtypes = [C.c_int, ip, ip, ip, vp]
     L.wt_cost_order.restype = C.c_int
+    L.wt_apply_commands.argtypes = [C.c_int, dp, dp, dp, dp, vp]
+    L.wt_apply_commands.restype = C.c_int
+    L.wt_scenario_commands.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, ip, dp, C.c_double, dp, vp]
+    L.wt_scenario_commands.restype = C.c_int
     L.wt_diagnostics.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, ip, vp]
     L.wt_diagnostics.restype = C.c_int
     L.wt_register_image.argtypes = [C.c_int, ip, C.c_int, dp, ip, C.c_double, vp, vp, vp, vp]

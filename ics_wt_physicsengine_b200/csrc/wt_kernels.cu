@@ -704,6 +704,47 @@ __global__ void wt_sensor_window_stats_kernel(int P, int m, const double *hist, 
   out[6 * Pz + p] = none ? 0.0 : (nf > 0 ? (double)(m - nf) / m : 1.0);
 }
 
+// ---------------------------------------------------------------------------------------
+// Orchestrator: the reference's main loop turns three actuator commands per plant into
+// boundary conditions through two layers of zero-trust clamps (__main__.py:57-63 validate_flow_rate, :227-252
+// read_modbus_commands, :255-271 apply_boundary_conditions).  One thread per plant, in place on the boundary SoA.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double wt_validate_flow_rate(double v, double vmax) {  // __main__.py:57-63
+  if (v != v) return 0.0;                 // NaN
+  return fmax(0.0, fmin(v, vmax));        // max(0.0, min(float(value), max_value)): +inf -> max, -inf -> 0
+}
+__device__ __forceinline__ void wt_apply_commands_one(double acid, double chlor, double inlet, double *bnd, size_t P, int p) {
+  // read_modbus_commands' clamps, then apply_boundary_conditions' (defence in depth)
+  acid = wt_validate_flow_rate(wt_validate_flow_rate(acid, 2.0), 2.0);
+  chlor = wt_validate_flow_rate(wt_validate_flow_rate(chlor, 1.0), 1.0);
+  inlet = wt_validate_flow_rate(inlet, 20.0);
+  bnd[(size_t)WTB_ACID_FLOW * P + p] = acid;
+  bnd[(size_t)WTB_CL_FLOW * P + p] = chlor;
+  if (inlet > 0.1) bnd[(size_t)WTB_INLET_FLOW * P + p] = wt_validate_flow_rate(inlet, 20.0);   // only a significant command
+}
+__global__ void wt_apply_commands_kernel(int P, const double *acid, const double *chlor, const double *inlet, double *bnd) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  wt_apply_commands_one(acid[p], chlor[p], inlet[p], bnd, (size_t)P, p);
+}
+// Scenario scripting: S scripts of K piecewise-constant command triplets (breakpoints times[K], ascending), every plant
+// follows script sid[p].  The time comes from the device clock of the sensor suite / step loop (clock[0]), so a whole
+// scripted run replays from a CUDA graph with no per-step host-to-device traffic.  Before the first breakpoint the
+// boundary is left as it is.
+__global__ void wt_scenario_commands_kernel(int P, int K, int S, const double *times, const double *cmd, const int32_t *sid,
+                                            const double *clock, double t_host, double *bnd) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double t = clock ? clock[0] : t_host;
+  int k = -1;
+  for (int i = 0; i < K; ++i) if (times[i] <= t) k = i;   // K is small; every thread takes the same path
+  if (k < 0) return;
+  int s = sid ? sid[p] : 0;
+  s = s < 0 ? 0 : (s >= S ? S - 1 : s);
+  const double *c = cmd + ((size_t)s * K + k) * 3;
+  wt_apply_commands_one(c[0], c[1], c[2], bnd, (size_t)P, p);
+}
+
 // 8 independent DFMA chains per thread: saturates the FP64 pipe without memory traffic
 __global__ void wt_dfma_peak_kernel(double *out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -877,6 +918,23 @@ int wt_sensor_window_stats(int P, int m, const double *hist, const int32_t *rows
   if (!out || (m > 0 && (!hist || !rows))) return set_err(WT_ERR_BAD_ARG, "null device pointer");
   wt_sensor_window_stats_kernel<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, m, hist, rows, sensor, out);
   return cuda_err(cudaGetLastError(), "wt_sensor_window_stats_kernel launch");
+}
+
+int wt_apply_commands(int P, const double *acid, const double *chlor, const double *inlet, double *bnd_soa, void *stream) {
+  if (P <= 0) return set_err(WT_ERR_BAD_ARG, "P must be positive");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (!acid || !chlor || !inlet || !bnd_soa) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  wt_apply_commands_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, acid, chlor, inlet, bnd_soa);
+  return cuda_err(cudaGetLastError(), "wt_apply_commands_kernel launch");
+}
+
+int wt_scenario_commands(int P, int K, int S, const double *times, const double *cmd, const int32_t *sid, const double *clock,
+                         double t, double *bnd_soa, void *stream) {
+  if (P <= 0 || K <= 0 || S <= 0) return set_err(WT_ERR_BAD_ARG, "P, K and S must be positive");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (!times || !cmd || !bnd_soa) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  wt_scenario_commands_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, K, S, times, cmd, sid, clock, t, bnd_soa);
+  return cuda_err(cudaGetLastError(), "wt_scenario_commands_kernel launch");
 }
 
 int wt_stats_size(int n) { return WT_STATS_HDR + 6 * n; }

@@ -137,14 +137,20 @@ __device__ double wt_transport_sample(const SensorArgs &a, int p, int line, doub
   *hd = head;
   *ct = count;
   const double target = t - a.s.line_delay_s;
-  int slot = head - count;  // oldest entry
-  if (slot < 0) slot += WT_RING;
+  // The reference scans the deque from the oldest entry and keeps the FIRST minimum of |timestamp - target|.
+  // Timestamps never decrease along the deque (read() rejects a decreasing current_time, base_sensor.py:543-549), so
+  // the distance falls to its minimum and rises again: scanning from the NEWEST entry backwards, taking every tie
+  // (-> the oldest of equal minima) and stopping at the first larger distance finds the same slot after reading
+  // ~delay/dt + 2 timestamps instead of all 100 (the kernel is bound by this HBM traffic).
+  int slot = head == 0 ? WT_RING - 1 : head - 1;  // newest entry
   int best = slot;
   double best_d = fabs(base[((size_t)slot * 2) * P] - target);
   for (int i = 1; i < count; ++i) {
-    slot = slot + 1 == WT_RING ? 0 : slot + 1;
+    slot = slot == 0 ? WT_RING - 1 : slot - 1;
     const double d = fabs(base[((size_t)slot * 2) * P] - target);
-    if (d < best_d) { best_d = d; best = slot; }
+    if (d > best_d) break;
+    best_d = d;
+    best = slot;
   }
   return base[((size_t)best * 2 + 1) * P];
 }

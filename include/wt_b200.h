@@ -297,6 +297,24 @@ int wt_sensor_stats(int P, const double *out_value_dev, const int32_t *out_statu
  * first (counting sort; bins_dev: 1024 int32 of device scratch).  Results of wt_advance never depend on the order. */
 int wt_cost_order(int P, const int32_t *cost_dev, int32_t *order_dev, int32_t *bins_dev, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Orchestrator (the caller of the path): actuator commands -> boundary conditions with the
+ * reference's two layers of zero-trust clamps, in place on the boundary SoA [WT_NBND][P]:
+ *   validate_flow_rate (__main__.py:57-63): NaN -> 0, clamp to [0, max]; read_modbus_commands (:227-252) clamps acid to
+ *   2, chlorine to 1, inlet to 20 L/min; apply_boundary_conditions (:255-271) clamps again and updates the inlet flow
+ *   only when the command exceeds 0.1 L/min.
+ * wt_apply_commands     per-plant command arrays (a controller's output, device memory).
+ * wt_scenario_commands  scenario scripting without per-step host traffic: S scripts of K piecewise-constant command
+ *                       triplets cmd[S][K][3] = (acid, chlorine, inlet) with ascending breakpoints times[K]; plant p
+ *                       follows script sid[p] (NULL: script 0).  The time is clock_dev[0] (the device clock advanced by
+ *                       wt_clock_tick; NULL: the host value t).  Before times[0] the boundary is left untouched.
+ * ------------------------------------------------------------------------------------- */
+int wt_apply_commands(int P, const double *acid_dev, const double *chlorine_dev, const double *inlet_dev,
+                      double *bnd_soa_dev, void *stream);
+int wt_scenario_commands(int P, int K, int S, const double *times_dev, const double *cmd_dev,
+                         const int32_t *sid_dev, const double *clock_dev, double t, double *bnd_soa_dev,
+                         void *stream);
+
 /* Measured-peak helper for the roofline denominator: runs a dependent-chain-free DFMA loop on
  * every SM and returns the sustained FP64 rate in TFLOP/s (2 flops per DFMA). */
 int wt_measure_fp64_peak(double *tflops_out, int iters);

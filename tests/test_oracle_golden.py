@@ -121,3 +121,22 @@ def test_temperature_range_is_a_status_not_a_crash(oracle):
     st, _, _ = oracle.step_batch(oracle.derive_params(e.cfg, 5), e.bnd, 5, t, y)
     assert st[0] & 2
     assert np.array_equal(y, before) and t[0] == 0.0
+
+
+def test_derived_state_against_reference(oracle, golden_dir):
+    """_update_derived_state (reactor.py:511-524): H_concentration, density, chlorine_decay_rate of the oracle after
+    every step against the reference's own ReactorState fields (tests/golden/derived_config3.npz)."""
+    g = np.load(os.path.join(golden_dir, "derived_config3.npz"))
+    n, P = int(g["n_zones"]), g["cfg"].shape[0]
+    par = oracle.derive_params(g["cfg"], n)
+    worst = 0.0
+    for p in range(P):
+        y = np.concatenate([g["pH0"][p], g["Cl0"][p], g["T0"][p]]).copy()
+        t, fl, d, cnt = np.zeros(1), np.zeros(1), np.zeros(3 * n), np.zeros(8, np.int32)
+        bnd = np.ascontiguousarray(g["bnd"][p])
+        for s in range(int(g["nsteps"])):
+            oracle.lib().wt_oracle_step(oracle._dp(par[p]), oracle._dp(bnd), n, 1.0, oracle._dp(t), oracle._dp(y), oracle._dp(fl),
+                                        oracle._dp(d), oracle._ip(cnt))
+            worst = max(worst, float(np.max(np.abs(d - g["D"][s, p]) / np.abs(g["D"][s, p]))))
+            assert np.max(np.abs(y - g["Y"][s, p]) / np.maximum(np.abs(g["Y"][s, p]), 1e-300)) < 1e-9
+    assert worst < 1e-12
