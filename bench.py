@@ -391,7 +391,7 @@ def main():
             "traffic": TRAFFIC_B_PER_UNIT * (timed_plant_steps / max(1, args.steps)) * N_ZONES / world,
             "traffic_source": f"modelled: {TRAFFIC_B_PER_UNIT} B per plant-zone-step measured by ncu on the 262144-plant launches "
                               "(profiles/r2_step_kernels.txt) x this run's units; it includes the begin -> run hand-off rows "
-                              "(2 x 614 B per plant-zone-step written and read back through L2 / HBM)",
+                              "(2 x 614 B per plant-zone-step written and read back; begin kernel 235 B, run kernel 316 B per plant-zone-step of DRAM traffic)",
             "peak_source": "measured in this run by wt_measure_fp64_peak (8 independent DFMA chains/thread); "
                            "MEASURED_PEAKS.json carries no FP64 figure (nominal 37.2 TFLOP/s at 1965 MHz)",
             "flops_model": "SURVEY 8(d): 310(nfev+9njev)+950(nlu/2)+740 newton+240 steps+900 per zone, from emitted counters",
@@ -421,7 +421,7 @@ def main():
 
 
 # dram__bytes_read + dram__bytes_write of one step per plant-zone-step (ncu --set full, 262,144 x 10 launches)
-TRAFFIC_B_PER_UNIT = 400.0
+TRAFFIC_B_PER_UNIT = 551.0
 
 
 def calc_ph_roofline(dev, fp64_peak):

@@ -145,6 +145,9 @@ struct StepArgs {
 #ifndef WT_STEP_CARVEOUT_PCT
 #define WT_STEP_CARVEOUT_PCT 100  // percent of the 228 KB: three blocks of ~63 KB (n = 10) or ~69 KB (n = 20)
 #endif
+#ifndef WT_BEGIN_MINBLOCKS
+#define WT_BEGIN_MINBLOCKS 3
+#endif
 #define WT_MAX_DEVICES 64
 
 // ---------------------------------------------------------------------------------------
@@ -183,7 +186,7 @@ __device__ __forceinline__ LaneMap wt_lane_map(const StepArgs &a, long long wg, 
 // NZ > 0: the zone count is a compile-time constant (the BASELINE shapes n = 10 and n = 20): lane geometry, PCR level
 // count and every LU slot offset fold to immediates after inlining; NZ = 0 reads n from the arguments.
 template <int WARPS, int NZ>
-__global__ void __launch_bounds__(WARPS * 32, 3) wt_step_begin_kernel(StepArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, WT_BEGIN_MINBLOCKS) wt_step_begin_kernel(StepArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = NZ > 0 ? NZ : a.n, gpw = 32 / n;
@@ -424,49 +427,87 @@ __global__ void wt_derivatives_kernel(int P, int n, const double *par_, const do
   }
 }
 
-// chemistry.py:193-330, one thread per buffer system
-__global__ void wt_calc_ph_kernel(int P, const double *alk, const double *ct, const double *temp,
-                                  const double *guess, double *ph, int32_t *iters, int32_t *status) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  const double tc = temp[i];
-  if (tc < 0.0 || tc > 100.0) {  // thermodynamics.py:146-157 via chemistry.py:118
-    ph[i] = nan("");
-    iters[i] = 0;
-    status[i] = 3;
-    return;
+// chemistry.py:193-330.  The Newton-Raphson iteration counts of independent buffer systems range from 1 to 100
+// (BASELINE configs[3]: mode 6-14, 15 % run into the 100-iteration limit), so one thread per system leaves 70 % of
+// the lanes of a warp idle (ncu, round 2: 9.6 of 32 threads active per instruction).  Here a warp owns a CHUNK of
+// systems and every lane that finishes one takes the next from the chunk (ballot + popc, no atomics): lanes stay busy
+// until the chunk is empty.  The arithmetic of a solve is unchanged, so results are bit-identical to the
+// one-thread-per-system kernel.
+#define WT_PH_CHUNK 256
+__global__ void __launch_bounds__(128) wt_calc_ph_kernel(int P, const double *alk, const double *ct, const double *temp,
+                                                           const double *guess, double *ph, int32_t *iters, int32_t *status) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long lo = warp * WT_PH_CHUNK;
+  if (lo >= P) return;
+  const int hi = (int)((lo + WT_PH_CHUNK < P) ? lo + WT_PH_CHUNK : P);
+  int cursor = (int)lo;          // next unassigned system of the chunk (warp-uniform)
+  bool busy = false;
+  int i = 0, it = 0;
+  double pH = 0.0, Kw = 0.0, Ka1 = 0.0, Ka2 = 0.0, C_T = 0.0, alk_eq = 0.0;
+  for (;;) {
+    // ---- idle lanes take the next systems of the chunk
+    const unsigned need = __ballot_sync(0xffffffffu, !busy);
+    if (!busy) {
+      const int idx = cursor + __popc(need & ((1u << lane) - 1u));
+      if (idx < hi) {
+        const double tc = temp[idx];
+        if (tc < 0.0 || tc > 100.0) {  // thermodynamics.py:146-157 via chemistry.py:118
+          ph[idx] = nan("");
+          iters[idx] = 0;
+          status[idx] = 3;
+        } else {
+          const double TK = tc + 273.15;
+          Kw = 1.0e-14 * exp((55900.0 / 8.314) * (1.0 / 298.15 - 1.0 / TK));
+          Ka1 = exp10(-(6.35 + (-0.008) * (tc - 25.0)));
+          Ka2 = exp10(-(10.33 + (-0.008) * (tc - 25.0)));
+          C_T = ct[idx] / 1000.0;
+          alk_eq = alk[idx] / 50000.0;
+          pH = guess[idx];
+          i = idx;
+          it = 0;
+          busy = true;
+        }
+      }
+    }
+    cursor += __popc(need);
+    if (!__any_sync(0xffffffffu, busy)) {
+      if (cursor >= hi) break;
+      continue;
+    }
+    // ---- one Newton-Raphson iteration of every busy lane (chemistry.py:291-330)
+    if (busy) {
+      const double H = exp10(-pH);
+      const double OH = Kw / H;
+      const double D = H * H + Ka1 * H + Ka1 * Ka2;
+      const double a1 = (Ka1 * H) / D;
+      const double a2 = (Ka1 * Ka2) / D;
+      const double f = H - OH + a1 * C_T + 2.0 * (a2 * C_T) - alk_eq;
+      const double dH = -WT_LN10 * H;
+      const double dOH = -(Kw / (H * H)) * dH;
+      const double dD = 2.0 * H + Ka1;
+      const double da1 = Ka1 * (D - H * dD) / (D * D);
+      const double da2 = -Ka1 * Ka2 * dD / (D * D);
+      const double df = dH - dOH + C_T * da1 * dH + 2.0 * (C_T * da2 * dH);
+      int st = -1;
+      if (fabs(df) < 1e-15) st = 1;
+      else {
+        const double delta = -f / df;
+        double pn = pH + delta;
+        pn = pn != pn ? pn : fmin(fmax(pn, 0.0), 14.0);  // np.clip keeps NaN
+        pH = pn;
+        if (fabs(delta) < 1e-6) st = 0;
+      }
+      ++it;
+      if (st < 0 && it >= 100) st = 2;
+      if (st >= 0) {
+        ph[i] = pH;
+        iters[i] = it;
+        status[i] = st;
+        busy = false;
+      }
+    }
   }
-  const double TK = tc + 273.15;
-  const double Kw = 1.0e-14 * exp((55900.0 / 8.314) * (1.0 / 298.15 - 1.0 / TK));
-  const double Ka1 = exp10(-(6.35 + (-0.008) * (tc - 25.0)));
-  const double Ka2 = exp10(-(10.33 + (-0.008) * (tc - 25.0)));
-  const double C_T = ct[i] / 1000.0;
-  const double alk_eq = alk[i] / 50000.0;
-  double pH = guess[i];
-  int st = 2, it = 0;
-  for (it = 0; it < 100; ++it) {
-    const double H = exp10(-pH);
-    const double OH = Kw / H;
-    const double D = H * H + Ka1 * H + Ka1 * Ka2;
-    const double a1 = (Ka1 * H) / D;
-    const double a2 = (Ka1 * Ka2) / D;
-    const double f = H - OH + a1 * C_T + 2.0 * (a2 * C_T) - alk_eq;
-    const double dH = -WT_LN10 * H;
-    const double dOH = -(Kw / (H * H)) * dH;
-    const double dD = 2.0 * H + Ka1;
-    const double da1 = Ka1 * (D - H * dD) / (D * D);
-    const double da2 = -Ka1 * Ka2 * dD / (D * D);
-    const double df = dH - dOH + C_T * da1 * dH + 2.0 * (C_T * da2 * dH);
-    if (fabs(df) < 1e-15) { st = 1; ++it; break; }
-    const double delta = -f / df;
-    double pn = pH + delta;
-    pn = pn != pn ? pn : fmin(fmax(pn, 0.0), 14.0);  // np.clip keeps NaN
-    if (fabs(delta) < 1e-6) { pH = pn; st = 0; ++it; break; }
-    pH = pn;
-  }
-  ph[i] = pH;
-  iters[i] = it;
-  status[i] = st;
 }
 
 
@@ -889,7 +930,8 @@ int wt_calc_ph(int P, const double *alk, const double *ct, const double *temp, c
   if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
   if (!alk || !ct || !temp || !guess || !ph || !iters || !status) return set_err(WT_ERR_BAD_ARG, "null device pointer");
   const int tpb = 128;
-  wt_calc_ph_kernel<<<(P + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(P, alk, ct, temp, guess, ph, iters, status);
+  const long long warps = ((long long)P + WT_PH_CHUNK - 1) / WT_PH_CHUNK;   // a warp per chunk of systems
+  wt_calc_ph_kernel<<<(unsigned)((warps * 32 + tpb - 1) / tpb), tpb, 0, (cudaStream_t)stream>>>(P, alk, ct, temp, guess, ph, iters, status);
   return cuda_err(cudaGetLastError(), "wt_calc_ph_kernel launch");
 }
 
@@ -1175,7 +1217,7 @@ int wt_sensors_read(int P, int n, long long plant0, unsigned read_index, double 
   a.s.flow_velocity = suite6[0]; a.s.bubble_per_min = suite6[1]; a.s.grounding = suite6[2]; a.s.vibration_g = suite6[3];
   a.s.ambient_temp = suite6[4]; a.s.line_delay_s = suite6[5];
   a.s.seed_lo = (uint32_t)seed; a.s.seed_hi = (uint32_t)(seed >> 32);
-  wt_sensors_read_kernel<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+  wt_sensors_read_kernel<<<dim3((P + 127) / 128, 5), 128, 0, (cudaStream_t)stream>>>(a);
   return cuda_err(cudaGetLastError(), "wt_sensors_read_kernel launch");
 }
 

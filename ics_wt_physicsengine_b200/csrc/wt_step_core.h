@@ -1136,7 +1136,9 @@ struct WtPlantStep {
         }
         // common.py:63-65 over the 3 n (closing) or 9 n (Newton) scaled unknowns
         const vd nrm = vsqrt(wt_gsum(g, q)) * sel(cl, g.inv_sqrtN, g.inv_sqrt3N);
-        // ---- Newton pass: convergence control (radau.py:101-130)
+        // ---- Newton pass: convergence control (radau.py:101-130).  (Not skipped in a pass without iterating plants:
+        // the branch costs more in scheduling freedom than the ~100 masked instructions it would save -- measured.)
+        vb cvn;
         {
           const vd dW_norm = nrm;
           vd new_rate = wt_div(dW_norm, dW_norm_old);
@@ -1155,12 +1157,14 @@ struct WtPlantStep {
             W[1][v] = sel(active, W[1][v] + cr[v], W[1][v]);
             W[2][v] = sel(active, W[2][v] + ci[v], W[2][v]);
           }
-          const vb cvn = active & ((dW_norm == 0.0) | (have_rate & (rate * i1r * dW_norm < WT_NEWTON_TOL)));
+          cvn = active & ((dW_norm == 0.0) | (have_rate & (rate * i1r * dW_norm < WT_NEWTON_TOL)));
           converged = converged | cvn;
           active = active & !cvn;
           dW_norm_old = sel(cl, dW_norm_old, dW_norm);
           have_norm_old = vbroadcast_b(true);
           if (k + 1 >= WT_NEWTON_MAXITER) active = vbroadcast_b(false);  // radau.py:87: at most NEWTON_MAXITER iterations
+        }
+        {
           // ---- closing pass: error norm, second estimate, accept / reject (radau.py:483-545)
           if (vany(cl)) {
             const vb clx = cl & fget(F_RUNNING);  // (not the plants whose evaluation at y + err just raised)

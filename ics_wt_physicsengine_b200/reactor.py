@@ -177,7 +177,9 @@ class PlantEnsemble:
     (__main__.py:404-406).
 
     max_attempts: budget of collocation solves per plant-step (engine policy, see DESIGN.md
-    "straggler policy"); 0 means unlimited, which is the reference's behaviour.
+    "straggler policy"); 0 means no budget -- the reference's behaviour -- up to a hard stop at 2,000,000
+    collocation solves of one step (WT_HARD_MAX_ATTEMPTS), after which the plant gets WT_ST_WORK_LIMIT like any
+    other budget overrun.
     """
 
     DEFAULT_MAX_ATTEMPTS = 64
@@ -385,6 +387,12 @@ class IntegratedCSTR:
         if st & _lib.ST_T_RANGE:
             raise ValueError("Temperature outside liquid water range [0.0, 100.0]°C inside the ODE solve "
                              "(thermodynamics.py:146-157)")
+        if st & _lib.ST_WORK_LIMIT:
+            # max_attempts = 0 means "no budget", but the kernel still stops after WT_HARD_MAX_ATTEMPTS (2,000,000)
+            # collocation solves of ONE step (the reference would grind on: such steps take it hours).  The state was
+            # left untouched; say so instead of returning an un-advanced state silently.
+            raise RuntimeError("step(dt) gave up after 2,000,000 collocation solves (plant on the 8 C density "
+                               "discontinuity, see DESIGN.md section 7); the state was not advanced")
         if st & _lib.ST_SOLVER_FAILED:
             logger.warning("ODE solver failed: Required step size is less than spacing between numbers.")
         new = e.state[0]

@@ -91,7 +91,8 @@ const char *wt_last_error(void);
  *              (ReactorState derived fields, reactor.py:136-147), may be NULL
  *   status     [P] in/out: plants whose word has a WT_ST_HALT_MASK bit are skipped
  *   counters   optional [WT_NCNT * P], accumulated, may be NULL
- *   max_attempts  budget of collocation solves per plant-step; 0 = unlimited (reference)
+ *   max_attempts  budget of collocation solves per plant-step; 0 = no budget (reference behaviour), up to a hard
+ *              stop at 2,000,000 collocation solves of one step (the plant then gets WT_ST_WORK_LIMIT as with any budget)
  * ------------------------------------------------------------------------------------- */
 int wt_step(int P, int n_zones, double dt, const double *par_dev, const double *bnd_dev,
             int bnd_stride, double *time_dev, double *y_dev, double *flow_rate_dev,
