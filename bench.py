@@ -304,8 +304,8 @@ def main():
     # shard at the same time; whole-job value = all plants / slowest rank
     if world > 1:
         dist.barrier()
-    live_e2e, el_e2e, k_e2e, h2d, d2h = e2e_measure(e, shard, args)
-    e2e_agg = torch.tensor([float(live_e2e), el_e2e, float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+    live_e2e, el_e2e, k_e2e, h2d, d2h, floor_e2e = e2e_measure(e, shard, args)
+    e2e_agg = torch.tensor([float(live_e2e), el_e2e, float(h2d), float(d2h), floor_e2e], dtype=torch.float64, device=dev)
     e2e_max = e2e_agg.clone()
     if world > 1:
         dist.all_reduce(e2e_agg)
@@ -313,6 +313,9 @@ def main():
     e2e = {"value": float(e2e_agg[0]) * N_ZONES * k_e2e / float(e2e_max[1]), "unit": UNIT,
            "h2d_bytes_per_step": int(e2e_agg[2]), "d2h_bytes_per_step": int(e2e_agg[3]), "steps": k_e2e,
            "work": "physics step only (IntegratedCSTR.step of every plant); the sensor suite is not part of this call",
+           "copy_only_floor_value": float(e2e_agg[0]) * N_ZONES * k_e2e / float(e2e_max[4]),
+           "copy_only_floor": "the same H2D and D2H bytes per step moved concurrently on two streams with no kernel, all ranks at "
+                              "once (max over ranks): what the host links of this box allow for this call",
            "api": "wt_step_host (C ABI, pinned host buffers: H2D of state+boundary, step, D2H of state+time+flow+status per call, "
                   "pipelined over >= 12 column slabs on three streams; per-plant constants resident after the first call)", "n_gpus": world}
 
@@ -482,7 +485,23 @@ def e2e_measure(e, shard, args):
     live = int(((st & _lib.ST_HALT_MASK) == 0).sum())
     h2d = (10 + 1 + 3 * n + 1) * P * 8 + P * 4
     d2h = (1 + 3 * n + 1) * P * 8 + P * 4
-    return live, el, k, h2d, d2h
+    # the floor of this call on this box: the same bytes copied both ways at once (two streams), no kernel
+    dev = shard.device
+    up_h, dn_h = torch.empty(h2d, dtype=torch.uint8).pin_memory(), torch.empty(d2h, dtype=torch.uint8).pin_memory()
+    up_d, dn_d = torch.empty(h2d, dtype=torch.uint8, device=dev), torch.empty(d2h, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    floor = None
+    for rep in range(2):
+        t0 = time.perf_counter()
+        for _ in range(k):
+            with torch.cuda.stream(s1):
+                up_d.copy_(up_h, non_blocking=True)
+            with torch.cuda.stream(s2):
+                dn_h.copy_(dn_d, non_blocking=True)
+        torch.cuda.synchronize()
+        floor = time.perf_counter() - t0
+    return live, el, k, h2d, d2h, floor
 
 
 def cpu_baseline(args):

@@ -505,8 +505,8 @@ struct WtPlantStep {
         c_ = -(c_up * k2);
         const vd adr = shfl_idx(ar, sd), adi = shfl_idx(ai, sd), cdr = shfl_idx(cr, sd), cdi = shfl_idx(ci, sd);
         const vd aur = shfl_idx(ar, su), aui = shfl_idx(ai, su), cur = shfl_idx(cr, su), cui = shfl_idx(ci, su);
-        br = br - (cdr * kc[0] - cdi * kc[1]) - (aur * kc[2] - aui * kc[3]);
-        bi = bi - (cdr * kc[1] + cdi * kc[0]) - (aur * kc[3] + aui * kc[2]);
+        br = wt_cmsub_re(wt_cmsub_re(br, cdr, cdi, kc[0], kc[1]), aur, aui, kc[2], kc[3]);
+        bi = wt_cmsub_im(wt_cmsub_im(bi, cdr, cdi, kc[0], kc[1]), aur, aui, kc[2], kc[3]);
         ar = -(adr * kc[0] - adi * kc[1]);
         ai = -(adr * kc[1] + adi * kc[0]);
         cr = -(cur * kc[2] - cui * kc[3]);
@@ -529,8 +529,8 @@ struct WtPlantStep {
         kc[0] = er * rpr - ei * rpi; kc[1] = er * rpi + ei * rpr;
         const vd ep = shfl_idx(e, sl), epr = shfl_idx(er, sl), epi = shfl_idx(ei, sl);
         b = b - ep * k;
-        br = br - (epr * kc[0] - epi * kc[1]);
-        bi = bi - (epr * kc[1] + epi * kc[0]);
+        br = wt_cmsub_re(br, epr, epi, kc[0], kc[1]);
+        bi = wt_cmsub_im(bi, epr, epi, kc[0], kc[1]);
         den[0] = b; den[1] = br * br + bi * bi;
         wt_rcp_n<2>(den, inv);
         kc[2] = br * inv[1];
@@ -559,8 +559,8 @@ struct WtPlantStep {
         vd kc[4];  // k1r, k1i, k2r, k2i
         lu->cx_get4(sc + 4 * l, kc);
         vd ddr = shfl_idx(dr, sd), ddi = shfl_idx(di, sd), dur = shfl_idx(dr, su), dui = shfl_idx(di, su);
-        vd nr = dr - (ddr * kc[0] - ddi * kc[1]) - (dur * kc[2] - dui * kc[3]);
-        vd ni = di - (ddr * kc[1] + ddi * kc[0]) - (dur * kc[3] + dui * kc[2]);
+        vd nr = wt_cmsub_re(wt_cmsub_re(dr, ddr, ddi, kc[0], kc[1]), dur, dui, kc[2], kc[3]);
+        vd ni = wt_cmsub_im(wt_cmsub_im(di, ddr, ddi, kc[0], kc[1]), dur, dui, kc[2], kc[3]);
         dr = nr;
         di = ni;
       }
@@ -574,8 +574,8 @@ struct WtPlantStep {
         vd kc[4];  // kr, ki, pivot re, pivot im
         lu->cx_get4(sc + 4 * l, kc);
         vd dpr = shfl_idx(dr, sl), dpi = shfl_idx(di, sl);
-        vd nr = dr - (dpr * kc[0] - dpi * kc[1]);
-        vd ni = di - (dpr * kc[1] + dpi * kc[0]);
+        vd nr = wt_cmsub_re(dr, dpr, dpi, kc[0], kc[1]);
+        vd ni = wt_cmsub_im(di, dpr, dpi, kc[0], kc[1]);
         dr = nr * kc[2] - ni * kc[3];
         di = nr * kc[3] + ni * kc[2];
       }

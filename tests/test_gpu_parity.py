@@ -502,3 +502,19 @@ def test_config2_600_steps_on_a_slice(oracle):
     n_excused, worst = _stepwise_parity(oracle, ens.config2(4096, 10).slice(slice(0, 1024)), 600)
     print(f"config2 1024x10x600: worst non-excused error {worst:.2e}, excused plant-steps {n_excused} of {1024 * 600}")
     assert worst <= TOL and n_excused <= 1024 * 600 // 2000
+
+
+def test_two_devices_in_one_process():
+    """The step kernels need > 48 KB of dynamic shared memory; that attribute belongs to the (kernel, device) pair.
+    Round 1 set it once per process, so the first launch on a second GPU of the same process failed."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    e = ens.config2(999, 10, seed=5)
+    a = PlantEnsemble(e, device="cuda:0", max_attempts=CAP)
+    b = PlantEnsemble(e, device="cuda:1", max_attempts=CAP)
+    for _ in range(3):
+        a.step(1.0, e.bnd)
+        b.step(1.0, e.bnd)
+    torch.cuda.synchronize(0)
+    torch.cuda.synchronize(1)
+    assert np.array_equal(a.state_numpy(), b.state_numpy()) and np.array_equal(a.status.cpu().numpy(), b.status.cpu().numpy())
