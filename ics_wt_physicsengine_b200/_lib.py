@@ -26,7 +26,9 @@ ST_CLIP_T = 16
 ST_NONFINITE = 32
 ST_T_RANGE_DERIVED = 64
 ST_WORK_LIMIT = 128
+ST_DEFERRED = 256
 ST_HALT_MASK = ST_T_RANGE | ST_WORK_LIMIT
+ST_SKIP_MASK = ST_HALT_MASK | ST_DEFERRED
 
 CNT_NAMES = ("nfev", "njev", "nlu", "nsteps", "nnewton", "nreject", "nnewton_fail", "jac_retry")
 
@@ -36,6 +38,7 @@ EXPORTS = (
     "wt_sensors_init", "wt_sensors_calibrate", "wt_sensors_read", "wt_diagnostics", "wt_register_image",
     "wt_sensors_maintain", "wt_sensor_window_stats", "wt_sensors_reset", "wt_clock_tick", "wt_sensor_stats_size",
     "wt_sensor_stats_scratch_doubles", "wt_sensor_stats", "wt_cost_order", "wt_apply_commands", "wt_scenario_commands",
+    "wt_defer_collect", "wt_catch_up", "wt_defer_rejoin",
 )
 
 
@@ -100,6 +103,13 @@ def lib() -> C.CDLL:
     L.wt_sensor_stats.restype = C.c_int
     L.wt_cost_order.argtypes = [C.c_int, ip, ip, ip, vp]
     L.wt_cost_order.restype = C.c_int
+    L.wt_defer_collect.argtypes = [C.c_int, up, ip, ip, C.c_int, vp]
+    L.wt_defer_collect.restype = C.c_int
+    L.wt_catch_up.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, up, ip, C.c_int,
+                              ip, ip, dp, vp, vp]
+    L.wt_catch_up.restype = C.c_int
+    L.wt_defer_rejoin.argtypes = [up, ip, ip, C.c_int, vp]
+    L.wt_defer_rejoin.restype = C.c_int
     L.wt_apply_commands.argtypes = [C.c_int, dp, dp, dp, dp, vp]
     L.wt_apply_commands.restype = C.c_int
     L.wt_scenario_commands.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, ip, dp, C.c_double, dp, vp]

@@ -134,6 +134,9 @@ struct StepArgs {
   int32_t *cost;         // optional: per-plant work of this launch (collocation solves + Newton iterations)
   char *ws;              // workspace (wt_step_workspace_bytes): work-queue counter + the begin -> run hand-off rows
   int n_groups;          // warps' worth of plants in this launch (ceil(P / plants per warp))
+  uint32_t skip_mask;    // plants with one of these status bits are passed over (WTS_SKIP_MASK; a catch-up launch: halts only)
+  const int32_t *count_dev;  // optional: number of valid entries of `order` (a device-side list shorter than P)
+  const double *t_stop;  // optional: plants whose time has reached *t_stop are passed over (catch-up launches)
 };
 
 #ifndef WT_STEP_WARPS
@@ -173,11 +176,20 @@ __host__ __device__ inline int wt_begin_smem_doubles(int n) { return wt_begin_la
 
 // lane <-> plant mapping of group `wg` (both kernels use the same one)
 struct LaneMap { int p, z, gi; bool in_plant; };
+__device__ __forceinline__ int wt_plant_count(const StepArgs &a) {
+  int Pn = a.P;
+  if (a.count_dev) { const int c = *a.count_dev; Pn = c < Pn ? c : Pn; }
+  return Pn;
+}
+// a plant this launch works on: not passed over by its status, not yet at the stop time of a catch-up launch
+__device__ __forceinline__ bool wt_plant_live(const StepArgs &a, uint32_t st, double t) {
+  return !(st & a.skip_mask) && !(a.t_stop && t >= *a.t_stop - 0.5 * a.dt);
+}
 __device__ __forceinline__ LaneMap wt_lane_map(const StepArgs &a, long long wg, int lane, int n, int gpw) {
   LaneMap m;
   m.gi = lane / n;
   const long long pl = wg * gpw + m.gi;
-  m.in_plant = m.gi < gpw && pl < a.P;
+  m.in_plant = m.gi < gpw && pl < wt_plant_count(a);
   m.p = m.in_plant ? (a.order ? a.order[pl] : (int)pl) : 0;
   m.z = m.in_plant ? lane - m.gi * n : 0;
   return m;
@@ -209,7 +221,7 @@ __global__ void __launch_bounds__(WARPS * 32, WT_BEGIN_MINBLOCKS) wt_step_begin_
 #pragma unroll
   for (int v = 0; v < 3; ++v) y0[v] = a.y[((size_t)v * n + z) * P + p];
 
-  const bool on = lm.in_plant && !(st_in & WTS_HALT_MASK);
+  const bool on = lm.in_plant && wt_plant_live(a, st_in, t);
   double *ho = (double *)(a.ws + WT_WS_HEADER) + (size_t)wg * HO_ROWS * 32 + lane;
   if (!__any_sync(0xffffffffu, on)) {
     ho[HO_FL * 32] = __longlong_as_double(0ll);  // nothing running in this group
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_run_ker
     {
       lm.gi = lane / n;
       const long long pl = wg * gpw + lm.gi;
-      lm.in_plant = lm.gi < gpw && pl < a.P;
+      lm.in_plant = lm.gi < gpw && pl < wt_plant_count(a);
       lm.p = lm.in_plant ? (order ? order[pl] : (int)pl) : 0;
       lm.z = lm.in_plant ? lane - lm.gi * n : 0;
     }
@@ -310,7 +322,8 @@ __global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_run_ker
     const double *ho = (const double *)(a.ws + WT_WS_HEADER) + (size_t)wg * HO_ROWS * 32 + lane;
     const int fl_in = (int)__double_as_longlong(ho[HO_FL * 32]);
     const uint32_t st_in = a.status[p];
-    const bool live = lm.in_plant && !(st_in & WTS_HALT_MASK);
+    double t = a.time[p];
+    const bool live = lm.in_plant && wt_plant_live(a, st_in, t);
     if (__any_sync(0xffffffffu, live)) {
       // all loads of the group issued back to back
       double par[WTP_NPAR], bnd[WTB_NBND], hrow[HO_SELF_H + 1];
@@ -318,7 +331,6 @@ __global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_run_ker
       for (int k = 0; k < WTP_NPAR; ++k) par[k] = a.par[(size_t)k * P + p];
 #pragma unroll
       for (int k = 0; k < WTB_NBND; ++k) bnd[k] = a.bnd[bnd_stride ? (size_t)k * P + p : (size_t)k];
-      double t = a.time[p];
       double y0[3];
 #pragma unroll
       for (int v = 0; v < 3; ++v) y0[v] = a.y[((size_t)v * n + z) * P + p];
@@ -365,7 +377,8 @@ __global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_run_ker
         }
         if (z == 0) {
           if (adv) a.time[p] = t + a.dt;
-          a.status[p] = (uint32_t)sb | (or_status > 0 ? (st_in & ~(uint32_t)WTS_HALT_MASK) : 0u);
+          // (the deferred mark survives: only wt_defer_rejoin takes it off)
+          a.status[p] = (uint32_t)sb | (or_status > 0 ? (st_in & ~(uint32_t)WTS_SKIP_MASK) : 0u) | (st_in & (uint32_t)WTS_DEFERRED);
           if (adv && flow) flow[p] = lu.cget(CK_flow);
           if (counters) {
             // fire-and-forget reductions: a load-add-store here made the whole warp wait for eight loads
@@ -546,7 +559,7 @@ __global__ void __launch_bounds__(WT_STATS_TPB) wt_stats_partial_kernel(int P, i
   const double t_cl = shift_thr[3], t_ph_lo = shift_thr[4], t_ph_hi = shift_thr[5], t_T = shift_thr[6];
   double live = 0, halted = 0, e0 = 0, e1 = 0, e2 = 0;
   for (int p = lo + threadIdx.x; p < hi; p += WT_STATS_TPB) {
-    const bool h = (status[p] & WTS_HALT_MASK) != 0;
+    const bool h = (status[p] & WTS_SKIP_MASK) != 0;   // halted, or deferred (being caught up on the side stream)
     if (h) { halted += 1.0; continue; }
     live += 1.0;
     const double ph = y[((size_t)0 * n + (n - 1)) * P + p], cl = y[((size_t)1 * n + (n - 1)) * P + p],
@@ -565,7 +578,7 @@ __global__ void __launch_bounds__(WT_STATS_TPB) wt_stats_partial_kernel(int P, i
     const double c = row < n ? c0 : (row < 2 * n ? c1 : c2);
     double s1 = 0, s2 = 0;
     for (int p = lo + threadIdx.x; p < hi; p += WT_STATS_TPB) {
-      if (status[p] & WTS_HALT_MASK) continue;
+      if (status[p] & WTS_SKIP_MASK) continue;
       const double d = y[(size_t)row * P + p] - c;
       s1 += d;
       s2 += d * d;
@@ -746,6 +759,34 @@ __global__ void wt_sensor_window_stats_kernel(int P, int m, const double *hist, 
 }
 
 // ---------------------------------------------------------------------------------------
+// Deferral of budget-exhausted plants.  The reference never drops a plant for work (solve_ivp runs to the end,
+// reactor.py:476-490); the engine budgets the collocation solves of a plant-step.  Instead of
+// halting for good, plants that ran out of budget are COLLECTED into a device-side list, marked WTS_DEFERRED (ordinary
+// launches pass over them), caught up by launches over that list with a larger budget on a side stream while the
+// ensemble moves on, and REJOINED at the next block boundary.  Only a plant that exhausts the larger budget too (or
+// raises in the reference's sense, WTS_T_RANGE) stays halted.
+// ---------------------------------------------------------------------------------------
+__global__ void wt_defer_collect_kernel(int P, uint32_t *status, int32_t *list, int32_t *count, int cap) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const uint32_t st = status[p];
+  if ((st & WTS_WORK_LIMIT) && !(st & WTS_DEFERRED)) {
+    const int slot = atomicAdd(count, 1);
+    if (slot < cap) {   // (a full list leaves the plant halted)
+      list[slot] = p;
+      status[p] = (st & ~(uint32_t)WTS_WORK_LIMIT) | (uint32_t)WTS_DEFERRED;
+    }
+  }
+}
+__global__ void wt_defer_rejoin_kernel(uint32_t *status, const int32_t *list, int32_t *count, int cap) {
+  int c = *count;
+  c = c < cap ? c : cap;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) status[list[i]] &= ~(uint32_t)WTS_DEFERRED;
+  __syncthreads();
+  if (threadIdx.x == 0) *count = 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // Orchestrator: the reference's main loop turns three actuator commands per plant into
 // boundary conditions through two layers of zero-trust clamps (__main__.py:57-63 validate_flow_rate, :227-252
 // read_modbus_commands, :255-271 apply_boundary_conditions).  One thread per plant, in place on the boundary SoA.
@@ -901,7 +942,43 @@ int wt_advance(int P, int n, int n_steps, double dt, const double *par, const do
   a.P = P; a.ld = P; a.n = n; a.n_steps = n_steps; a.bnd_stride = bnd_stride; a.max_attempts = max_attempts;
   a.dt = dt; a.par = par; a.bnd = bnd; a.time = time; a.y = y; a.flow = flow; a.derived = derived;
   a.status = status; a.counters = counters; a.order = order; a.cost = cost; a.ws = (char *)workspace;
+  a.skip_mask = WTS_SKIP_MASK; a.count_dev = nullptr; a.t_stop = nullptr;
   return launch_step(a, (cudaStream_t)stream);
+}
+
+int wt_catch_up(int cap, int ld, int n, int n_steps, double dt, const double *par, const double *bnd, int bnd_stride,
+                double *time, double *y, double *flow, double *derived, uint32_t *status, int32_t *counters,
+                int max_attempts, const int32_t *list, const int32_t *count, const double *t_stop, void *workspace,
+                void *stream) {
+  int rc = check_common(cap, n);
+  if (rc) return rc;
+  if (!(dt > 0.0) || n_steps < 1 || ld < 1) return set_err(WT_ERR_BAD_ARG, "bad dt, n_steps or ld");
+  if (!par || !bnd || !time || !y || !status || !list || !count || !t_stop || !workspace)
+    return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  if (bnd_stride != 0 && bnd_stride != ld) return set_err(WT_ERR_BAD_ARG, "bnd_stride must be 0 or ld");
+  StepArgs a;
+  a.P = cap; a.ld = ld; a.n = n; a.n_steps = n_steps; a.bnd_stride = bnd_stride; a.max_attempts = max_attempts;
+  a.dt = dt; a.par = par; a.bnd = bnd; a.time = time; a.y = y; a.flow = flow; a.derived = derived;
+  a.status = status; a.counters = counters; a.order = list; a.cost = nullptr; a.ws = (char *)workspace;
+  a.skip_mask = WTS_HALT_MASK;   // the listed plants carry WTS_DEFERRED: that is what this launch is for
+  a.count_dev = count; a.t_stop = t_stop;
+  return launch_step(a, (cudaStream_t)stream);
+}
+
+int wt_defer_collect(int P, uint32_t *status, int32_t *list, int32_t *count, int cap, void *stream) {
+  if (P <= 0 || cap <= 0) return set_err(WT_ERR_BAD_ARG, "P and cap must be positive");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (!status || !list || !count) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  wt_defer_collect_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, status, list, count, cap);
+  return cuda_err(cudaGetLastError(), "wt_defer_collect_kernel launch");
+}
+
+int wt_defer_rejoin(uint32_t *status, const int32_t *list, int32_t *count, int cap, void *stream) {
+  if (cap <= 0) return set_err(WT_ERR_BAD_ARG, "cap must be positive");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (!status || !list || !count) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  wt_defer_rejoin_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(status, list, count, cap);
+  return cuda_err(cudaGetLastError(), "wt_defer_rejoin_kernel launch");
 }
 
 int wt_step(int P, int n, double dt, const double *par, const double *bnd, int bnd_stride, double *time,
@@ -1067,7 +1144,7 @@ __global__ void __launch_bounds__(WT_STATS_TPB) wt_sensor_stats_partial_kernel(i
   const double c = shift7[s];
   double nv = 0, s1 = 0, s2 = 0;
   for (int p = lo + threadIdx.x; p < hi; p += WT_STATS_TPB) {
-    if (plant_status[p] & WTS_HALT_MASK) continue;
+    if (plant_status[p] & WTS_SKIP_MASK) continue;
     const double v = value[(size_t)s * P + p];
     if (isfinite(v)) { const double d = v - c; nv += 1.0; s1 += d; s2 += d * d; }
     const int a = st[(size_t)s * P + p], b = ft[(size_t)s * P + p];
@@ -1369,6 +1446,7 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
     a.dt = dt; a.par = d_par + p0; a.bnd = bnd_stride ? d_bnd + p0 : d_bnd; a.time = d_t + p0; a.y = d_y + p0;
     a.flow = flow ? d_f + p0 : nullptr; a.derived = nullptr; a.status = d_s + p0; a.counters = nullptr;
     a.order = nullptr; a.cost = nullptr; a.ws = d_ws + (size_t)(c % NSTREAM) * b_ws;
+    a.skip_mask = WTS_SKIP_MASK; a.count_dev = nullptr; a.t_stop = nullptr;
     rc = launch_step(a, s);
     if (rc) return rc;
     cudaMemcpyAsync(time + p0, d_t + p0, wb, cudaMemcpyDeviceToHost, s);

@@ -40,9 +40,10 @@ enum {
 };
 enum {
   WTS_SOLVER_FAILED = 1, WTS_T_RANGE = 2, WTS_CLIP_PH = 4, WTS_CLIP_CL = 8, WTS_CLIP_T = 16,
-  WTS_NONFINITE = 32, WTS_T_RANGE_DERIVED = 64, WTS_WORK_LIMIT = 128
+  WTS_NONFINITE = 32, WTS_T_RANGE_DERIVED = 64, WTS_WORK_LIMIT = 128, WTS_DEFERRED = 256
 };
 #define WTS_HALT_MASK (WTS_T_RANGE | WTS_WORK_LIMIT)
+#define WTS_SKIP_MASK (WTS_HALT_MASK | WTS_DEFERRED)   // what an ordinary launch passes over
 enum {
   WTC_NFEV = 0, WTC_NJEV, WTC_NLU, WTC_NSTEPS, WTC_NNEWTON, WTC_NREJECT, WTC_NNEWTON_FAIL,
   WTC_JAC_RETRY, WTC_NCNT

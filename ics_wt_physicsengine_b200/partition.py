@@ -181,6 +181,12 @@ class PipelinedShard:
         self._sum = torch.zeros(self.stats_parts[0].size, dtype=torch.float64, device=self.device)
         self._stack = torch.zeros((len(self.engines), self.stats_parts[0].size), dtype=torch.float64, device=self.device)
         self._graph = None
+        # side streams of the deferral (PlantEnsemble(catch_up_attempts=...)): catch-up launches of one block overlap the
+        # ordinary steps of the next
+        self.defer = bool(self.engines[0].catch_up_attempts > 0)
+        if self.defer:
+            with torch.cuda.device(self.device):
+                self.side = [torch.cuda.Stream(device=self.device) for _ in self.engines]
         self.fork()
 
     def fork(self) -> None:
@@ -208,6 +214,41 @@ class PipelinedShard:
                 e.step(dt, self.bnd[i])
                 if self.suites is not None and read_time is not None:
                     self.suites[i].read(e.state, read_time)
+
+    def _block(self, n_steps: int, dt: float, read) -> None:
+        """One block of steps of every sub-ensemble on its stream; ``read(i)`` reads sub-ensemble i's sensors.  With
+        deferral: the plants that ran out of budget during the PREVIOUS block are collected at the start, caught up on
+        the side stream (larger budget, until the end time of THIS block) while this block's steps run, and rejoined at
+        its end -- every plant is time-aligned again at each block boundary."""
+        for i, (e, s) in enumerate(zip(self.engines, self.streams)):
+            with torch.cuda.stream(s):
+                if self.defer:
+                    e._t_stop.add_(n_steps * dt)
+                    e.collect_deferred()
+                    self.side[i].wait_stream(s)
+                    with torch.cuda.stream(self.side[i]):
+                        e.catch_up(2 * n_steps, dt, self.bnd[i])
+                for _ in range(n_steps):
+                    e.step(dt, self.bnd[i])
+                    if self.suites is not None:
+                        read(i)
+                if self.defer:
+                    s.wait_stream(self.side[i])
+                    e.rejoin_deferred()
+
+    def start_deferral(self, t_now: float) -> None:
+        """The stop time of the catch-up launches starts at the ensemble's current time (then + n_steps dt per block)."""
+        for e in self.engines:
+            e._t_stop.fill_(float(t_now))
+
+    def block(self, n_steps: int, dt: float, t_first: float) -> None:
+        """``n_steps`` eager steps (+ sensor reads at t_first, t_first + dt, ...) with the block-wise deferral."""
+        k = [0] * len(self.engines)
+
+        def read(i):
+            self.suites[i].read(self.engines[i].state, t_first + k[i] * dt)
+            k[i] += 1
+        self._block(n_steps, dt, read)
 
     def advance(self, n_steps: int, dt: float) -> None:
         for i, (e, s) in enumerate(zip(self.engines, self.streams)):
@@ -250,12 +291,7 @@ class PipelinedShard:
         with torch.cuda.stream(cap):
             with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
                 self.fork()
-                for _ in range(n_steps):
-                    for i, (e, s) in enumerate(zip(self.engines, self.streams)):
-                        with torch.cuda.stream(s):
-                            e.step(dt, self.bnd[i])
-                            if self.suites is not None:
-                                self.suites[i].read_clocked()
+                self._block(n_steps, dt, lambda i: self.suites[i].read_clocked())
                 if with_stats:
                     self.local_stats()
                 self.synchronize()
@@ -293,3 +329,7 @@ class PipelinedShard:
     def halted(self) -> int:
         self.synchronize()
         return int(sum(int(((e.status & _lib.ST_HALT_MASK) != 0).sum()) for e in self.engines))
+
+    def deferred(self) -> int:
+        self.synchronize()
+        return int(sum(int(((e.status & _lib.ST_DEFERRED) != 0).sum()) for e in self.engines))

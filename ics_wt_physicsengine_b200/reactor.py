@@ -186,7 +186,7 @@ class PlantEnsemble:
 
     def __init__(self, cfg: Union[np.ndarray, Sequence[ReactorConfiguration], Ensemble], n_zones: Optional[int] = None,
                  device: Union[str, torch.device, None] = None, max_attempts: int = DEFAULT_MAX_ATTEMPTS,
-                 validate: bool = True, sort_every: int = 0):
+                 validate: bool = True, sort_every: int = 0, catch_up_attempts: int = 0):
         _lib.require_device()
         init = None
         if isinstance(cfg, Ensemble):
@@ -207,6 +207,9 @@ class PlantEnsemble:
         self.n_plants = int(cfg.shape[0])
         self.cfg = cfg
         self.max_attempts = int(max_attempts)
+        # > 0: plants that exhaust max_attempts are not halted but DEFERRED: collect_deferred / catch_up / rejoin_deferred
+        # continue them with this larger budget (partition.PipelinedShard runs the three per block of steps)
+        self.catch_up_attempts = int(catch_up_attempts)
         # scheduling only (results do not depend on it): every `sort_every` launches the plants are
         # re-ordered by the work of their last step, most expensive first (0 = natural order)
         self.sort_every = int(sort_every)
@@ -229,6 +232,13 @@ class PlantEnsemble:
             self._order = torch.arange(P, dtype=torch.int32, device=self.device) if self.sort_every > 0 else None
             self._cost = torch.zeros(P, dtype=torch.int32, device=self.device) if self.sort_every > 0 else None
             self._bins = torch.zeros(1024, dtype=torch.int32, device=self.device) if self.sort_every > 0 else None
+            if self.catch_up_attempts > 0:
+                cap = max(1024, P // 64)
+                self._defer_cap = cap
+                self._defer_list = torch.zeros(cap, dtype=torch.int32, device=self.device)
+                self._defer_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+                self._t_stop = torch.zeros(1, dtype=torch.float64, device=self.device)
+                self._ws_defer = torch.empty(int(_lib.lib().wt_step_workspace_bytes(cap, n)), dtype=torch.uint8, device=self.device)
             # device workspace of the step (work queue + hand-off rows between its two launches), reused by every step
             self._ws = torch.empty(int(_lib.lib().wt_step_workspace_bytes(P, n)), dtype=torch.uint8, device=self.device)
         self.state = EnsembleState(self._y, self._derived, self._time, self._flow)
@@ -322,6 +332,34 @@ class PlantEnsemble:
         _lib.check(rc, "wt_advance")
         self._launches += 1
         return self.state
+
+    # ---- deferral of budget-exhausted plants (include/wt_b200.h: wt_defer_collect / wt_catch_up / wt_defer_rejoin) ----
+    def collect_deferred(self) -> None:
+        """Plants that ran out of ``max_attempts`` -> the deferred list (they keep their state, ordinary steps pass
+        over them until ``rejoin_deferred``)."""
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().wt_defer_collect(self.n_plants, _ptr(self._status), _ptr(self._defer_list), _ptr(self._defer_count),
+                                             self._defer_cap, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "wt_defer_collect")
+
+    def catch_up(self, n_steps: int, dt: float, boundary: BoundaryLike) -> None:
+        """Up to ``n_steps`` x step(dt) for the deferred plants with the budget ``catch_up_attempts``, each only until its
+        time reaches the device scalar ``_t_stop``.  Launch it on a side stream: it only touches the listed plants."""
+        bnd, stride = self._boundary(boundary)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().wt_catch_up(self._defer_cap, self.n_plants, self.n_zones, int(n_steps), float(dt), _ptr(self._par),
+                                        _ptr(bnd), stride, _ptr(self._time), _ptr(self._y), _ptr(self._flow), _ptr(self._derived),
+                                        _ptr(self._status), _ptr(self._counters), self.catch_up_attempts, _ptr(self._defer_list),
+                                        _ptr(self._defer_count), _ptr(self._t_stop), _ptr(self._ws_defer),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "wt_catch_up")
+
+    def rejoin_deferred(self) -> None:
+        """After the catch-up (stream order): the listed plants take part in the ordinary steps again."""
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().wt_defer_rejoin(_ptr(self._status), _ptr(self._defer_list), _ptr(self._defer_count), self._defer_cap,
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "wt_defer_rejoin")
 
     def derivatives(self, boundary: BoundaryLike, y: Optional[torch.Tensor] = None):
         """Batched IntegratedCSTR.derivatives (reactor.py:272-448) -> (dy [3,n,P], bad [P])."""

@@ -54,10 +54,14 @@ enum {
   WT_ST_CLIP_T = 1u << 4,          /* reactor.py:538-541 */
   WT_ST_NONFINITE = 1u << 5,
   WT_ST_T_RANGE_DERIVED = 1u << 6, /* ValueError in _update_derived_state (reactor.py:521-524) */
-  WT_ST_WORK_LIMIT = 1u << 7       /* engine policy, not reference behaviour: attempt budget
-                                      exhausted, state untouched; plant HALTS */
+  WT_ST_WORK_LIMIT = 1u << 7,      /* engine policy, not reference behaviour: attempt budget
+                                      exhausted, state untouched; plant HALTS (unless deferred, below) */
+  WT_ST_DEFERRED = 1u << 8         /* the plant ran out of budget and is being caught up by wt_catch_up with a larger
+                                      one: ordinary launches, statistics and sensors' consumers pass over it until
+                                      wt_defer_rejoin */
 };
 #define WT_ST_HALT_MASK (WT_ST_T_RANGE | WT_ST_WORK_LIMIT)
+#define WT_ST_SKIP_MASK (WT_ST_HALT_MASK | WT_ST_DEFERRED)
 /* solver path counters, accumulated per plant */
 enum {
   WT_CNT_NFEV = 0, WT_CNT_NJEV, WT_CNT_NLU, WT_CNT_NSTEPS, WT_CNT_NNEWTON, WT_CNT_NREJECT,
@@ -114,6 +118,24 @@ int wt_advance(int P, int n_zones, int n_steps, double dt, const double *par_dev
                double *flow_rate_dev, double *derived_dev, uint32_t *status_dev,
                int32_t *counters_dev, int max_attempts, const int32_t *order_dev,
                int32_t *cost_dev, void *workspace_dev, void *stream);
+
+/* Deferral of budget-exhausted plants (the reference never drops a plant for work: solve_ivp runs to the end and a
+ * failure only logs, reactor.py:476-490).
+ *   wt_defer_collect  plants with WT_ST_WORK_LIMIT are appended to list_dev (capacity cap; count_dev must be 0 or hold
+ *                     the number of entries already there) and re-marked WT_ST_DEFERRED: wt_step / wt_advance pass
+ *                     over them, nothing else touches their state.
+ *   wt_catch_up       n_steps x step(dt) for the listed plants only, with their own (larger) budget, each plant only
+ *                     until its time reaches *t_stop_dev; meant for a side stream while the ensemble moves on.  Arrays
+ *                     are the ensemble's (row stride ld = its plant count); workspace: wt_step_workspace_bytes(cap, n).
+ *                     A plant that exhausts this budget too gets WT_ST_WORK_LIMIT and stays halted.
+ *   wt_defer_rejoin   after the catch-up has finished (stream order): takes WT_ST_DEFERRED off the listed plants and
+ *                     empties the list. */
+int wt_defer_collect(int P, uint32_t *status_dev, int32_t *list_dev, int32_t *count_dev, int cap, void *stream);
+int wt_catch_up(int cap, int ld, int n_zones, int n_steps, double dt, const double *par_dev, const double *bnd_dev,
+                int bnd_stride, double *time_dev, double *y_dev, double *flow_rate_dev, double *derived_dev,
+                uint32_t *status_dev, int32_t *counters_dev, int max_attempts, const int32_t *list_dev,
+                const int32_t *count_dev, const double *t_stop_dev, void *workspace_dev, void *stream);
+int wt_defer_rejoin(uint32_t *status_dev, const int32_t *list_dev, int32_t *count_dev, int cap, void *stream);
 
 /* IntegratedCSTR.derivatives(t, y, boundary) for P plants (reactor.py:272-448).
  * dy has the layout of y; bad[p] != 0 where the reference would raise ValueError. */

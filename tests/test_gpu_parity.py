@@ -518,3 +518,66 @@ def test_two_devices_in_one_process():
     torch.cuda.synchronize(0)
     torch.cuda.synchronize(1)
     assert np.array_equal(a.state_numpy(), b.state_numpy()) and np.array_equal(a.status.cpu().numpy(), b.status.cpu().numpy())
+
+
+def test_deferred_plants_are_continued_and_equal_a_run_with_the_larger_budget(oracle):
+    """Budget-exhausted plants are not dropped: with a deliberately tiny main budget (8 collocation solves per
+    plant-step, so that thousands of plant-steps overrun it) and a catch-up budget of 2,048 on the side stream, every
+    plant that rejoins carries exactly the state of a run in which ALL plants had the larger budget; a plant that needs
+    65..2,000 collocation solves for one step -- halted for good in round 1 -- equals the oracle without any budget."""
+    from ics_wt_physicsengine_b200 import _lib
+    from ics_wt_physicsengine_b200.partition import PipelinedShard
+    P, n, B, blocks, BIG = 40009, 10, 5, 4, 2048
+    e = ens.config5(P, n)
+    ref = PipelinedShard(e, parts=2, max_attempts=BIG)
+    dfr = PipelinedShard(e, parts=2, max_attempts=8, catch_up_attempts=BIG)
+    dfr.start_deferral(0.0)
+    n_deferred_seen = 0
+    for b in range(blocks):
+        for _ in range(B):
+            ref.step(1.0)
+        dfr.block(B, 1.0, t_first=float(b * B))
+        n_deferred_seen += dfr.deferred()
+    dfr.block(B, 1.0, t_first=float(blocks * B))       # one more block: the plants deferred in the last one rejoin
+    for _ in range(B):
+        ref.step(1.0)
+    torch.cuda.synchronize()
+    yr = np.concatenate([x.state_numpy() for x in ref.engines]); yd = np.concatenate([x.state_numpy() for x in dfr.engines])
+    tr = np.concatenate([x.state.time.cpu().numpy() for x in ref.engines]); td = np.concatenate([x.state.time.cpu().numpy() for x in dfr.engines])
+    sr = np.concatenate([x.status.cpu().numpy() for x in ref.engines]); sd = np.concatenate([x.status.cpu().numpy() for x in dfr.engines])
+    assert n_deferred_seen > 100, "the tiny budget must actually defer plants"
+    settled = ((sd & _lib.ST_SKIP_MASK) == 0) & ((sr & _lib.ST_HALT_MASK) == 0)   # not deferred in the very last block, not halted
+    assert settled.mean() > 0.99
+    assert np.array_equal(td[settled], tr[settled]) and np.all(tr[settled] == (blocks + 1) * B)
+    assert np.array_equal(yd[settled], yr[settled]), "a continued plant must equal the run with the larger budget bit for bit"
+    # plants halted in the reference run (monsters beyond 2,048 solves) are halted here too, nothing else is
+    assert ((sd & _lib.ST_WORK_LIMIT) != 0).sum() <= ((sr & _lib.ST_WORK_LIMIT) != 0).sum() + (sd & _lib.ST_DEFERRED != 0).sum()
+
+    # a step that needs 65 .. 2,000 collocation solves, against the oracle WITHOUT a budget
+    e2 = ens.config5(131072, n)
+    eng = PlantEnsemble(e2, max_attempts=64)
+    found = None
+    for k in range(40):
+        y_before, t_before = eng.state_numpy(), eng.state.time.cpu().numpy().copy()
+        eng.step(1.0, e2.bnd)
+        hit = np.nonzero(eng.status.cpu().numpy() & _lib.ST_WORK_LIMIT)[0]
+        for p in hit:
+            one = PlantEnsemble(e2.slice(slice(int(p), int(p) + 1)), max_attempts=2000)
+            one.set_state(y_before[p:p + 1, :n], y_before[p:p + 1, n:2 * n], y_before[p:p + 1, 2 * n:], time=t_before[p:p + 1])
+            one.step(1.0, e2.bnd[p:p + 1])
+            c = one.counters.cpu().numpy()[:, 0]
+            if int(one.status[0]) & _lib.ST_WORK_LIMIT == 0 and c[3] + c[5] + c[6] > 64:
+                found = (int(p), y_before[p].copy(), float(t_before[p]), one.state_numpy()[0], int(c[3] + c[5] + c[6]))
+                break
+        if found:
+            break
+    if found is None:
+        pytest.skip("no plant-step with 65..2,000 collocation solves in this sample")
+    p, y0, t0, got, attempts = found
+    oracle.set_max_attempts(0)
+    par = np.ascontiguousarray(eng.par_host[p:p + 1])
+    yo, to = y0[None, :].copy(), np.array([t0])
+    oracle.step_batch(par, np.ascontiguousarray(e2.bnd[p:p + 1]), n, to, yo, dt=1.0)
+    r, excused = check_step_parity(oracle, got[None, :], yo, par, np.ascontiguousarray(e2.bnd[p:p + 1]), n, np.array([t0]), y0[None, :], 1.0, 0,
+                                   tol=TOL, what=f"plant {p} ({attempts} collocation solves)")
+    print(f"plant {p}: {attempts} collocation solves for one step, error vs the unbudgeted oracle {r[0]:.2e}, excused: {bool(excused)}")

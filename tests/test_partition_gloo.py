@@ -15,7 +15,7 @@ from ics_wt_physicsengine_b200.partition import (StatsSpec, finalize_stats, shar
 
 def local_stats_numpy(y_pn, status, n, spec: StatsSpec) -> np.ndarray:
     """y_pn: [P, 3n] species-major.  Same layout as the wt_stats kernel."""
-    live = (status & (2 | 128)) == 0
+    live = (status & (2 | 128 | 256)) == 0   # not halted, not deferred
     v = np.zeros(stats_size(n))
     v[0], v[1] = live.sum(), (~live).sum()
     yl = y_pn[live]
@@ -33,7 +33,7 @@ def local_stats_numpy(y_pn, status, n, spec: StatsSpec) -> np.ndarray:
 def sensor_stats_numpy(value_7p, status_7p, fault_7p, plant_status, spec: StatsSpec) -> np.ndarray:
     """Numpy restatement of the wt_sensor_stats layout (include/wt_b200.h): per sensor valid count, shifted sum,
     shifted sum of squares over the finite readings, SensorStatus (12) and SensorFault (7) histograms; live plants."""
-    live = (plant_status & (2 | 128)) == 0
+    live = (plant_status & (2 | 128 | 256)) == 0
     out = np.zeros((7, 22))
     for s in range(7):
         v = value_7p[s][live]
