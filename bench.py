@@ -168,6 +168,9 @@ def main():
     ap.add_argument("--no-sensors", action="store_true", help="physics only (BASELINE configs[1]-style step)")
     ap.add_argument("--streams", type=int, default=0, help="independent sub-ensembles (CUDA streams) per GPU; 0 = by shard size")
     ap.add_argument("--stats-every", type=int, default=10)
+    ap.add_argument("--catch-up-attempts", type=int, default=0,
+                    help="budget of the side-stream catch-up of plants that exhaust --max-attempts (0 = halt them for good; "
+                         "measured with 2048: 35.4 instead of 15.1 ms/step at N=1, DESIGN.md section 7)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -200,7 +203,7 @@ def main():
     parts = args.streams if args.streams > 0 else max(1, min(4, P // 65536))
     sensors_on = not args.no_sensors
     shard = PipelinedShard(e, parts=parts, device=dev, plant0=lo, sensor_seed=20260004 if sensors_on else None,
-                           max_attempts=args.max_attempts, sort_every=args.sort_every)
+                           max_attempts=args.max_attempts, sort_every=args.sort_every, catch_up_attempts=args.catch_up_attempts)
     fp64_peak = _lib.measure_fp64_peak() if rank == 0 else 0.0
     # Sensors: calibrated at t = -2000 s, then 100 reads of the initial state at t = -100 .. -1 s: when the timed region
     # starts every sensor is past its warm-up (10 / 30 / 60 / 300 / 1800 s) and the four 100-slot delay rings per plant
@@ -231,6 +234,8 @@ def main():
         while sim["k"] % block:
             eager_steps(1)
         shard.synchronize()
+        if shard.defer:
+            shard.start_deferral(float(sim["k"]))
         shard.capture(block, DT, t_next=float(sim["k"]), with_stats=True)
         shard.replay()            # one untimed replay (graph upload)
         sim["k"] += block
@@ -267,6 +272,7 @@ def main():
     cnt_sum = agg[:8].cpu().numpy()
     timed_plant_steps = float(agg[8])
     halted_after = shard.halted()
+    deferred_after = shard.deferred() if shard.defer else 0
     value = timed_plant_steps * N_ZONES / (ms * 1e-3)
     stats_vec = shard._sum.cpu().numpy().copy()
 
@@ -382,7 +388,11 @@ def main():
             "sensor_suite": shard.suites is not None,
             "sensor_state": "warm (calibrated at t=-2000 s), delay rings full" if sensors_on else None,
             "sort_every": args.sort_every, "sub_ensembles_per_gpu": nparts,
-            "max_attempts": args.max_attempts, "plants_halted_at_end_rank0": halted_after,
+            "max_attempts": args.max_attempts, "catch_up_attempts": args.catch_up_attempts,
+            "deferral": ("plants that exhaust max_attempts are collected at the next block boundary, continued with catch_up_attempts "
+                         "on a side stream during that block and rejoined at its end (inside the graph)") if shard.defer and use_graph
+                        else "off (eager launches)" if shard.defer else "off",
+            "plants_halted_at_end_rank0": halted_after, "plants_deferred_at_end_rank0": deferred_after,
             "halted_fraction_rank0": halted_after / P,
             "stats_allreduce_every": block, "stats_vector_doubles": int(stats_vec.size),
         },

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "../../include/wt_b200.h"
@@ -440,52 +441,55 @@ __global__ void wt_derivatives_kernel(int P, int n, const double *par_, const do
   }
 }
 
+__device__ int wt_ph_queues[64];
 // chemistry.py:193-330.  The Newton-Raphson iteration counts of independent buffer systems range from 1 to 100
-// (BASELINE configs[3]: mode 6-14, 15 % run into the 100-iteration limit), so one thread per system leaves 70 % of
-// the lanes of a warp idle (ncu, round 2: 9.6 of 32 threads active per instruction).  Here a warp owns a CHUNK of
-// systems and every lane that finishes one takes the next from the chunk (ballot + popc, no atomics): lanes stay busy
-// until the chunk is empty.  The arithmetic of a solve is unchanged, so results are bit-identical to the
-// one-thread-per-system kernel.
-#define WT_PH_CHUNK 256
+// (BASELINE configs[3]: mode 6-14, 15 % run into the 100-iteration limit and hold half of all iterations), so one thread
+// per system leaves 70 % of the lanes of a warp idle (ncu, round 2: 9.6 of 32 threads active per instruction, FP64 pipe
+// 61 % busy on them).  Here the warps are persistent and every lane that finishes a solve takes the next system from a
+// global queue (one warp-aggregated atomicAdd per refill): lanes stay busy until the queue is empty and the tail is one
+// solve.  The arithmetic of a solve is unchanged.
 __global__ void __launch_bounds__(128) wt_calc_ph_kernel(int P, const double *alk, const double *ct, const double *temp,
-                                                           const double *guess, double *ph, int32_t *iters, int32_t *status) {
+                                                           const double *guess, double *ph, int32_t *iters, int32_t *status,
+                                                           int *queue) {
   const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long lo = warp * WT_PH_CHUNK;
-  if (lo >= P) return;
-  const int hi = (int)((lo + WT_PH_CHUNK < P) ? lo + WT_PH_CHUNK : P);
-  int cursor = (int)lo;          // next unassigned system of the chunk (warp-uniform)
-  bool busy = false;
+  bool busy = false, drained = false;
   int i = 0, it = 0;
   double pH = 0.0, Kw = 0.0, Ka1 = 0.0, Ka2 = 0.0, C_T = 0.0, alk_eq = 0.0;
   for (;;) {
-    // ---- idle lanes take the next systems of the chunk
+    // ---- idle lanes take the next systems of the queue.  The set-up of a solve (three transcendentals) is as long as
+    // two or three iterations, so it only runs when at least half of the lanes are idle (or none is busy).
     const unsigned need = __ballot_sync(0xffffffffu, !busy);
-    if (!busy) {
-      const int idx = cursor + __popc(need & ((1u << lane) - 1u));
-      if (idx < hi) {
-        const double tc = temp[idx];
-        if (tc < 0.0 || tc > 100.0) {  // thermodynamics.py:146-157 via chemistry.py:118
-          ph[idx] = nan("");
-          iters[idx] = 0;
-          status[idx] = 3;
-        } else {
-          const double TK = tc + 273.15;
-          Kw = 1.0e-14 * exp((55900.0 / 8.314) * (1.0 / 298.15 - 1.0 / TK));
-          Ka1 = exp10(-(6.35 + (-0.008) * (tc - 25.0)));
-          Ka2 = exp10(-(10.33 + (-0.008) * (tc - 25.0)));
-          C_T = ct[idx] / 1000.0;
-          alk_eq = alk[idx] / 50000.0;
-          pH = guess[idx];
-          i = idx;
-          it = 0;
-          busy = true;
+    const bool refill = !drained && (__popc(need) >= 16 || need == 0xffffffffu);
+    if (refill) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(queue, __popc(need));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      drained = base + __popc(need) >= P;
+      if (!busy) {
+        const int idx = base + __popc(need & ((1u << lane) - 1u));
+        if (idx < P) {
+          const double tc = temp[idx];
+          if (tc < 0.0 || tc > 100.0) {  // thermodynamics.py:146-157 via chemistry.py:118
+            ph[idx] = nan("");
+            iters[idx] = 0;
+            status[idx] = 3;
+          } else {
+            const double TK = tc + 273.15;
+            Kw = 1.0e-14 * exp((55900.0 / 8.314) * (1.0 / 298.15 - 1.0 / TK));
+            Ka1 = exp10(-(6.35 + (-0.008) * (tc - 25.0)));
+            Ka2 = exp10(-(10.33 + (-0.008) * (tc - 25.0)));
+            C_T = ct[idx] / 1000.0;
+            alk_eq = alk[idx] / 50000.0;
+            pH = guess[idx];
+            i = idx;
+            it = 0;
+            busy = true;
+          }
         }
       }
     }
-    cursor += __popc(need);
     if (!__any_sync(0xffffffffu, busy)) {
-      if (cursor >= hi) break;
+      if (drained) break;
       continue;
     }
     // ---- one Newton-Raphson iteration of every busy lane (chemistry.py:291-330)
@@ -1007,8 +1011,24 @@ int wt_calc_ph(int P, const double *alk, const double *ct, const double *temp, c
   if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
   if (!alk || !ct || !temp || !guess || !ph || !iters || !status) return set_err(WT_ERR_BAD_ARG, "null device pointer");
   const int tpb = 128;
-  const long long warps = ((long long)P + WT_PH_CHUNK - 1) / WT_PH_CHUNK;   // a warp per chunk of systems
-  wt_calc_ph_kernel<<<(unsigned)((warps * 32 + tpb - 1) / tpb), tpb, 0, (cudaStream_t)stream>>>(P, alk, ct, temp, guess, ph, iters, status);
+  DevInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  // persistent warps: 8 blocks per SM (fewer when there are fewer systems than lanes); the queue counter is a
+  // stream-ordered allocation, so concurrent calls on different streams do not share it
+  long long blocks = (long long)di.sms * 8;
+  const long long want = ((long long)P / 2 + tpb - 1) / tpb;   // at least ~2 systems per lane
+  if (blocks > want) blocks = want < 1 ? 1 : want;
+  // the queue counter: one of 64 device words handed out round robin, so that calls in flight on different streams
+  // do not share one (a stream-ordered allocation per call cost 12 ms with the default pool settings)
+  static std::atomic<unsigned> next_slot{0};
+  int *queues = nullptr;
+  cudaError_t e = cudaGetSymbolAddress((void **)&queues, wt_ph_queues);
+  if (e != cudaSuccess) return cuda_err(e, "cudaGetSymbolAddress");
+  int *queue = queues + (next_slot.fetch_add(1) % 64);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(queue, 0, sizeof(int), st);
+  wt_calc_ph_kernel<<<(unsigned)blocks, tpb, 0, st>>>(P, alk, ct, temp, guess, ph, iters, status, queue);
   return cuda_err(cudaGetLastError(), "wt_calc_ph_kernel launch");
 }
 
