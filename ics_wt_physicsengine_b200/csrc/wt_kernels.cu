@@ -1367,18 +1367,58 @@ int wt_cost_order(int P, const int32_t *cost_dev, int32_t *order_dev, int32_t *b
   return cuda_err(cudaGetLastError(), "wt_cost_order launch");
 }
 
-// Host-buffer path: per device, one workspace grown on demand, three copy/compute streams, one event, and the
-// shape whose constants are resident.  One call at a time per device (the context is locked for the call).
-enum { WT_HOST_NSTREAM = 3 };
+// Host-buffer path: per device, one workspace grown on demand, one copy-in stream, one copy-out stream, three
+// compute streams, a pool of events, and the shape whose constants are resident.  One call at a time per device
+// (the context is locked for the call).
+enum { WT_HOST_NCOMPUTE = 3, WT_HOST_MAX_SLABS = 64 };
 struct HostCtx {
   std::mutex mu;
   size_t cap_bytes;
   char *dev;
-  cudaStream_t st[WT_HOST_NSTREAM];
-  cudaEvent_t ev;
+  cudaStream_t s_in, s_out, s_k[WT_HOST_NCOMPUTE];
+  cudaEvent_t ev_in[WT_HOST_MAX_SLABS], ev_k[WT_HOST_MAX_SLABS];
+  bool ready;
   int res_P, res_n;
 };
 static HostCtx g_host[WT_MAX_DEVICES];
+
+// Slab schedule of one call: plants per slab.  A pipeline over EQUAL slabs pays the upload of its first slab and the
+// download of its last one in the open, and small slabs make short launches (a launch of 32,768 plants runs the step
+// kernels at 0.73 of the rate of a 262,144-plant launch: VERDICT round 1).  So the slabs ramp up from `lo` plants
+// (a 16,384-plant upload takes ~0.1 ms), double up to `hi`, stay there, and ramp down again at the end.
+static int wt_host_slab_plan(int P, int *sizes) {
+  int lo = 16384, hi = P / 4;  // (a 131,072-plant shard of an 8-GPU run: 16k, 3 x 32k, 16k)
+  if (hi > 131072) hi = 131072;
+  if (hi < 2 * lo) hi = 2 * lo;
+  if (const char *e = getenv("WT_B200_HOST_SLAB_MIN")) lo = atoi(e);
+  if (const char *e = getenv("WT_B200_HOST_SLAB_MAX")) hi = atoi(e);
+  if (lo < 96) lo = 96;
+  lo = (lo + 31) & ~31;
+  if (hi < lo) hi = lo;
+  if (const char *e = getenv("WT_B200_HOST_SLABS")) {  // tuning runs: this many equal slabs
+    int k = atoi(e);
+    if (k < 1) k = 1;
+    if (k > WT_HOST_MAX_SLABS) k = WT_HOST_MAX_SLABS;
+    const int per = ((P + k - 1) / k + 31) & ~31;
+    int c = 0;
+    for (int p0 = 0; p0 < P; p0 += per) sizes[c++] = (P - p0 < per) ? P - p0 : per;
+    return c;
+  }
+  int head[16], nh = 0;
+  long long ramp = 0;
+  for (int sz = lo; sz < hi && nh < 16 && 2 * (ramp + sz) <= P / 2; sz *= 2) { head[nh++] = sz; ramp += sz; }
+  const long long mid = (long long)P - 2 * ramp;
+  int nm = (int)((mid + hi - 1) / hi);
+  if (nm < 1) nm = 1;
+  while (2 * nh + nm > WT_HOST_MAX_SLABS) ++hi, nm = (int)((mid + hi - 1) / hi);
+  const int per = (int)(((mid + nm - 1) / nm + 31) & ~31ll);
+  int c = 0;
+  for (int i = 0; i < nh; ++i) sizes[c++] = head[i];
+  long long left = mid;
+  for (int i = 0; i < nm && left > 0; ++i) { const int w = left < per ? (int)left : per; sizes[c++] = w; left -= w; }
+  for (int i = nh - 1; i >= 0; --i) sizes[c++] = head[i];
+  return c;
+}
 
 int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, int bnd_stride, double *time,
                  double *y, double *flow, uint32_t *status, int max_attempts, int flags) {
@@ -1387,26 +1427,25 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
   if (!par || !bnd || !time || !y || !status) return set_err(WT_ERR_BAD_ARG, "null host pointer");
   if (bnd_stride != 0 && bnd_stride != P) return set_err(WT_ERR_BAD_ARG, "bnd_stride must be 0 or P");
   if (!(dt > 0.0)) return set_err(WT_ERR_BAD_ARG, "dt must be positive");
-  // Pipelined over column slabs of the SoA arrays: slab c's H2D copies, its kernels and its D2H copies go to
-  // stream c % 3, so the copies of one slab overlap the kernels of another (PCIe is full duplex and the
-  // device has separate copy engines per direction).  A slab of plants is a column range of every row:
-  // 2-D copies with the row pitch P.  Plants are independent, so slabs need no ordering among themselves.
-  // Slab count: at least 12 (four rounds over the three streams keep every engine busy even for the 131,072-plant
-  // shard of an 8-GPU run), at most 32, about 32,768 plants (9 MB of state) each in between.
-  enum { NSTREAM = WT_HOST_NSTREAM };
-  int slabs = P / 32768;
-  if (slabs < 12) slabs = 12;
-  if (slabs > 32) slabs = 32;
-  if (const char *e = getenv("WT_B200_HOST_SLABS")) slabs = atoi(e);  // tuning runs
-  if (slabs > (P + 95) / 96) slabs = (P + 95) / 96;
-  if (slabs < 1) slabs = 1;
-  const int per = ((P + slabs - 1) / slabs + 31) & ~31;  // plants per slab, a multiple of the warp width
+  // Pipelined over column slabs of the SoA arrays (a slab of plants is a column range of every row: 2-D copies with
+  // the row pitch P; plants are independent, so slabs need no ordering among themselves).  Three stages on their own
+  // streams, chained per slab by events:
+  //   copy-in stream   every H2D copy, slab after slab (one DMA engine direction, always busy)
+  //   compute streams  slab c's two step kernels on stream c % 3 once its upload has landed; consecutive slabs sit on
+  //                    different streams, so the persistent warps of the next launch take over the SMs as the blocks
+  //                    of the previous one drain
+  //   copy-out stream  every D2H copy, as the kernels finish (PCIe is full duplex: the other DMA direction)
+  // No stage waits for a later one, so nothing but the first upload and the last download is exposed.
+  int sizes[WT_HOST_MAX_SLABS];
+  const int slabs = wt_host_slab_plan(P, sizes);
+  int per = 0;
+  for (int c = 0; c < slabs; ++c) per = sizes[c] > per ? sizes[c] : per;
   const size_t Pz = (size_t)P;
   const size_t b_par = WT_NPAR * Pz * 8, b_bnd = WT_NBND * (bnd_stride ? Pz : 1) * 8, b_t = Pz * 8,
                b_y = 3 * (size_t)n * Pz * 8, b_f = Pz * 8, b_s = Pz * 4;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t b_ws = al(wt_step_workspace_bytes(per, n));  // one step workspace per stream
-  const size_t total = al(b_par) + al(b_bnd) + al(b_t) + al(b_y) + al(b_f) + al(b_s) + NSTREAM * b_ws;
+  const size_t b_ws = al(wt_step_workspace_bytes(per, n));  // one step workspace per compute stream
+  const size_t total = al(b_par) + al(b_bnd) + al(b_t) + al(b_y) + al(b_f) + al(b_s) + WT_HOST_NCOMPUTE * b_ws;
   int dev = 0;
   {
     cudaError_t e = cudaGetDevice(&dev);
@@ -1435,50 +1474,55 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
   const bool up_par = !(flags & 1) || g_ws.res_P != P || g_ws.res_n != n;
   g_ws.res_P = P; g_ws.res_n = n;
 
-  cudaStream_t *st = g_ws.st;
-  if (!st[0]) {
-    for (int i = 0; i < NSTREAM; ++i) {
-      cudaError_t e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
-      if (e != cudaSuccess) return cuda_err(e, "cudaStreamCreate");
+  if (!g_ws.ready) {
+    cudaError_t e = cudaStreamCreateWithFlags(&g_ws.s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g_ws.s_out, cudaStreamNonBlocking);
+    for (int i = 0; i < WT_HOST_NCOMPUTE && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&g_ws.s_k[i], cudaStreamNonBlocking);
+    for (int i = 0; i < WT_HOST_MAX_SLABS && e == cudaSuccess; ++i) {
+      e = cudaEventCreateWithFlags(&g_ws.ev_in[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_ws.ev_k[i], cudaEventDisableTiming);
     }
-    cudaError_t e = cudaEventCreateWithFlags(&g_ws.ev, cudaEventDisableTiming);
-    if (e != cudaSuccess) return cuda_err(e, "cudaEventCreate");
+    if (e != cudaSuccess) return cuda_err(e, "wt_step_host: stream / event creation");
+    g_ws.ready = true;
   }
+  const cudaStream_t s_in = g_ws.s_in, s_out = g_ws.s_out;
   const size_t pitch = Pz * 8;
-  if (!bnd_stride) {  // one broadcast boundary row: uploaded once, the other streams wait for it
-    cudaEvent_t ev = g_ws.ev;
-    cudaMemcpyAsync(d_bnd, bnd, b_bnd, cudaMemcpyHostToDevice, st[0]);
-    cudaEventRecord(ev, st[0]);
-    for (int i = 1; i < NSTREAM; ++i) cudaStreamWaitEvent(st[i], ev, 0);
-  }
-  for (int c = 0; c * per < P; ++c) {
-    const int p0 = c * per, w = (P - p0 < per) ? P - p0 : per;
-    cudaStream_t s = st[c % NSTREAM];
+  if (!bnd_stride) cudaMemcpyAsync(d_bnd, bnd, b_bnd, cudaMemcpyHostToDevice, s_in);  // one broadcast row, ahead of slab 0
+  int p0 = 0;
+  for (int c = 0; c < slabs; ++c) {
+    const int w = sizes[c];
     const size_t wb = (size_t)w * 8;
-    if (up_par) cudaMemcpy2DAsync(d_par + p0, pitch, par + p0, pitch, wb, WT_NPAR, cudaMemcpyHostToDevice, s);
-    if (bnd_stride) cudaMemcpy2DAsync(d_bnd + p0, pitch, bnd + p0, pitch, wb, WT_NBND, cudaMemcpyHostToDevice, s);
-    cudaMemcpyAsync(d_t + p0, time + p0, wb, cudaMemcpyHostToDevice, s);
-    cudaMemcpy2DAsync(d_y + p0, pitch, y + p0, pitch, wb, 3 * (size_t)n, cudaMemcpyHostToDevice, s);
-    cudaMemcpyAsync(d_s + p0, status + p0, (size_t)w * 4, cudaMemcpyHostToDevice, s);
-    if (flow) cudaMemcpyAsync(d_f + p0, flow + p0, wb, cudaMemcpyHostToDevice, s);
+    if (up_par) cudaMemcpy2DAsync(d_par + p0, pitch, par + p0, pitch, wb, WT_NPAR, cudaMemcpyHostToDevice, s_in);
+    if (bnd_stride) cudaMemcpy2DAsync(d_bnd + p0, pitch, bnd + p0, pitch, wb, WT_NBND, cudaMemcpyHostToDevice, s_in);
+    cudaMemcpyAsync(d_t + p0, time + p0, wb, cudaMemcpyHostToDevice, s_in);
+    cudaMemcpy2DAsync(d_y + p0, pitch, y + p0, pitch, wb, 3 * (size_t)n, cudaMemcpyHostToDevice, s_in);
+    cudaMemcpyAsync(d_s + p0, status + p0, (size_t)w * 4, cudaMemcpyHostToDevice, s_in);
+    if (flow) cudaMemcpyAsync(d_f + p0, flow + p0, wb, cudaMemcpyHostToDevice, s_in);
+    cudaEventRecord(g_ws.ev_in[c], s_in);
+    const cudaStream_t s = g_ws.s_k[c % WT_HOST_NCOMPUTE];
+    cudaStreamWaitEvent(s, g_ws.ev_in[c], 0);
     StepArgs a;
     a.P = w; a.ld = P; a.n = n; a.n_steps = 1; a.bnd_stride = bnd_stride; a.max_attempts = max_attempts;
     a.dt = dt; a.par = d_par + p0; a.bnd = bnd_stride ? d_bnd + p0 : d_bnd; a.time = d_t + p0; a.y = d_y + p0;
     a.flow = flow ? d_f + p0 : nullptr; a.derived = nullptr; a.status = d_s + p0; a.counters = nullptr;
-    a.order = nullptr; a.cost = nullptr; a.ws = d_ws + (size_t)(c % NSTREAM) * b_ws;
+    a.order = nullptr; a.cost = nullptr; a.ws = d_ws + (size_t)(c % WT_HOST_NCOMPUTE) * b_ws;
     a.skip_mask = WTS_SKIP_MASK; a.count_dev = nullptr; a.t_stop = nullptr;
     rc = launch_step(a, s);
     if (rc) return rc;
-    cudaMemcpyAsync(time + p0, d_t + p0, wb, cudaMemcpyDeviceToHost, s);
-    cudaMemcpy2DAsync(y + p0, pitch, d_y + p0, pitch, wb, 3 * (size_t)n, cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(status + p0, d_s + p0, (size_t)w * 4, cudaMemcpyDeviceToHost, s);
-    if (flow) cudaMemcpyAsync(flow + p0, d_f + p0, wb, cudaMemcpyDeviceToHost, s);
+    cudaEventRecord(g_ws.ev_k[c], s);
+    cudaStreamWaitEvent(s_out, g_ws.ev_k[c], 0);
+    cudaMemcpyAsync(time + p0, d_t + p0, wb, cudaMemcpyDeviceToHost, s_out);
+    cudaMemcpy2DAsync(y + p0, pitch, d_y + p0, pitch, wb, 3 * (size_t)n, cudaMemcpyDeviceToHost, s_out);
+    cudaMemcpyAsync(status + p0, d_s + p0, (size_t)w * 4, cudaMemcpyDeviceToHost, s_out);
+    if (flow) cudaMemcpyAsync(flow + p0, d_f + p0, wb, cudaMemcpyDeviceToHost, s_out);
+    p0 += w;
   }
-  for (int i = 0; i < NSTREAM; ++i) {
-    rc = cuda_err(cudaStreamSynchronize(st[i]), "wt_step_host");
-    if (rc) return rc;
-  }
-  return 0;
+  // every kernel is followed by copies on the copy-out stream, which therefore finishes last
+  rc = cuda_err(cudaStreamSynchronize(s_out), "wt_step_host");
+  if (rc) return rc;
+  rc = cuda_err(cudaStreamSynchronize(s_in), "wt_step_host");
+  for (int i = 0; i < WT_HOST_NCOMPUTE && !rc; ++i) rc = cuda_err(cudaStreamSynchronize(g_ws.s_k[i]), "wt_step_host");
+  return rc;
 }
 
 int wt_measure_fp64_peak(double *tflops_out, int iters) {
