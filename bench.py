@@ -169,9 +169,14 @@ def main():
     ap.add_argument("--streams", type=int, default=0, help="independent sub-ensembles (CUDA streams) per GPU; 0 = by shard size")
     ap.add_argument("--stats-every", type=int, default=10)
     ap.add_argument("--catch-up-attempts", type=int, default=0,
-                    help="budget of the side-stream catch-up of plants that exhaust --max-attempts (0 = halt them for good; "
-                         "measured with 2048: 35.4 instead of 15.1 ms/step at N=1, DESIGN.md section 7)")
+                    help="budget of the side-stream catch-up of plants that exhaust --max-attempts (0 = halt them for good, or "
+                         "8 x --catch-up-floor-div when that is given)")
+    ap.add_argument("--catch-up-floor-div", type=int, default=16,
+                    help="0: no deferral unless --catch-up-attempts is given.  > 0: the catch-up runs in floor mode (step sizes >= dt / floor_div, forced acceptance at the floor, "
+                         "WT_ST_DEGRADED): bounded-cost continuation of the plants on the 8 C density discontinuity, DESIGN.md section 7")
     args = ap.parse_args()
+    if args.catch_up_floor_div > 0 and args.catch_up_attempts <= 0:
+        args.catch_up_attempts = 8 * args.catch_up_floor_div
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,7 +208,8 @@ def main():
     parts = args.streams if args.streams > 0 else max(1, min(4, P // 65536))
     sensors_on = not args.no_sensors
     shard = PipelinedShard(e, parts=parts, device=dev, plant0=lo, sensor_seed=20260004 if sensors_on else None,
-                           max_attempts=args.max_attempts, sort_every=args.sort_every, catch_up_attempts=args.catch_up_attempts)
+                           max_attempts=args.max_attempts, sort_every=args.sort_every, catch_up_attempts=args.catch_up_attempts,
+                           catch_up_floor_div=args.catch_up_floor_div)
     fp64_peak = _lib.measure_fp64_peak() if rank == 0 else 0.0
     # Sensors: calibrated at t = -2000 s, then 100 reads of the initial state at t = -100 .. -1 s: when the timed region
     # starts every sensor is past its warm-up (10 / 30 / 60 / 300 / 1800 s) and the four 100-slot delay rings per plant
@@ -273,6 +279,11 @@ def main():
     timed_plant_steps = float(agg[8])
     halted_after = shard.halted()
     deferred_after = shard.deferred() if shard.defer else 0
+    degraded_after = shard.degraded()
+    # plants that have fallen behind for good: more than two blocks behind the front (a deferred plant is at most two
+    # blocks behind: over budget in one block, caught up during the next)
+    t_all = torch.cat([en.state.time for en in shard.engines])
+    stalled_after = int((t_all < t_all.max() - 2 * block * DT - 0.5 * DT).sum())
     value = timed_plant_steps * N_ZONES / (ms * 1e-3)
     stats_vec = shard._sum.cpu().numpy().copy()
 
@@ -389,11 +400,18 @@ def main():
             "sensor_state": "warm (calibrated at t=-2000 s), delay rings full" if sensors_on else None,
             "sort_every": args.sort_every, "sub_ensembles_per_gpu": nparts,
             "max_attempts": args.max_attempts, "catch_up_attempts": args.catch_up_attempts,
+            "catch_up_floor_div": args.catch_up_floor_div,
             "deferral": ("plants that exhaust max_attempts are collected at the next block boundary, continued with catch_up_attempts "
-                         "on a side stream during that block and rejoined at its end (inside the graph)") if shard.defer and use_graph
+                         + ("in floor mode (step sizes >= dt / catch_up_floor_div, forced acceptance at the floor, WT_ST_DEGRADED) "
+                            if args.catch_up_floor_div > 0 else "")
+                         + "on a side stream during that block and rejoined at its end (inside the graph)") if shard.defer and use_graph
                         else "off (eager launches)" if shard.defer else "off",
             "plants_halted_at_end_rank0": halted_after, "plants_deferred_at_end_rank0": deferred_after,
             "halted_fraction_rank0": halted_after / P,
+            "plants_degraded_in_last_step_rank0": degraded_after,
+            "plants_stalled_rank0": stalled_after, "stalled_fraction_rank0": stalled_after / P,
+            "stalled": "plants more than two statistics blocks behind the front at the end of the timed region (halted for good; "
+                       "'halted' above also counts plants that ran over the budget in the last blocks and are waiting for their catch-up)",
             "stats_allreduce_every": block, "stats_vector_doubles": int(stats_vec.size),
         },
         "roofline": {

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # WT_B200_LIB selects an alternative build of the SAME library (A/B tuning builds); never a CPU path
 LIB_PATH = os.environ.get("WT_B200_LIB") or os.path.join(_HERE, "csrc", "libwt_b200.so")
 
-ABI_VERSION = 3   # WT_ABI_VERSION of include/wt_b200.h
+ABI_VERSION = 4   # WT_ABI_VERSION of include/wt_b200.h
 NPAR = 12
 NBND = 10
 NCNT = 8
@@ -27,6 +27,7 @@ ST_NONFINITE = 32
 ST_T_RANGE_DERIVED = 64
 ST_WORK_LIMIT = 128
 ST_DEFERRED = 256
+ST_DEGRADED = 512
 ST_HALT_MASK = ST_T_RANGE | ST_WORK_LIMIT
 ST_SKIP_MASK = ST_HALT_MASK | ST_DEFERRED
 
@@ -106,7 +107,7 @@ def lib() -> C.CDLL:
     L.wt_defer_collect.argtypes = [C.c_int, up, ip, ip, C.c_int, vp]
     L.wt_defer_collect.restype = C.c_int
     L.wt_catch_up.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, up, ip, C.c_int,
-                              ip, ip, dp, vp, vp]
+                              C.c_int, ip, ip, dp, vp, vp]
     L.wt_catch_up.restype = C.c_int
     L.wt_defer_rejoin.argtypes = [up, ip, ip, C.c_int, vp]
     L.wt_defer_rejoin.restype = C.c_int

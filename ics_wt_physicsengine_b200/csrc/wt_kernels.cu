@@ -138,6 +138,7 @@ struct StepArgs {
   uint32_t skip_mask;    // plants with one of these status bits are passed over (WTS_SKIP_MASK; a catch-up launch: halts only)
   const int32_t *count_dev;  // optional: number of valid entries of `order` (a device-side list shorter than P)
   const double *t_stop;  // optional: plants whose time has reached *t_stop are passed over (catch-up launches)
+  double h_floor;        // > 0: floor mode (catch-up launches only): step sizes >= h_floor with forced acceptance at the floor
 };
 
 #ifndef WT_STEP_WARPS
@@ -265,7 +266,8 @@ __global__ void __launch_bounds__(WARPS * 32, WT_BEGIN_MINBLOCKS) wt_step_begin_
   }
 }
 
-template <int WARPS, int NZ>
+// FLOOR: the floor-mode variant of the attempt loop (WtPlantStep::run<true>), launched by wt_catch_up only.
+template <int WARPS, int NZ, bool FLOOR>
 __global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_run_kernel(StepArgs a) {
   extern __shared__ double smem[];
   static_assert(WARPS == 4, "one warp per tensor-memory lane quarter");
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_run_ker
         ps.J.cp = hrow[HO_JCP];
       }
       double yin[3] = {ps.y[0], ps.y[1], ps.y[2]};
-      ps.run(t, a.max_attempts);
+      ps.template run<FLOOR>(t, a.max_attempts, a.h_floor);
       double der[3];
       bool adv;
       const int sb = wt_finish_step(ps, yin, der, adv);
@@ -862,12 +864,12 @@ static int check_common(int P, int n) {
   return 0;
 }
 
-struct StepKernels { void (*begin)(StepArgs); void (*run)(StepArgs); };
+struct StepKernels { void (*begin)(StepArgs); void (*run)(StepArgs); void (*run_floor)(StepArgs); };
 static StepKernels step_kernels(int n) {
   if (getenv("WT_B200_GENERIC_N")) n = 0;  // A/B runs
-  if (n == 10) return {wt_step_begin_kernel<WT_STEP_WARPS, 10>, wt_step_run_kernel<WT_STEP_WARPS, 10>};
-  if (n == 20) return {wt_step_begin_kernel<WT_STEP_WARPS, 20>, wt_step_run_kernel<WT_STEP_WARPS, 20>};
-  return {wt_step_begin_kernel<WT_STEP_WARPS, 0>, wt_step_run_kernel<WT_STEP_WARPS, 0>};
+  if (n == 10) return {wt_step_begin_kernel<WT_STEP_WARPS, 10>, wt_step_run_kernel<WT_STEP_WARPS, 10, false>, wt_step_run_kernel<WT_STEP_WARPS, 10, true>};
+  if (n == 20) return {wt_step_begin_kernel<WT_STEP_WARPS, 20>, wt_step_run_kernel<WT_STEP_WARPS, 20, false>, wt_step_run_kernel<WT_STEP_WARPS, 20, true>};
+  return {wt_step_begin_kernel<WT_STEP_WARPS, 0>, wt_step_run_kernel<WT_STEP_WARPS, 0, false>, wt_step_run_kernel<WT_STEP_WARPS, 0, true>};
 }
 
 // per-device launch facts, set up once per device under a lock (several host threads, one per device, may call in)
@@ -890,6 +892,8 @@ static int device_info(DevInfo *out) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k.begin, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
       // shared memory for the resident blocks, the rest of the 256 KB stays L1 (it backs the register spills)
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k.run, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k.run_floor, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k.run_floor, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
       if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute");
     }
     e = cudaDeviceGetAttribute(&info[dev].sms, cudaDevAttrMultiProcessorCount, dev);
@@ -921,7 +925,7 @@ static int launch_step(StepArgs a, cudaStream_t s) {
   for (int i = 0; i < n_steps; ++i) {
     a.n_steps = i;  // > 0: OR the non-halting status bits of the earlier steps into this step's word
     k.begin<<<(unsigned)blocks, WT_STEP_WARPS * 32, smem_begin, s>>>(a);
-    k.run<<<(unsigned)run_blocks, WT_STEP_WARPS * 32, smem_run, s>>>(a);
+    (a.h_floor > 0.0 ? k.run_floor : k.run)<<<(unsigned)run_blocks, WT_STEP_WARPS * 32, smem_run, s>>>(a);
   }
   return cuda_err(cudaGetLastError(), "wt_step kernels launch");
 }
@@ -946,15 +950,16 @@ int wt_advance(int P, int n, int n_steps, double dt, const double *par, const do
   a.P = P; a.ld = P; a.n = n; a.n_steps = n_steps; a.bnd_stride = bnd_stride; a.max_attempts = max_attempts;
   a.dt = dt; a.par = par; a.bnd = bnd; a.time = time; a.y = y; a.flow = flow; a.derived = derived;
   a.status = status; a.counters = counters; a.order = order; a.cost = cost; a.ws = (char *)workspace;
-  a.skip_mask = WTS_SKIP_MASK; a.count_dev = nullptr; a.t_stop = nullptr;
+  a.skip_mask = WTS_SKIP_MASK; a.count_dev = nullptr; a.t_stop = nullptr; a.h_floor = 0.0;
   return launch_step(a, (cudaStream_t)stream);
 }
 
 int wt_catch_up(int cap, int ld, int n, int n_steps, double dt, const double *par, const double *bnd, int bnd_stride,
                 double *time, double *y, double *flow, double *derived, uint32_t *status, int32_t *counters,
-                int max_attempts, const int32_t *list, const int32_t *count, const double *t_stop, void *workspace,
-                void *stream) {
+                int max_attempts, int floor_div, const int32_t *list, const int32_t *count, const double *t_stop,
+                void *workspace, void *stream) {
   int rc = check_common(cap, n);
+  if (floor_div < 0) return set_err(WT_ERR_BAD_ARG, "floor_div must be >= 0");
   if (rc) return rc;
   if (!(dt > 0.0) || n_steps < 1 || ld < 1) return set_err(WT_ERR_BAD_ARG, "bad dt, n_steps or ld");
   if (!par || !bnd || !time || !y || !status || !list || !count || !t_stop || !workspace)
@@ -966,6 +971,7 @@ int wt_catch_up(int cap, int ld, int n, int n_steps, double dt, const double *pa
   a.status = status; a.counters = counters; a.order = list; a.cost = nullptr; a.ws = (char *)workspace;
   a.skip_mask = WTS_HALT_MASK;   // the listed plants carry WTS_DEFERRED: that is what this launch is for
   a.count_dev = count; a.t_stop = t_stop;
+  a.h_floor = floor_div > 0 ? dt / (double)floor_div : 0.0;
   return launch_step(a, (cudaStream_t)stream);
 }
 
@@ -1506,7 +1512,7 @@ int wt_step_host(int P, int n, double dt, const double *par, const double *bnd, 
     a.dt = dt; a.par = d_par + p0; a.bnd = bnd_stride ? d_bnd + p0 : d_bnd; a.time = d_t + p0; a.y = d_y + p0;
     a.flow = flow ? d_f + p0 : nullptr; a.derived = nullptr; a.status = d_s + p0; a.counters = nullptr;
     a.order = nullptr; a.cost = nullptr; a.ws = d_ws + (size_t)(c % WT_HOST_NCOMPUTE) * b_ws;
-    a.skip_mask = WTS_SKIP_MASK; a.count_dev = nullptr; a.t_stop = nullptr;
+    a.skip_mask = WTS_SKIP_MASK; a.count_dev = nullptr; a.t_stop = nullptr; a.h_floor = 0.0;
     rc = launch_step(a, s);
     if (rc) return rc;
     cudaEventRecord(g_ws.ev_k[c], s);

@@ -40,7 +40,7 @@ enum {
 };
 enum {
   WTS_SOLVER_FAILED = 1, WTS_T_RANGE = 2, WTS_CLIP_PH = 4, WTS_CLIP_CL = 8, WTS_CLIP_T = 16,
-  WTS_NONFINITE = 32, WTS_T_RANGE_DERIVED = 64, WTS_WORK_LIMIT = 128, WTS_DEFERRED = 256
+  WTS_NONFINITE = 32, WTS_T_RANGE_DERIVED = 64, WTS_WORK_LIMIT = 128, WTS_DEFERRED = 256, WTS_DEGRADED = 512
 };
 #define WTS_HALT_MASK (WTS_T_RANGE | WTS_WORK_LIMIT)
 #define WTS_SKIP_MASK (WTS_HALT_MASK | WTS_DEFERRED)   // what an ordinary launch passes over
@@ -448,13 +448,14 @@ struct WtPlantStep {
   // byte lanes of several registers and spilled those to local memory, which misses L1 here: long_sb stalls)
   enum { F_RUNNING = 1, F_NEED_JAC = 2, F_CURRENT_JAC = 4, F_LU_VALID = 8, F_NEW_STEP = 16, F_HAVE_OLD = 32,
          F_REJECTED = 64, F_HAVE_JFAC = 128, F_HAVE_SOL = 256, F_TRANGE = 512, F_FAILED = 1024,
-         F_WORKLIMIT = 2048, F_SELF_HAVE_OLD = 4096 };
+         F_WORKLIMIT = 2048, F_SELF_HAVE_OLD = 4096, F_DEGRADED = 8192 };
   vi fl;
   WT_DEV vb fget(int bit) const { return (fl & bit) != 0; }
   WT_DEV void fset(int bit, vb m) { fl = fl | seli(m, bit, 0); }      // set where m
   WT_DEV void fclr(int bit, vb m) { fl = fl & seli(m, ~bit, -1); }    // clear where m
   WT_DEV vb trange() const { return fget(F_TRANGE); }      // the reference would have raised ValueError inside the solve
   WT_DEV vb failed() const { return fget(F_FAILED); }      // TOO_SMALL_STEP
+  WT_DEV vb degraded() const { return fget(F_DEGRADED); }    // engine policy: floor mode forced an acceptance (not reference behaviour)
   WT_DEV vb worklimit() const { return fget(F_WORKLIMIT); }  // engine policy: attempt budget exhausted (not reference behaviour)
   vd W[3][3];     // W[k][var]
   // Per-plant step-control scalars live in the per-plant store (shared memory), not replicated in two
@@ -880,9 +881,10 @@ struct WtPlantStep {
   //   run()    the attempt loop (_step_impl, radau.py:405-545), data-dependent.
   // What crosses from one to the other: fl, J.pt / J.ct / J.cp, the parked f / jfac / J diagonal blocks and
   // PV_SELF_H (everything else begin() leaves behind is rebuilt by reset()).
-  WT_DEV void integrate(vd t0, vd dt, vb plant_on, int max_attempts) {
+  WT_DEV void integrate(vd t0, vd dt, vb plant_on, int max_attempts, double h_floor = 0.0) {
     begin(t0, dt, plant_on);
-    run(t0, max_attempts);
+    if (h_floor > 0.0) run<true>(t0, max_attempts, h_floor);
+    else run<false>(t0, max_attempts, 0.0);
   }
 
   // solver state at the start of a step (radau.py:295-347 minus f0 / h_abs / the Jacobian)
@@ -959,7 +961,13 @@ struct WtPlantStep {
     }
   }
 
-  WT_DEV void run(vd t0, int max_attempts) {
+  // FLOOR (engine policy, not reference behaviour): the catch-up launches of plants that exhausted
+  // their budget on the 8 C density discontinuity.  The step size of every attempt is kept >= h_floor, and AT the floor
+  // (a) an error estimate above 1 no longer rejects, (b) a Newton iteration that stops unconverged with a current
+  // Jacobian keeps its last iterate.  Such plant-steps report WTS_DEGRADED.  A compile-time variant: the ordinary
+  // kernel carries none of it.
+  template <bool FLOOR>
+  WT_DEV void run(vd t0, int max_attempts, double h_floor) {
     if (max_attempts <= 0 || max_attempts > WT_HARD_MAX_ATTEMPTS) max_attempts = WT_HARD_MAX_ATTEMPTS;
     vd t = t0;
     vd h_abs = vbroadcast(0.0);  // set from PV_SELF_H on the first pass (F_NEW_STEP)
@@ -990,6 +998,7 @@ struct WtPlantStep {
         vb big = self_h_abs > max_step, small = self_h_abs < ms;
         vd hh_ = sel(big, max_step, sel(small, ms, self_h_abs));
         h_abs = sel(m, hh_, h_abs);
+        if (FLOOR) h_abs = vmax(h_abs, h_floor);
         pvset(PV_H_OLD, pv(PV_SELF_H_OLD), m);
         pvset(PV_ERR_OLD, pv(PV_SELF_ERR_OLD), m);
         fclr(F_HAVE_OLD | F_REJECTED | F_NEW_STEP, m);
@@ -1008,6 +1017,9 @@ struct WtPlantStep {
       }
       const vd h = t_new - t;
       h_abs = sel(fget(F_RUNNING), vabs(h), h_abs);
+      vb at_floor = vbroadcast_b(false);
+      // (h = fl(fl(t + h_floor) - t) can exceed h_floor by rounding: a relative slack far above that, far below a step ratio)
+      if (FLOOR) at_floor = h_abs <= h_floor * 1.000001;
       vd scale[3];  // 1 / (atol + |y| rtol)
       WT_UNROLL
       for (int v = 0; v < 3; ++v) scale[v] = wt_rcp(WT_ATOL + vabs(y[v]) * WT_RTOL);
@@ -1151,14 +1163,25 @@ struct WtPlantStep {
           for (int e = 1; e < WT_NEWTON_MAXITER - k; ++e) rp = rp * rate;
           const vd i1r = wt_rcp(1.0 - rate);
           vb brk = active & have_rate & ((rate >= 1.0) | (rp * i1r * dW_norm > WT_NEWTON_TOL));
+          vb forced = vbroadcast_b(false), upd = active & !brk;
+          if (FLOOR) {  // at the floor a diverging iteration keeps its last iterate (no update) and closes
+            forced = brk & at_floor & fget(F_CURRENT_JAC);
+            brk = brk & !forced;
+          }
           active = active & !brk;
           WT_UNROLL
           for (int v = 0; v < 3; ++v) {
-            W[0][v] = sel(active, W[0][v] + fr[v], W[0][v]);
-            W[1][v] = sel(active, W[1][v] + cr[v], W[1][v]);
-            W[2][v] = sel(active, W[2][v] + ci[v], W[2][v]);
+            W[0][v] = sel(upd, W[0][v] + fr[v], W[0][v]);
+            W[1][v] = sel(upd, W[1][v] + cr[v], W[1][v]);
+            W[2][v] = sel(upd, W[2][v] + ci[v], W[2][v]);
           }
-          cvn = active & ((dW_norm == 0.0) | (have_rate & (rate * i1r * dW_norm < WT_NEWTON_TOL)));
+          cvn = active & ((dW_norm == 0.0) | (have_rate & (rate * i1r * dW_norm < WT_NEWTON_TOL)) | forced);
+          if (FLOOR && k + 1 >= WT_NEWTON_MAXITER) {  // ... and so does one that has used up its iterations
+            const vb f2 = active & !cvn & at_floor & fget(F_CURRENT_JAC);
+            forced = forced | f2;
+            cvn = cvn | f2;
+          }
+          if (FLOOR) fset(F_DEGRADED, forced);
           converged = converged | cvn;
           active = active & !cvn;
           dW_norm_old = sel(cl, dW_norm_old, dW_norm);
@@ -1179,11 +1202,17 @@ struct WtPlantStep {
             bad_new = selb(cl0, bad, bad_new);
             lu->cadd(WTC_NFEV, seli(again, 1, 0));  // the evaluation at y + err of the next pass
             const vb decide = clx & !again;
-            const vb rej = decide & (err_norm > 1.0);
+            vb rej = decide & (err_norm > 1.0);
+            if (FLOOR) {  // at the floor the error test no longer rejects
+              const vb frc = rej & at_floor;
+              fset(F_DEGRADED, frc);
+              rej = rej & !frc;
+            }
             vb acc = decide & !rej;
             const vd safety = wt_div(vbroadcast(0.9 * (2 * WT_NEWTON_MAXITER + 1)), vfromint(n_iter + 2 * WT_NEWTON_MAXITER));
             const vd pf = predict_factor(h_abs, pv(PV_H_OLD), err_norm, pv(PV_ERR_OLD), fget(F_HAVE_OLD));
             h_abs = sel(rej, h_abs * vmax(safety * pf, 0.2), h_abs);
+            if (FLOOR) h_abs = vmax(h_abs, h_floor);
             fclr(F_LU_VALID, rej);
             fset(F_REJECTED, rej);
             lu->cadd(WTC_NREJECT, seli(rej, 1, 0));
@@ -1248,6 +1277,7 @@ struct WtPlantStep {
         fset(F_NEED_JAC, stale);  // recompute J at (t, y, f), same h
         vb halve = nc & fget(F_CURRENT_JAC);
         h_abs = sel(halve, h_abs * 0.5, h_abs);
+        if (FLOOR) h_abs = vmax(h_abs, h_floor);
         fclr(F_LU_VALID, halve);
       }
     }
@@ -1263,6 +1293,7 @@ WT_DEV vi wt_finish_step(WtPlantStep<LuStore> &ps, const vd *y_in, vd *derived, 
   const WtGroup &g = ps.g;
   vi st = seli(ps.failed(), (int)WTS_SOLVER_FAILED, 0);
   st = st | seli(ps.trange(), (int)WTS_T_RANGE, 0) | seli(ps.worklimit(), (int)WTS_WORK_LIMIT, 0);
+  st = st | seli(ps.degraded(), (int)WTS_DEGRADED, 0);
   advance = !(ps.trange() | ps.worklimit());  // exception inside solve_ivp: state untouched, time not advanced
   WT_UNROLL
   for (int v = 0; v < 3; ++v) ps.y[v] = sel(advance, ps.y[v], y_in[v]);

@@ -333,3 +333,8 @@ class PipelinedShard:
     def deferred(self) -> int:
         self.synchronize()
         return int(sum(int(((e.status & _lib.ST_DEFERRED) != 0).sum()) for e in self.engines))
+
+    def degraded(self) -> int:
+        """Plants whose LAST step was completed by a floor-mode catch-up with a forced acceptance (WT_ST_DEGRADED)."""
+        self.synchronize()
+        return int(sum(int(((e.status & _lib.ST_DEGRADED) != 0).sum()) for e in self.engines))

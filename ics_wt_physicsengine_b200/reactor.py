@@ -186,7 +186,7 @@ class PlantEnsemble:
 
     def __init__(self, cfg: Union[np.ndarray, Sequence[ReactorConfiguration], Ensemble], n_zones: Optional[int] = None,
                  device: Union[str, torch.device, None] = None, max_attempts: int = DEFAULT_MAX_ATTEMPTS,
-                 validate: bool = True, sort_every: int = 0, catch_up_attempts: int = 0):
+                 validate: bool = True, sort_every: int = 0, catch_up_attempts: int = 0, catch_up_floor_div: int = 0):
         _lib.require_device()
         init = None
         if isinstance(cfg, Ensemble):
@@ -210,6 +210,13 @@ class PlantEnsemble:
         # > 0: plants that exhaust max_attempts are not halted but DEFERRED: collect_deferred / catch_up / rejoin_deferred
         # continue them with this larger budget (partition.PipelinedShard runs the three per block of steps)
         self.catch_up_attempts = int(catch_up_attempts)
+        # > 0: the catch-up runs in FLOOR MODE (engine policy, include/wt_b200.h wt_catch_up): step sizes >= dt / floor_div
+        # with forced acceptance at the floor, WT_ST_DEGRADED on the plant-steps that needed it.  Bounded cost for the
+        # plants that sit on the 8 C density discontinuity, where the reference's adaptive control needs 1e5 .. 1e7
+        # evaluations per step.
+        self.catch_up_floor_div = int(catch_up_floor_div)
+        if self.catch_up_floor_div < 0:
+            raise ValueError("catch_up_floor_div must be >= 0")
         # scheduling only (results do not depend on it): every `sort_every` launches the plants are
         # re-ordered by the work of their last step, most expensive first (0 = natural order)
         self.sort_every = int(sort_every)
@@ -233,7 +240,7 @@ class PlantEnsemble:
             self._cost = torch.zeros(P, dtype=torch.int32, device=self.device) if self.sort_every > 0 else None
             self._bins = torch.zeros(1024, dtype=torch.int32, device=self.device) if self.sort_every > 0 else None
             if self.catch_up_attempts > 0:
-                cap = max(1024, P // 64)
+                cap = max(1024, P // 32)
                 self._defer_cap = cap
                 self._defer_list = torch.zeros(cap, dtype=torch.int32, device=self.device)
                 self._defer_count = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -349,7 +356,8 @@ class PlantEnsemble:
         with torch.cuda.device(self.device):
             rc = _lib.lib().wt_catch_up(self._defer_cap, self.n_plants, self.n_zones, int(n_steps), float(dt), _ptr(self._par),
                                         _ptr(bnd), stride, _ptr(self._time), _ptr(self._y), _ptr(self._flow), _ptr(self._derived),
-                                        _ptr(self._status), _ptr(self._counters), self.catch_up_attempts, _ptr(self._defer_list),
+                                        _ptr(self._status), _ptr(self._counters), self.catch_up_attempts, self.catch_up_floor_div,
+                                        _ptr(self._defer_list),
                                         _ptr(self._defer_count), _ptr(self._t_stop), _ptr(self._ws_defer),
                                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, "wt_catch_up")

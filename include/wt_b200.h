@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define WT_ABI_VERSION 3   /* 3: wt_step / wt_advance take a device workspace (wt_step_workspace_bytes); new entry points of round 2 */
+#define WT_ABI_VERSION 4   /* 3: wt_step / wt_advance take a device workspace (wt_step_workspace_bytes); new entry points of round 2
+                              4: wt_catch_up takes floor_div (floor mode), WT_ST_DEGRADED */
 #define WT_MAX_ZONES 32
 
 /* derived per-plant constants; computed on the host exactly as the reference constructors do
@@ -56,9 +57,13 @@ enum {
   WT_ST_T_RANGE_DERIVED = 1u << 6, /* ValueError in _update_derived_state (reactor.py:521-524) */
   WT_ST_WORK_LIMIT = 1u << 7,      /* engine policy, not reference behaviour: attempt budget
                                       exhausted, state untouched; plant HALTS (unless deferred, below) */
-  WT_ST_DEFERRED = 1u << 8         /* the plant ran out of budget and is being caught up by wt_catch_up with a larger
+  WT_ST_DEFERRED = 1u << 8,        /* the plant ran out of budget and is being caught up by wt_catch_up with a larger
                                       one: ordinary launches, statistics and sensors' consumers pass over it until
                                       wt_defer_rejoin */
+  WT_ST_DEGRADED = 1u << 9         /* engine policy, not reference behaviour: this step was completed by a floor-mode
+                                      catch-up (wt_catch_up with floor_div > 0) that forced an acceptance at the
+                                      step-size floor; the state is a bounded-step continuation, not the reference's
+                                      adaptive solution (which needs 1e5 .. 1e7 evaluations there) */
 };
 #define WT_ST_HALT_MASK (WT_ST_T_RANGE | WT_ST_WORK_LIMIT)
 #define WT_ST_SKIP_MASK (WT_ST_HALT_MASK | WT_ST_DEFERRED)
@@ -128,12 +133,18 @@ int wt_advance(int P, int n_zones, int n_steps, double dt, const double *par_dev
  *                     until its time reaches *t_stop_dev; meant for a side stream while the ensemble moves on.  Arrays
  *                     are the ensemble's (row stride ld = its plant count); workspace: wt_step_workspace_bytes(cap, n).
  *                     A plant that exhausts this budget too gets WT_ST_WORK_LIMIT and stays halted.
+ *                     floor_div = 0: the reference's adaptive step control, as in wt_step.  floor_div > 0 (FLOOR MODE,
+ *                     engine policy): the step size of every attempt is kept >= dt / floor_div, and at that floor an
+ *                     error estimate above 1 no longer rejects and a Newton iteration that stops unconverged with a
+ *                     current Jacobian keeps its last iterate; such plant-steps report WT_ST_DEGRADED.  This is how a
+ *                     plant sitting on the 8 C density discontinuity (spatial.py:177-189) is continued at bounded cost
+ *                     instead of being halted: <= ~4 floor_div collocation solves per step.
  *   wt_defer_rejoin   after the catch-up has finished (stream order): takes WT_ST_DEFERRED off the listed plants and
  *                     empties the list. */
 int wt_defer_collect(int P, uint32_t *status_dev, int32_t *list_dev, int32_t *count_dev, int cap, void *stream);
 int wt_catch_up(int cap, int ld, int n_zones, int n_steps, double dt, const double *par_dev, const double *bnd_dev,
                 int bnd_stride, double *time_dev, double *y_dev, double *flow_rate_dev, double *derived_dev,
-                uint32_t *status_dev, int32_t *counters_dev, int max_attempts, const int32_t *list_dev,
+                uint32_t *status_dev, int32_t *counters_dev, int max_attempts, int floor_div, const int32_t *list_dev,
                 const int32_t *count_dev, const double *t_stop_dev, void *workspace_dev, void *stream);
 int wt_defer_rejoin(uint32_t *status_dev, const int32_t *list_dev, int32_t *count_dev, int cap, void *stream);
 

@@ -86,7 +86,9 @@ enum {
   WT_ST_CLIP_T = 1u << 4,          /* reactor.py:538-541 */
   WT_ST_NONFINITE = 1u << 5,       /* a state value is NaN/inf after the step */
   WT_ST_T_RANGE_DERIVED = 1u << 6, /* ValueError in _update_derived_state (reactor.py:521-524): state assigned, not clipped */
-  WT_ST_WORK_LIMIT = 1u << 7       /* engine policy (not in the reference): attempt budget exhausted; state unchanged */
+  WT_ST_WORK_LIMIT = 1u << 7,      /* engine policy (not in the reference): attempt budget exhausted; state unchanged */
+  WT_ST_DEFERRED = 1u << 8,        /* engine bookkeeping (never set by the oracle) */
+  WT_ST_DEGRADED = 1u << 9         /* engine policy (not in the reference): floor mode forced an acceptance in this step */
 };
 
 /* ---- solver path counters */
@@ -126,6 +128,7 @@ uint32_t wt_oracle_step(const double *par, const double *bnd, int n, double dt,
 
 /* Engine policy knob mirrored for tests: budget of collocation solves per step (0 = unlimited). */
 void wt_oracle_set_max_attempts(int m);
+void wt_oracle_set_floor_div(int d); /* engine policy mirror: step-size floor dt / d with forced acceptance (0 = off) */
 
 /* Batched driver: plant p uses cfg-derived par[p*WT_NPAR..], bnd[p*WT_NBND..] (or
  * bnd broadcast when bnd_stride == 0), y[p*3n..].  Runs `nsteps` steps of dt on

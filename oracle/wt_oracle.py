@@ -40,6 +40,8 @@ ST_CLIP_T = 16
 ST_NONFINITE = 32
 ST_T_RANGE_DERIVED = 64
 ST_WORK_LIMIT = 128
+ST_DEFERRED = 256
+ST_DEGRADED = 512
 ST_HALT_MASK = ST_T_RANGE | ST_WORK_LIMIT
 
 
@@ -73,6 +75,8 @@ def lib():
         L.wt_oracle_step_batch.restype = None
         L.wt_oracle_set_max_attempts.argtypes = [C.c_int]
         L.wt_oracle_set_max_attempts.restype = None
+        L.wt_oracle_set_floor_div.argtypes = [C.c_int]
+        L.wt_oracle_set_floor_div.restype = None
         L.wt_oracle_set_ph_h_eps.argtypes = [C.c_double]
         L.wt_oracle_set_ph_h_eps.restype = None
         L.wt_oracle_calc_ph.argtypes = [C.c_double] * 5 + [C.c_int, dp, ip]
@@ -101,6 +105,11 @@ def lib():
 
 def set_max_attempts(m: int) -> None:
     lib().wt_oracle_set_max_attempts(int(m))
+
+
+def set_floor_div(d: int) -> None:
+    """Engine policy mirror (floor mode): step sizes >= dt / d with forced acceptance; 0 = off."""
+    lib().wt_oracle_set_floor_div(int(d))
 
 
 def set_ph_h_eps(eps: float) -> None:

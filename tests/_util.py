@@ -35,7 +35,7 @@ class EmuLib:
                                    "-I" + inc, "-o", so, src])
         self.L = C.CDLL(so)
 
-    def step(self, par, bnd, n, t, y, dt=1.0, nsteps=1, max_attempts=0, status=None):
+    def step(self, par, bnd, n, t, y, dt=1.0, nsteps=1, max_attempts=0, status=None, floor_div=0):
         dp, ip, up = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
         P = y.shape[0]
         st = np.zeros(P, np.uint32) if status is None else status
@@ -45,7 +45,7 @@ class EmuLib:
         assert bnd.shape == (P, 10)
         self.L.wt_emu_step_batch(P, n, nsteps, C.c_double(dt), par.ctypes.data_as(dp), bnd.ctypes.data_as(dp), 10,
                                  t.ctypes.data_as(dp), y.ctypes.data_as(dp), fl.ctypes.data_as(dp),
-                                 st.ctypes.data_as(up), cnt.ctypes.data_as(ip), None, int(max_attempts))
+                                 st.ctypes.data_as(up), cnt.ctypes.data_as(ip), None, int(max_attempts), int(floor_div))
         return st, cnt, fl
 
     def rhs(self, par, bnd, n, y):

@@ -35,7 +35,7 @@ extern "C" {
 // Same argument convention as wt_oracle_step_batch (AoS per plant, species-major y).
 void wt_emu_step_batch(int P, int n, int nsteps, double dt, const double *par, const double *bnd,
                        int bnd_stride, double *t, double *y, double *flow_rate, uint32_t *status,
-                       int32_t *counters, double *derived, int max_attempts) {
+                       int32_t *counters, double *derived, int max_attempts, int floor_div) {
   const int gpw = 32 / n;
   for (int p0 = 0; p0 < P; p0 += gpw) {
     for (int s = 0; s < nsteps; ++s) {
@@ -62,7 +62,7 @@ void wt_emu_step_batch(int P, int n, int nsteps, double dt, const double *par, c
       ps.c = wt_make_const(&lu, ps.g, 110, vpar, vbnd);
       lu.czero();
       for (int v = 0; v < 3; ++v) ps.y[v] = yin[v];
-      ps.integrate(t0, vdt, on, max_attempts);
+      ps.integrate(t0, vdt, on, max_attempts, floor_div > 0 ? dt / (double)floor_div : 0.0);
       vd der[3];
       vb adv;
       vi st = wt_finish_step(ps, yin, der, adv);

@@ -588,3 +588,81 @@ def test_deferred_plants_are_continued_and_equal_a_run_with_the_larger_budget(or
     print(f"plant {p}: {attempts} collocation solves for one step; error vs the unbudgeted oracle {r:.2e}; the oracle's own "
           f"sensitivity to 1-8 ulp of input there {sens:.2e}")
     assert r <= TOL or r <= 10.0 * sens
+
+
+def test_floor_mode_catch_up_equals_the_oracle_and_nobody_stays_halted(oracle, golden_dir):
+    """Floor mode (engine policy).  (1) The plant-steps of tests/golden/overrun_plants.npz -- config-5
+    plants on the 8 C density discontinuity that exhaust the budget of 64 -- go through collect / catch-up / rejoin with
+    catch_up_floor_div = 16 and come back with the state of the oracle's mirror of the policy, WT_ST_DEGRADED set, time
+    advanced, nobody halted.  (2) A config-5 ensemble run block-wise with floor-mode deferral loses no plant to the
+    budget (the run without it does)."""
+    from ics_wt_physicsengine_b200 import _lib
+    from ics_wt_physicsengine_b200.partition import PipelinedShard
+    g = np.load(os.path.join(golden_dir, "overrun_plants.npz"))
+    n, K = int(g["n_zones"]), len(g["plant"])
+    e = ens.config5(65536, n).slice(g["plant"])
+    y0 = g["y0"]
+    eng = PlantEnsemble(e, max_attempts=64, catch_up_attempts=128, catch_up_floor_div=16)
+    eng.set_state(y0[:, :n], y0[:, n:2 * n], y0[:, 2 * n:], time=np.zeros(K))
+    eng.step(1.0, e.bnd)
+    torch.cuda.synchronize()
+    assert np.all(eng.status.cpu().numpy() & _lib.ST_WORK_LIMIT), "these plant-steps overrun the budget of 64"
+    assert np.array_equal(eng.state_numpy(), y0) and np.all(eng.state.time.cpu().numpy() == 0.0)
+    eng.reset_counters()   # (the path counters of the abandoned attempt are kept by the engine; the oracle's start here)
+    eng._t_stop.fill_(1.0)
+    eng.collect_deferred()
+    assert np.all(eng.status.cpu().numpy() & _lib.ST_DEFERRED)
+    eng.catch_up(2, 1.0, e.bnd)   # the second launch finds every plant at the stop time
+    eng.rejoin_deferred()
+    torch.cuda.synchronize()
+    yo, to = y0.copy(), np.zeros(K)
+    oracle.set_max_attempts(128)
+    oracle.set_floor_div(16)
+    try:
+        so, co, _ = oracle.step_batch(np.ascontiguousarray(g["par"]), np.ascontiguousarray(g["bnd"]), n, to, yo, dt=1.0)
+    finally:
+        oracle.set_floor_div(0)
+        oracle.set_max_attempts(0)
+    st = eng.status.cpu().numpy()
+    rel = np.abs(eng.state_numpy() - yo) / np.maximum(np.abs(yo), 1e-300)
+    # These plants sit ON a discontinuity of the RHS: a last-bit difference (FMA contraction, exp) flips a Richardson
+    # switch in some stage evaluation and moves the result by O(jump x step).  The kernel SOURCE equals the oracle's
+    # mirror of the policy bit for bit (tests/test_floor_mode.py, lane-emulation build without contraction); the
+    # compiled kernel must equal it on the plant-steps whose switches do not flip, and stay inside the spread of the
+    # policy itself (floor dt/4 .. dt/256 agree to 5e-5; bound 2e-3) on the others.
+    worst = rel.max(axis=1)
+    cnt = eng.counters.cpu().numpy().T[:, :7]
+    same_path = (cnt == co[:, :7]).all(axis=1)
+    print(f"floor mode: {K} overrun plant-steps vs the oracle's floor mode: {int((worst < 1e-9).sum())} within 1e-9, "
+          f"{int(same_path.sum())} on the same solver path, worst {worst.max():.2e}, median {np.median(worst):.2e}")
+    assert (worst < 1e-9).sum() >= K - 3 and worst.max() < 2e-3   # measured on B200: 21 of 21 within 1e-9 (worst 3e-14)
+    assert np.all(worst[same_path] < 1e-6)
+    assert np.all(st & _lib.ST_DEGRADED) and not np.any(st & _lib.ST_SKIP_MASK), (st, so, cnt[:, 3] + cnt[:, 5] + cnt[:, 6])
+    assert np.array_equal(st[worst < 1e-9], so[worst < 1e-9])
+    assert np.all(eng.state.time.cpu().numpy() == 1.0)
+    # the next ordinary step takes them again (they are neither halted nor deferred)
+    eng.step(1.0, e.bnd)
+    torch.cuda.synchronize()
+    assert np.all((eng.state.time.cpu().numpy() == 2.0) | ((eng.status.cpu().numpy() & _lib.ST_WORK_LIMIT) != 0))
+
+    # (2) block-wise, with sensors off: budget 64, floor-mode catch-up vs plain halting
+    P, B, blocks = 65536, 5, 8
+    e2 = ens.config5(P, n)
+    plain = PipelinedShard(e2, parts=2, max_attempts=64)
+    floor = PipelinedShard(e2, parts=2, max_attempts=64, catch_up_attempts=128, catch_up_floor_div=16)
+    floor.start_deferral(0.0)
+    for b in range(blocks):
+        for _ in range(B):
+            plain.step(1.0)
+        floor.block(B, 1.0, t_first=float(b * B))
+    floor.block(B, 1.0, t_first=float(blocks * B))   # the plants deferred in the last block rejoin
+    torch.cuda.synchronize()
+    sd = np.concatenate([x.status.cpu().numpy() for x in floor.engines])
+    td = np.concatenate([x.state.time.cpu().numpy() for x in floor.engines])
+    lost_plain = plain.halted()
+    print(f"floor mode: {lost_plain} of {P} plants halted after {blocks * B} steps without deferral; with floor-mode deferral "
+          f"{int(((sd & _lib.ST_T_RANGE) != 0).sum())} (temperature range) + {int(((sd & _lib.ST_WORK_LIMIT) != 0).sum())} (over budget "
+          f"in the very last block, collected by the next one); degraded plant-steps in the last block: {int(((sd & _lib.ST_DEGRADED) != 0).sum())}")
+    assert lost_plain >= 10
+    settled = (sd & _lib.ST_SKIP_MASK) == 0
+    assert settled.mean() > 0.999 and np.all(td[settled] == (blocks + 1) * B)

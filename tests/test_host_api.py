@@ -74,7 +74,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for n in names:
         assert hasattr(L, n), n
-    assert L.wt_abi_version() == _lib.ABI_VERSION == 3
+    assert L.wt_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_no_silent_cpu_path_without_a_gpu():
