@@ -535,7 +535,9 @@ __global__ void __launch_bounds__(128) wt_calc_ph_kernel(int P, const double *al
 // Stage 1: each block reduces a slab of plants to per-block partials (coalesced rows of the
 // zone-major state).  Stage 2: one block sums the partials in a fixed order -> deterministic.
 //   out[0] live plants, out[1] halted plants, out[2] outlet Cl < thr[0],
-//   out[3] outlet pH outside [thr[1], thr[2]], out[4] outlet T > thr[3], out[5..7] reserved,
+//   out[3] outlet pH outside [thr[1], thr[2]], out[4] outlet T > thr[3], out[5] live plants whose last step was a
+//   floor-mode continuation (WTS_DEGRADED), out[6] of the "halted": plants being caught up (WTS_DEFERRED) or waiting
+//   for it (WTS_WORK_LIMIT), out[7] reserved,
 //   out[8 + 2*(v*n+z)] = sum (x - shift[v]), out[9 + 2*(v*n+z)] = sum (x - shift[v])^2   (live plants)
 // ---------------------------------------------------------------------------------------
 #define WT_STATS_HDR 8
@@ -563,11 +565,13 @@ __global__ void __launch_bounds__(WT_STATS_TPB) wt_stats_partial_kernel(int P, i
   const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
   const double c0 = shift_thr[0], c1 = shift_thr[1], c2 = shift_thr[2];
   const double t_cl = shift_thr[3], t_ph_lo = shift_thr[4], t_ph_hi = shift_thr[5], t_T = shift_thr[6];
-  double live = 0, halted = 0, e0 = 0, e1 = 0, e2 = 0;
+  double live = 0, halted = 0, e0 = 0, e1 = 0, e2 = 0, degraded = 0, pending = 0;
   for (int p = lo + threadIdx.x; p < hi; p += WT_STATS_TPB) {
-    const bool h = (status[p] & WTS_SKIP_MASK) != 0;   // halted, or deferred (being caught up on the side stream)
-    if (h) { halted += 1.0; continue; }
+    const uint32_t sw = status[p];
+    const bool h = (sw & WTS_SKIP_MASK) != 0;   // halted, or deferred (being caught up on the side stream)
+    if (h) { halted += 1.0; pending += (sw & (WTS_DEFERRED | WTS_WORK_LIMIT)) ? 1.0 : 0.0; continue; }
     live += 1.0;
+    degraded += (sw & WTS_DEGRADED) ? 1.0 : 0.0;
     const double ph = y[((size_t)0 * n + (n - 1)) * P + p], cl = y[((size_t)1 * n + (n - 1)) * P + p],
                  T = y[((size_t)2 * n + (n - 1)) * P + p];
     e0 += cl < t_cl ? 1.0 : 0.0;
@@ -579,7 +583,9 @@ __global__ void __launch_bounds__(WT_STATS_TPB) wt_stats_partial_kernel(int P, i
   r = block_sum(halted, sh); if (threadIdx.x == 0) out[1] = r;
   r = block_sum(e0, sh); if (threadIdx.x == 0) out[2] = r;
   r = block_sum(e1, sh); if (threadIdx.x == 0) out[3] = r;
-  r = block_sum(e2, sh); if (threadIdx.x == 0) { out[4] = r; out[5] = 0; out[6] = 0; out[7] = 0; }
+  r = block_sum(e2, sh); if (threadIdx.x == 0) { out[4] = r; out[7] = 0; }
+  r = block_sum(degraded, sh); if (threadIdx.x == 0) out[5] = r;
+  r = block_sum(pending, sh); if (threadIdx.x == 0) out[6] = r;
   for (int row = 0; row < 3 * n; ++row) {
     const double c = row < n ? c0 : (row < 2 * n ? c1 : c2);
     double s1 = 0, s2 = 0;

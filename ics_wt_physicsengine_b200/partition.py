@@ -66,7 +66,7 @@ def finalize_stats(vec: np.ndarray, n_zones: int, spec: StatsSpec) -> Dict[str, 
     """Turn a (summed) statistics vector into means / variances / exceedance fractions."""
     vec = np.asarray(vec, dtype=np.float64)
     live = vec[0]
-    out: Dict[str, np.ndarray] = {"live": live, "halted": vec[1]}
+    out: Dict[str, np.ndarray] = {"live": live, "halted": vec[1], "degraded": vec[5], "pending_catch_up": vec[6]}
     denom = live if live > 0 else np.nan
     out["frac_outlet_chlorine_low"] = vec[2] / denom
     out["frac_outlet_pH_out_of_band"] = vec[3] / denom

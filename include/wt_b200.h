@@ -239,7 +239,9 @@ int wt_diagnostics(int P, int n_zones, const double *par_dev, const double *y_de
  *   shift_thr[7] = {shift_pH, shift_Cl, shift_T,  Cl_min, pH_lo, pH_hi, T_max}   (device)
  *   out[wt_stats_size(n)]:
  *     [0] live plants  [1] halted plants  [2] #outlet Cl < Cl_min  [3] #outlet pH outside [pH_lo,pH_hi]
- *     [4] #outlet T > T_max  [5..7] reserved
+ *     [4] #outlet T > T_max  [5] live plants whose last step was a floor-mode continuation (WT_ST_DEGRADED)
+ *     [6] of the halted: plants over budget that are being caught up or wait for it (WT_ST_DEFERRED | WT_ST_WORK_LIMIT)
+ *     [7] reserved
  *     [8 + 2*(var*n+zone)] = sum(x - shift[var]),  [9 + 2*(var*n+zone)] = sum (x - shift[var])^2   over live plants
  *   scratch: wt_stats_scratch_doubles(n) doubles of device workspace.  Deterministic (fixed
  *   summation order).  accumulate != 0 adds to `out` instead of overwriting it.

@@ -23,6 +23,8 @@ def local_stats_numpy(y_pn, status, n, spec: StatsSpec) -> np.ndarray:
     v[2] = (cl < spec.chlorine_min).sum()
     v[3] = ((ph < spec.pH_low) | (ph > spec.pH_high)).sum()
     v[4] = (T > spec.temperature_max).sum()
+    v[5] = ((status & 512) != 0)[live].sum()            # floor-mode continuations among the live plants
+    v[6] = ((status & (128 | 256)) != 0)[~live].sum()   # over budget: being caught up or waiting for it
     sh = np.repeat([spec.shift_pH, spec.shift_chlorine, spec.shift_temperature], n)
     d = yl - sh[None, :]
     v[8::2] = d.sum(axis=0)
@@ -81,6 +83,9 @@ def _worker(rank, world, port, q):
     status = np.zeros(e.n_plants, dtype=np.uint32)
     if rank == 0:
         status[3] = 2    # a halted plant is excluded from the moments and counted as halted
+    else:
+        status[5] = 512  # a floor-mode continuation: live, counted as degraded
+        status[7] = 256  # a plant being caught up: excluded, counted as halted and as pending
     val, st, ft = _fake_readings(full.n_plants)
     lo, hi = shard_bounds(full.n_plants, rank, world)
     v = torch.from_numpy(np.concatenate([local_stats_numpy(y, status, 10, spec),
@@ -108,19 +113,21 @@ def test_gloo_allreduce_of_statistics_world2():
     y = np.concatenate([full.pH0, full.Cl0, full.T0], axis=1)
     status = np.zeros(257, dtype=np.uint32)
     status[3] = 2
+    lo1 = shard_bounds(257, 1, world)[0]
+    status[lo1 + 5], status[lo1 + 7] = 512, 256
     spec = StatsSpec()
     val, st, ft = _fake_readings(257)
     want = np.concatenate([local_stats_numpy(y, status, 10, spec), sensor_stats_numpy(val, st, ft, status, spec)])
     assert got.size == stats_size(10, sensors=True)
     assert np.allclose(got, want, rtol=1e-13, atol=1e-9)
     r = finalize_stats(got, 10, spec)
-    lv = status == 0
+    lv = (status & (2 | 128 | 256)) == 0
     assert np.array_equal(r["sensor_valid_count"], np.isfinite(val[:, lv]).sum(axis=1))
     assert np.allclose(r["sensor_mean"], np.nanmean(val[:, lv], axis=1), rtol=1e-12)
     assert np.allclose(r["sensor_var"], np.nanvar(val[:, lv], axis=1), rtol=1e-9)
     assert np.allclose(r["sensor_status_hist"].sum(axis=1), 1.0) and np.allclose(r["sensor_fault_hist"].sum(axis=1), 1.0)
-    live = status == 0
-    assert r["live"] == 256 and r["halted"] == 1
+    live = lv
+    assert r["live"] == 255 and r["halted"] == 2 and r["degraded"] == 1 and r["pending_catch_up"] == 1
     assert np.allclose(r["mean_pH"], full.pH0[live].mean(axis=0), rtol=1e-12)
     assert np.allclose(r["var_temperature"], full.T0[live].var(axis=0), rtol=1e-9)
     assert 0 <= r["frac_outlet_chlorine_low"] <= 1
