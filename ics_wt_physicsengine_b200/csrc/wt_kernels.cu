@@ -406,6 +406,113 @@ __global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_step_run_ker
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(WT_TMEM_COLS) : "memory");
 }
 
+// K1c  wt_catch_up_kernel  the deferred plants of one block of steps, ALL their steps in ONE launch.
+// A warp takes one group of listed plants and runs begin() + run() step after step until every plant of the group has
+// reached *t_stop (or halted).  The list is short (1e-4 .. 1e-2 of the ensemble), so what matters here is not the
+// instruction cache (this kernel is the fused 7,000-instruction form the step kernels were split out of) but the number
+// of launches: 2 x steps-per-block launch pairs of the two step kernels on the side stream cost more than the plants in
+// them (each had to wait for a gap between the persistent main launches).  One launch per block of steps instead.
+template <int WARPS, int NZ, bool FLOOR>
+__global__ void __launch_bounds__(WARPS * 32, WT_STEP_MINBLOCKS) wt_catch_up_kernel(StepArgs a) {
+  extern __shared__ double smem[];
+  static_assert(WARPS == 4, "one warp per tensor-memory lane quarter");
+  __shared__ uint32_t tmem_slot;
+  const int lane = threadIdx.x & 31, warp = (int)__reduce_max_sync(0xffffffffu, threadIdx.x >> 5);
+  const int n = NZ > 0 ? NZ : a.n, gpw = 32 / n;
+  const long long groups = ((long long)wt_plant_count(a) + gpw - 1) / gpw;
+  if ((long long)blockIdx.x * WARPS >= groups) return;  // (block-uniform) nothing listed for this block
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_slot)), "n"(WT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+  const size_t P = (size_t)a.ld;
+  typedef WtPlantStep<SmemLu> PS;
+  const long long wg = (long long)blockIdx.x * WARPS + warp;
+  if (wg < groups) {
+    const LaneMap lm = wt_lane_map(a, wg, lane, n, gpw);
+    const int p = lm.p, z = lm.z;
+    const uint32_t st_in = a.status[p];
+    double t = a.time[p];
+    double par[WTP_NPAR], bnd[WTB_NBND], y[3], der[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < WTP_NPAR; ++k) par[k] = a.par[(size_t)k * P + p];
+#pragma unroll
+    for (int k = 0; k < WTB_NBND; ++k) bnd[k] = a.bnd[a.bnd_stride ? (size_t)k * P + p : (size_t)k];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) y[v] = a.y[((size_t)v * n + z) * P + p];
+    bool on = lm.in_plant && !(st_in & a.skip_mask);
+    SmemLu lu;
+    lu.p = smem + (size_t)warp * wt_warp_smem_doubles(n) + lane;
+    lu.cp = smem + (size_t)warp * wt_warp_smem_doubles(n) + wt_lane_slots(n) * 32 + (lm.gi < gpw ? lm.gi : gpw) * WT_PLANT_DOUBLES;
+    lu.ci = (int *)(lu.cp + CK_N);
+    lu.tm = tmem_base + ((uint32_t)(warp * 32) << 16);
+    lu.rmw = false;
+    PS ps;
+    ps.g = wt_make_group(n, a.inv_sqrtN, a.inv_sqrt3N);
+    ps.lu = &lu;
+    ps.pk0 = wt_lu_slots(n) + LK_N;
+    ps.c = wt_make_const(&lu, ps.g, wt_lu_slots(n), par, bnd);
+    const double flow = bnd[WTB_INLET_FLOW] + bnd[WTB_ACID_FLOW] + bnd[WTB_CL_FLOW];  // reactor.py:500
+    const double t_stop = a.t_stop ? *a.t_stop : 1e300;
+    uint32_t st_acc = st_in;
+    bool advanced = false;
+#pragma unroll 1
+    for (int s = 0; s < a.n_steps; ++s) {
+      on = on && !(t >= t_stop - 0.5 * a.dt);
+      if (!__any_sync(0xffffffffu, on)) break;
+      __syncwarp();
+      lu.czero();
+      const double yin[3] = {y[0], y[1], y[2]};
+#pragma unroll
+      for (int v = 0; v < 3; ++v) ps.y[v] = y[v];
+      ps.begin(t, a.dt, on);
+      ps.template run<FLOOR>(t, a.max_attempts, a.h_floor);
+      double d[3];
+      bool adv;
+      const int sb = wt_finish_step(ps, yin, d, adv);
+      if (on) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) y[v] = ps.y[v];
+        if (adv) {
+          t += a.dt;
+          advanced = true;
+#pragma unroll
+          for (int v = 0; v < 3; ++v) der[v] = d[v];
+        }
+        // the non-halting bits of the earlier steps of this launch stay (as wt_advance ORs them); the deferred mark survives
+        st_acc = (uint32_t)sb | (s > 0 ? (st_acc & ~(uint32_t)WTS_SKIP_MASK) : 0u) | (st_in & (uint32_t)WTS_DEFERRED);
+        if (z == 0 && a.counters) {
+#pragma unroll
+          for (int k = 0; k < WTC_NCNT; ++k)
+            if (lu.cval(k)) atomicAdd(&a.counters[(size_t)k * P + p], lu.cval(k));
+        }
+        if (sb & (int)WTS_HALT_MASK) on = false;
+      }
+    }
+    if (lm.in_plant && !(st_in & a.skip_mask) && (advanced || st_acc != st_in)) {
+#pragma unroll
+      for (int v = 0; v < 3; ++v) a.y[((size_t)v * n + z) * P + p] = y[v];
+      if (a.derived && advanced) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) a.derived[((size_t)v * n + z) * P + p] = der[v];
+      }
+      if (z == 0) {
+        a.time[p] = t;
+        a.status[p] = st_acc;
+        if (advanced && a.flow) a.flow[p] = flow;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(WT_TMEM_COLS) : "memory");
+}
+
 __global__ void wt_derivatives_kernel(int P, int n, const double *par_, const double *bnd_, int bnd_stride,
                                       const double *y, double *dy, int32_t *bad_out) {
   const int lane = threadIdx.x & 31;
@@ -870,12 +977,16 @@ static int check_common(int P, int n) {
   return 0;
 }
 
-struct StepKernels { void (*begin)(StepArgs); void (*run)(StepArgs); void (*run_floor)(StepArgs); };
+struct StepKernels { void (*begin)(StepArgs); void (*run)(StepArgs); void (*run_floor)(StepArgs); void (*catch_up)(StepArgs); void (*catch_up_floor)(StepArgs); };
 static StepKernels step_kernels(int n) {
   if (getenv("WT_B200_GENERIC_N")) n = 0;  // A/B runs
-  if (n == 10) return {wt_step_begin_kernel<WT_STEP_WARPS, 10>, wt_step_run_kernel<WT_STEP_WARPS, 10, false>, wt_step_run_kernel<WT_STEP_WARPS, 10, true>};
-  if (n == 20) return {wt_step_begin_kernel<WT_STEP_WARPS, 20>, wt_step_run_kernel<WT_STEP_WARPS, 20, false>, wt_step_run_kernel<WT_STEP_WARPS, 20, true>};
-  return {wt_step_begin_kernel<WT_STEP_WARPS, 0>, wt_step_run_kernel<WT_STEP_WARPS, 0, false>, wt_step_run_kernel<WT_STEP_WARPS, 0, true>};
+  // (the catch-up kernel handles a few hundred plants: only the headline shape n = 10 gets its own instantiation)
+  if (n == 10) return {wt_step_begin_kernel<WT_STEP_WARPS, 10>, wt_step_run_kernel<WT_STEP_WARPS, 10, false>, wt_step_run_kernel<WT_STEP_WARPS, 10, true>,
+                       wt_catch_up_kernel<WT_STEP_WARPS, 10, false>, wt_catch_up_kernel<WT_STEP_WARPS, 10, true>};
+  if (n == 20) return {wt_step_begin_kernel<WT_STEP_WARPS, 20>, wt_step_run_kernel<WT_STEP_WARPS, 20, false>, wt_step_run_kernel<WT_STEP_WARPS, 20, true>,
+                       wt_catch_up_kernel<WT_STEP_WARPS, 0, false>, wt_catch_up_kernel<WT_STEP_WARPS, 0, true>};
+  return {wt_step_begin_kernel<WT_STEP_WARPS, 0>, wt_step_run_kernel<WT_STEP_WARPS, 0, false>, wt_step_run_kernel<WT_STEP_WARPS, 0, true>,
+          wt_catch_up_kernel<WT_STEP_WARPS, 0, false>, wt_catch_up_kernel<WT_STEP_WARPS, 0, true>};
 }
 
 // per-device launch facts, set up once per device under a lock (several host threads, one per device, may call in)
@@ -900,6 +1011,8 @@ static int device_info(DevInfo *out) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k.run, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k.run_floor, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k.run_floor, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k.catch_up, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k.catch_up_floor, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute");
     }
     e = cudaDeviceGetAttribute(&info[dev].sms, cudaDevAttrMultiProcessorCount, dev);
@@ -968,7 +1081,8 @@ int wt_catch_up(int cap, int ld, int n, int n_steps, double dt, const double *pa
   if (floor_div < 0) return set_err(WT_ERR_BAD_ARG, "floor_div must be >= 0");
   if (rc) return rc;
   if (!(dt > 0.0) || n_steps < 1 || ld < 1) return set_err(WT_ERR_BAD_ARG, "bad dt, n_steps or ld");
-  if (!par || !bnd || !time || !y || !status || !list || !count || !t_stop || !workspace)
+  (void)workspace;  // (ABI v3 ran the two step kernels per step and needed their hand-off rows; the fused kernel does not)
+  if (!par || !bnd || !time || !y || !status || !list || !count || !t_stop)
     return set_err(WT_ERR_BAD_ARG, "null device pointer");
   if (bnd_stride != 0 && bnd_stride != ld) return set_err(WT_ERR_BAD_ARG, "bnd_stride must be 0 or ld");
   StepArgs a;
@@ -978,7 +1092,20 @@ int wt_catch_up(int cap, int ld, int n, int n_steps, double dt, const double *pa
   a.skip_mask = WTS_HALT_MASK;   // the listed plants carry WTS_DEFERRED: that is what this launch is for
   a.count_dev = count; a.t_stop = t_stop;
   a.h_floor = floor_div > 0 ? dt / (double)floor_div : 0.0;
-  return launch_step(a, (cudaStream_t)stream);
+  // ONE launch for all n_steps of the listed plants (wt_catch_up_kernel); the workspace is not needed by it
+  a.inv_sqrtN = 1.0 / sqrt((double)(3 * n));
+  a.inv_sqrt3N = 1.0 / sqrt((double)(9 * n));
+  const int gpw = 32 / n;
+  const long long groups = ((long long)cap + gpw - 1) / gpw;
+  a.n_groups = (int)groups;
+  DevInfo di;
+  rc = device_info(&di);
+  if (rc) return rc;
+  const StepKernels k = step_kernels(n);
+  const size_t smem_run = (size_t)WT_STEP_WARPS * wt_warp_smem_doubles(n) * sizeof(double);
+  (a.h_floor > 0.0 ? k.catch_up_floor : k.catch_up)<<<(unsigned)((groups + WT_STEP_WARPS - 1) / WT_STEP_WARPS), WT_STEP_WARPS * 32, smem_run,
+                                                       (cudaStream_t)stream>>>(a);
+  return cuda_err(cudaGetLastError(), "wt_catch_up_kernel launch");
 }
 
 int wt_defer_collect(int P, uint32_t *status, int32_t *list, int32_t *count, int cap, void *stream) {

@@ -130,8 +130,9 @@ int wt_advance(int P, int n_zones, int n_steps, double dt, const double *par_dev
  *                     the number of entries already there) and re-marked WT_ST_DEFERRED: wt_step / wt_advance pass
  *                     over them, nothing else touches their state.
  *   wt_catch_up       n_steps x step(dt) for the listed plants only, with their own (larger) budget, each plant only
- *                     until its time reaches *t_stop_dev; meant for a side stream while the ensemble moves on.  Arrays
- *                     are the ensemble's (row stride ld = its plant count); workspace: wt_step_workspace_bytes(cap, n).
+ *                     until its time reaches *t_stop_dev; meant for a side stream while the ensemble moves on.  ONE
+ *                     kernel launch for all n_steps (a warp stays with its plants).  Arrays are the ensemble's (row
+ *                     stride ld = its plant count); workspace_dev is not used any more (may be NULL).
  *                     A plant that exhausts this budget too gets WT_ST_WORK_LIMIT and stays halted.
  *                     floor_div = 0: the reference's adaptive step control, as in wt_step.  floor_div > 0 (FLOOR MODE,
  *                     engine policy): the step size of every attempt is kept >= dt / floor_div, and at that floor an
