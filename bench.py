@@ -164,10 +164,12 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying one CUDA graph per block of steps")
-    ap.add_argument("--sort-every", type=int, default=2, help="re-order plants by last-step work every k launches (scheduling only)")
+    ap.add_argument("--sort-every", type=int, default=1, help="re-order plants by last-step work every k launches (scheduling only)")
     ap.add_argument("--no-sensors", action="store_true", help="physics only (BASELINE configs[1]-style step)")
     ap.add_argument("--streams", type=int, default=0, help="independent sub-ensembles (CUDA streams) per GPU; 0 = by shard size")
     ap.add_argument("--stats-every", type=int, default=10)
+    ap.add_argument("--blocking-allreduce", action="store_true",
+                    help="all-reduce the statistics in front of the next block instead of beside it")
     ap.add_argument("--catch-up-attempts", type=int, default=0,
                     help="budget of the side-stream catch-up of plants that exhaust --max-attempts (0 = halt them for good, or "
                          "8 x --catch-up-floor-div when that is given)")
@@ -255,9 +257,12 @@ def main():
     with ClockSampler(local_rank) as clk:
         torch.cuda.synchronize()
         ev0.record()
+        stats_out = None
         for _ in range(n_blocks):
-            shard.replay()        # + the NCCL all-reduce of the statistics vector
+            # + the NCCL all-reduce of the statistics vector, overlapped with the next block (two staging buffers)
+            stats_out = shard.replay(overlap=not args.blocking_allreduce)
             sim["k"] += block
+        shard.finish_stats()      # every reduction complete inside the timed region
         if rem or not use_graph:
             shard.fork()
             eager_steps(rem if use_graph else args.steps)
@@ -285,7 +290,7 @@ def main():
     t_all = torch.cat([en.state.time for en in shard.engines])
     stalled_after = int((t_all < t_all.max() - 2 * block * DT - 0.5 * DT).sum())
     value = timed_plant_steps * N_ZONES / (ms * 1e-3)
-    stats_vec = shard._sum.cpu().numpy().copy()
+    stats_vec = (stats_out if (use_graph and n_blocks and stats_out is not None) else shard._sum).cpu().numpy().copy()
 
     # ---- the kernels alone: the sub-ensembles' launches overlap on the device inside the timed region, so single launches
     # are timed here with CUDA events on the stream they are launched on, streams joined between launches
@@ -393,7 +398,8 @@ def main():
             "workload": f"BASELINE configs[4] physics: {P_total} plants x {N_ZONES} zones (ensembles.config5 seed 20260004), "
                         f"IntegratedCSTR.step(dt=1s) + 7-sensor suite read per plant per step, sharded over {world} GPU(s)",
             "launch_mode": (f"one CUDA graph per rank per {block} steps (step begin + run kernels, sensor read, clock tick, cost "
-                            f"order of every sub-ensemble, local statistics), then one NCCL all-reduce") if use_graph
+                            f"order of every sub-ensemble, local statistics), then one NCCL all-reduce "
+                            + ("in front of the next block" if args.blocking_allreduce else "overlapped with the next block")) if use_graph
                            else "every kernel launched from the host",
             "l2": "state+params per GPU >> 126 MB L2 at N<=4; inputs larger than L2 (no flush needed)",
             "sensor_suite": shard.suites is not None,

@@ -1348,12 +1348,24 @@ __global__ void wt_cost_scan_kernel(int32_t *bins) {  // one block of WT_COST_BI
   }
   bins[WT_COST_BINS - 1 - i] = sh[i] - (i == 0 ? sh[0] : sh[i] - sh[i - 1]);  // exclusive
 }
-__global__ void wt_cost_scatter_kernel(int P, const int32_t *cost, int32_t *cursor, int32_t *order) {
+// Scatter: almost all plants share a handful of keys, so one global atomic per plant serialises on ~10 addresses
+// (0.15 ms per 262,144 plants, 4 % of a step).  A block ranks its plants per key in shared memory, reserves one range
+// per (block, key) with a single global atomic, and scatters: ~40x fewer global atomics, none of them hot.
+__global__ void __launch_bounds__(WT_COST_BINS) wt_cost_scatter_kernel(int P, const int32_t *cost, int32_t *cursor, int32_t *order) {
+  __shared__ int cnt[WT_COST_BINS], base[WT_COST_BINS];
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  int c = cost[p];
-  c = c < 0 ? 0 : (c >= WT_COST_BINS ? WT_COST_BINS - 1 : c);
-  order[atomicAdd(&cursor[c], 1)] = p;
+  int c = 0, rank = 0;
+  if (p < P) {
+    c = cost[p];
+    c = c < 0 ? 0 : (c >= WT_COST_BINS ? WT_COST_BINS - 1 : c);
+    rank = atomicAdd(&cnt[c], 1);
+  }
+  __syncthreads();
+  if (cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]);
+  __syncthreads();
+  if (p < P) order[base[c] + rank] = p;
 }
 
 // Maintenance operations of the reference sensors, for sensor `sensor` of every plant:
@@ -1502,7 +1514,7 @@ int wt_cost_order(int P, const int32_t *cost_dev, int32_t *order_dev, int32_t *b
   if (blocks > 1184) blocks = 1184;
   wt_cost_hist_kernel<<<blocks, 256, 0, s>>>(P, cost_dev, bins_dev);
   wt_cost_scan_kernel<<<1, WT_COST_BINS, 0, s>>>(bins_dev);
-  wt_cost_scatter_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, cost_dev, bins_dev, order_dev);
+  wt_cost_scatter_kernel<<<(P + WT_COST_BINS - 1) / WT_COST_BINS, WT_COST_BINS, 0, s>>>(P, cost_dev, bins_dev, order_dev);
   return cuda_err(cudaGetLastError(), "wt_cost_order launch");
 }
 

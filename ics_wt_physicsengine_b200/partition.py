@@ -297,9 +297,15 @@ class PipelinedShard:
                 self.synchronize()
         self._graph, self._graph_steps, self._graph_stats = g, int(n_steps), bool(with_stats)
 
-    def replay(self, group=None) -> Optional[torch.Tensor]:
+    def replay(self, group=None, overlap: bool = False) -> Optional[torch.Tensor]:
         """Replay the captured block of steps on the current stream; returns the (all-reduced) statistics vector when the
-        block was captured with statistics."""
+        block was captured with statistics.
+
+        ``overlap``: the all-reduce runs BESIDE the next block instead of in front of it.  A blocking all-reduce makes
+        every rank wait for the slowest one at every block boundary (the ranks' blocks differ by the stragglers they
+        hold); here the local vector is copied to one of two staging buffers, reduced asynchronously on NCCL's stream,
+        and the compute stream only waits for a reduction when its buffer comes round again two blocks later.  The
+        returned tensor is valid after ``finish_stats()`` (or two blocks later)."""
         self._graph.replay()
         if self.suites is not None:
             for su in self.suites:
@@ -308,8 +314,28 @@ class PipelinedShard:
             return None
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self._sum, op=dist.ReduceOp.SUM, group=group)
+            if not overlap:
+                dist.all_reduce(self._sum, op=dist.ReduceOp.SUM, group=group)
+                return self._sum
+            if not hasattr(self, "_ar_buf"):
+                self._ar_buf = [torch.zeros_like(self._sum) for _ in range(2)]
+                self._ar_work = [None, None]
+                self._ar_k = 0
+            k = self._ar_k % 2
+            if self._ar_work[k] is not None:
+                self._ar_work[k].wait()          # stream-level: the reduction of two blocks ago
+            self._ar_buf[k].copy_(self._sum)     # after the graph in stream order
+            self._ar_work[k] = dist.all_reduce(self._ar_buf[k], op=dist.ReduceOp.SUM, group=group, async_op=True)
+            self._ar_k += 1
+            return self._ar_buf[k]
         return self._sum
+
+    def finish_stats(self) -> None:
+        """The compute stream waits for the outstanding overlapped all-reduces (``replay(overlap=True)``)."""
+        for k, w in enumerate(getattr(self, "_ar_work", [])):
+            if w is not None:
+                w.wait()
+                self._ar_work[k] = None
 
     # aggregate views (they join the streams first)
     def time_sum(self) -> torch.Tensor:
