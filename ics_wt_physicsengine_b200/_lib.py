@@ -39,7 +39,7 @@ EXPORTS = (
     "wt_sensors_init", "wt_sensors_calibrate", "wt_sensors_read", "wt_diagnostics", "wt_register_image",
     "wt_sensors_maintain", "wt_sensor_window_stats", "wt_sensors_reset", "wt_clock_tick", "wt_sensor_stats_size",
     "wt_sensor_stats_scratch_doubles", "wt_sensor_stats", "wt_cost_order", "wt_apply_commands", "wt_scenario_commands",
-    "wt_defer_collect", "wt_catch_up", "wt_defer_rejoin",
+    "wt_defer_collect", "wt_catch_up", "wt_defer_rejoin", "wt_sum_rows",
 )
 
 
@@ -104,7 +104,9 @@ def lib() -> C.CDLL:
     L.wt_sensor_stats.restype = C.c_int
     L.wt_cost_order.argtypes = [C.c_int, ip, ip, ip, vp]
     L.wt_cost_order.restype = C.c_int
-    L.wt_defer_collect.argtypes = [C.c_int, up, ip, ip, C.c_int, vp]
+    L.wt_defer_collect.argtypes = [C.c_int, up, ip, ip, C.c_int, dp, C.c_double, vp]
+    L.wt_sum_rows.argtypes = [C.c_int, C.c_int, dp, dp, vp]
+    L.wt_sum_rows.restype = C.c_int
     L.wt_defer_collect.restype = C.c_int
     L.wt_catch_up.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, up, ip, C.c_int,
                               C.c_int, ip, ip, dp, vp, vp]

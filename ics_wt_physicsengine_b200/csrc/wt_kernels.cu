@@ -885,8 +885,10 @@ __global__ void wt_sensor_window_stats_kernel(int P, int m, const double *hist, 
 // ensemble moves on, and REJOINED at the next block boundary.  Only a plant that exhausts the larger budget too (or
 // raises in the reference's sense, WTS_T_RANGE) stays halted.
 // ---------------------------------------------------------------------------------------
-__global__ void wt_defer_collect_kernel(int P, uint32_t *status, int32_t *list, int32_t *count, int cap) {
+__global__ void wt_defer_collect_kernel(int P, uint32_t *status, int32_t *list, int32_t *count, int cap, double *t_stop,
+                                        double t_stop_inc) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p == 0 && t_stop) *t_stop += t_stop_inc;   // the end time of the block the catch-up that follows works towards
   if (p >= P) return;
   const uint32_t st = status[p];
   if ((st & WTS_WORK_LIMIT) && !(st & WTS_DEFERRED)) {
@@ -1108,11 +1110,12 @@ int wt_catch_up(int cap, int ld, int n, int n_steps, double dt, const double *pa
   return cuda_err(cudaGetLastError(), "wt_catch_up_kernel launch");
 }
 
-int wt_defer_collect(int P, uint32_t *status, int32_t *list, int32_t *count, int cap, void *stream) {
+int wt_defer_collect(int P, uint32_t *status, int32_t *list, int32_t *count, int cap, double *t_stop, double t_stop_inc,
+                     void *stream) {
   if (P <= 0 || cap <= 0) return set_err(WT_ERR_BAD_ARG, "P and cap must be positive");
   if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
   if (!status || !list || !count) return set_err(WT_ERR_BAD_ARG, "null device pointer");
-  wt_defer_collect_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, status, list, count, cap);
+  wt_defer_collect_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, status, list, count, cap, t_stop, t_stop_inc);
   return cuda_err(cudaGetLastError(), "wt_defer_collect_kernel launch");
 }
 
@@ -1217,6 +1220,14 @@ int wt_scenario_commands(int P, int K, int S, const double *times, const double 
 
 int wt_stats_size(int n) { return WT_STATS_HDR + 6 * n; }
 int wt_stats_scratch_doubles(int n) { return 1024 * (WT_STATS_HDR + 6 * n); }
+
+int wt_sum_rows(int rows, int n, const double *in, double *out, void *stream) {
+  if (rows <= 0 || n <= 0) return set_err(WT_ERR_BAD_ARG, "rows and n must be positive");
+  if (wt_device_count() <= 0) return set_err(WT_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  if (!in || !out) return set_err(WT_ERR_BAD_ARG, "null device pointer");
+  wt_stats_final_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rows, n, in, out, 0);
+  return cuda_err(cudaGetLastError(), "wt_sum_rows launch");
+}
 
 int wt_stats(int P, int n, const double *y, const uint32_t *status, const double *shift_thr, double *out,
              double *scratch, int accumulate, void *stream) {

@@ -98,9 +98,10 @@ def finalize_stats(vec: np.ndarray, n_zones: int, spec: StatsSpec) -> Dict[str, 
 class EnsembleStatistics:
     """Device-side accumulation + all-reduce of the ensemble statistics of one PlantEnsemble shard."""
 
-    def __init__(self, ensemble, spec: Optional[StatsSpec] = None, suite=None):
+    def __init__(self, ensemble, spec: Optional[StatsSpec] = None, suite=None, out: Optional[torch.Tensor] = None):
         """``suite``: the ensemble's SensorSuite; its per-sensor statistics then follow the plant statistics in the
-        vector (valid count, sum, sum of squares, status and fault histograms per sensor)."""
+        vector (valid count, sum, sum of squares, status and fault histograms per sensor).
+        ``out``: where the vector is written (e.g. this sub-ensemble's row of a rank's stack); default: an own buffer."""
         self.ens = ensemble
         self.spec = spec or StatsSpec()
         self.suite = suite
@@ -111,7 +112,8 @@ class EnsembleStatistics:
         assert self.size == stats_size(n, suite is not None)
         dev = ensemble.device
         self._spec_dev = torch.from_numpy(self.spec.as_row()).to(dev)
-        self._out = torch.zeros(self.size, dtype=torch.float64, device=dev)
+        self._out = torch.zeros(self.size, dtype=torch.float64, device=dev) if out is None else out
+        assert self._out.numel() == self.size and self._out.is_contiguous() and self._out.dtype == torch.float64
         self._scratch = torch.empty(L.wt_stats_scratch_doubles(n), dtype=torch.float64, device=dev)
         if suite is not None:
             self._shift7 = torch.tensor(self.spec.sensor_shifts, dtype=torch.float64, device=dev)
@@ -176,10 +178,12 @@ class PipelinedShard:
             from .sensors import create_realistic_sensor_suite
             self.suites = [create_realistic_sensor_suite(e, seed=sensor_seed, plant0=plant0 + lo)
                            for e, (lo, _) in zip(self.engines, self.bounds)]
-        self.stats_parts = [EnsembleStatistics(e, spec, None if self.suites is None else self.suites[i])
+        nstat = stats_size(self.n_zones, self.suites is not None)
+        # every sub-ensemble writes its vector straight into its row of the stack; wt_sum_rows adds the rows in order
+        self._stack = torch.zeros((len(self.engines), nstat), dtype=torch.float64, device=self.device)
+        self.stats_parts = [EnsembleStatistics(e, spec, None if self.suites is None else self.suites[i], out=self._stack[i])
                             for i, e in enumerate(self.engines)]
-        self._sum = torch.zeros(self.stats_parts[0].size, dtype=torch.float64, device=self.device)
-        self._stack = torch.zeros((len(self.engines), self.stats_parts[0].size), dtype=torch.float64, device=self.device)
+        self._sum = torch.zeros(nstat, dtype=torch.float64, device=self.device)
         self._graph = None
         # side streams of the deferral (PlantEnsemble(catch_up_attempts=...)): catch-up launches of one block overlap the
         # ordinary steps of the next
@@ -223,8 +227,7 @@ class PipelinedShard:
         for i, (e, s) in enumerate(zip(self.engines, self.streams)):
             with torch.cuda.stream(s):
                 if self.defer:
-                    e._t_stop.add_(n_steps * dt)
-                    e.collect_deferred()
+                    e.collect_deferred(n_steps * dt)
                     self.side[i].wait_stream(s)
                     with torch.cuda.stream(self.side[i]):
                         e.catch_up(2 * n_steps, dt, self.bnd[i])
@@ -260,9 +263,12 @@ class PipelinedShard:
         summed in a fixed order."""
         for i, (sp, s) in enumerate(zip(self.stats_parts, self.streams)):
             with torch.cuda.stream(s):
-                self._stack[i].copy_(sp.local())
+                sp.local()   # -> self._stack[i]
         self.synchronize()
-        torch.sum(self._stack, dim=0, out=self._sum)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().wt_sum_rows(len(self.engines), self._sum.numel(), C.c_void_p(self._stack.data_ptr()),
+                                        C.c_void_p(self._sum.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "wt_sum_rows")
         self.fork()  # the statistics buffers are reused by the next call
         return self._sum
 

@@ -341,12 +341,13 @@ class PlantEnsemble:
         return self.state
 
     # ---- deferral of budget-exhausted plants (include/wt_b200.h: wt_defer_collect / wt_catch_up / wt_defer_rejoin) ----
-    def collect_deferred(self) -> None:
+    def collect_deferred(self, t_stop_inc: float = 0.0) -> None:
         """Plants that ran out of ``max_attempts`` -> the deferred list (they keep their state, ordinary steps pass
-        over them until ``rejoin_deferred``)."""
+        over them until ``rejoin_deferred``).  ``t_stop_inc`` is added to the stop time of the catch-up first."""
         with torch.cuda.device(self.device):
             rc = _lib.lib().wt_defer_collect(self.n_plants, _ptr(self._status), _ptr(self._defer_list), _ptr(self._defer_count),
-                                             self._defer_cap, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                             self._defer_cap, _ptr(self._t_stop), float(t_stop_inc),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, "wt_defer_collect")
 
     def catch_up(self, n_steps: int, dt: float, boundary: BoundaryLike) -> None:

@@ -128,7 +128,8 @@ int wt_advance(int P, int n_zones, int n_steps, double dt, const double *par_dev
  * failure only logs, reactor.py:476-490).
  *   wt_defer_collect  plants with WT_ST_WORK_LIMIT are appended to list_dev (capacity cap; count_dev must be 0 or hold
  *                     the number of entries already there) and re-marked WT_ST_DEFERRED: wt_step / wt_advance pass
- *                     over them, nothing else touches their state.
+ *                     over them, nothing else touches their state.  t_stop_dev (optional): *t_stop_dev += t_stop_inc first
+ *                     (the end time of the block of steps that begins; no separate launch inside a captured graph).
  *   wt_catch_up       n_steps x step(dt) for the listed plants only, with their own (larger) budget, each plant only
  *                     until its time reaches *t_stop_dev; meant for a side stream while the ensemble moves on.  ONE
  *                     kernel launch for all n_steps (a warp stays with its plants).  Arrays are the ensemble's (row
@@ -142,7 +143,8 @@ int wt_advance(int P, int n_zones, int n_steps, double dt, const double *par_dev
  *                     instead of being halted: <= ~4 floor_div collocation solves per step.
  *   wt_defer_rejoin   after the catch-up has finished (stream order): takes WT_ST_DEFERRED off the listed plants and
  *                     empties the list. */
-int wt_defer_collect(int P, uint32_t *status_dev, int32_t *list_dev, int32_t *count_dev, int cap, void *stream);
+int wt_defer_collect(int P, uint32_t *status_dev, int32_t *list_dev, int32_t *count_dev, int cap, double *t_stop_dev,
+                     double t_stop_inc, void *stream);
 int wt_catch_up(int cap, int ld, int n_zones, int n_steps, double dt, const double *par_dev, const double *bnd_dev,
                 int bnd_stride, double *time_dev, double *y_dev, double *flow_rate_dev, double *derived_dev,
                 uint32_t *status_dev, int32_t *counters_dev, int max_attempts, int floor_div, const int32_t *list_dev,
@@ -248,6 +250,9 @@ int wt_diagnostics(int P, int n_zones, const double *par_dev, const double *y_de
  *   summation order).  accumulate != 0 adds to `out` instead of overwriting it.
  * ------------------------------------------------------------------------------------- */
 int wt_stats_size(int n_zones);
+/* out[k] = sum over r < rows of in[r * n + k], in row order (bitwise reproducible): the statistics vectors of a rank's
+ * sub-ensembles -> the rank's vector, before the all-reduce. */
+int wt_sum_rows(int rows, int n, const double *in_dev, double *out_dev, void *stream);
 int wt_stats_scratch_doubles(int n_zones);
 int wt_stats(int P, int n_zones, const double *y_dev, const uint32_t *status_dev,
              const double *shift_thr_dev, double *out_dev, double *scratch_dev, int accumulate,
