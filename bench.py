@@ -341,6 +341,25 @@ def main():
            "api": "wt_step_host (C ABI, pinned host buffers: H2D of state+boundary, step, D2H of state+time+flow+status per call, "
                   "pipelined over >= 12 column slabs on three streams; per-plant constants resident after the first call)", "n_gpus": world}
 
+    # ---- the same work as `value` (step + suite read) from and to host buffers, through the Python API
+    e2e_s = None
+    if sensors_on:
+        if world > 1:
+            dist.barrier()
+        live_s, el_s, k_s, h2d_s, d2h_s, parts_s = e2e_sensors_measure(e, lo, dev, args)
+        ag = torch.tensor([float(live_s), float(h2d_s), float(d2h_s)], dtype=torch.float64, device=dev)
+        mx = torch.tensor([el_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ag)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        e2e_s = {"value": float(ag[0]) * N_ZONES * k_s / float(mx[0]), "unit": UNIT, "h2d_bytes_per_step": int(ag[1]),
+                 "d2h_bytes_per_step": int(ag[2]), "steps": k_s, "sub_ensembles_per_gpu": parts_s,
+                 "work": "IntegratedCSTR.step of every plant + one read of the 7-sensor suite per plant (the work `value` times)",
+                 "api": "PipelinedShard.step_host (Python API over wt_advance + wt_sensors_read): state, time and boundary rows from "
+                        "pinned host buffers, state, time, flow, status and the 7 x 5 sensor outputs + status / fault words back to them "
+                        "every step; every sub-ensemble uploads, steps, reads and downloads on its own stream"}
+    e2e["with_sensors"] = e2e_s
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -536,6 +555,46 @@ def e2e_measure(e, shard, args):
         torch.cuda.synchronize()
         floor = time.perf_counter() - t0
     return live, el, k, h2d, d2h, floor
+
+
+def e2e_sensors_measure(e, lo, dev, args):
+    """Step + suite read with the state in pinned HOST memory between steps (PipelinedShard.step_host).  Returns
+    (live plants, seconds, steps, h2d bytes/step, d2h bytes/step, sub-ensembles) of this rank's shard."""
+    import torch
+
+    from ics_wt_physicsengine_b200 import _lib
+    from ics_wt_physicsengine_b200.partition import PipelinedShard
+    P = e.n_plants
+    parts = max(4, min(8, P // 32768))
+    sh = PipelinedShard(e, parts=parts, device=dev, plant0=lo, sensor_seed=20260004, max_attempts=args.max_attempts,
+                        sort_every=args.sort_every)
+    sh.initialize_sensors(-2000.0)
+    for j in range(100):
+        for su, s in zip(sh.suites, sh.streams):
+            with torch.cuda.stream(s):
+                su.read(None, float(j - 100))
+    sh.synchronize()
+    torch.cuda.synchronize()
+    io = sh.alloc_host_io()
+    k = max(3, min(args.steps, 10))
+    tsim = 0.0
+
+    def one():
+        nonlocal tsim
+        sh.fork()
+        sh.step_host(io, DT, read_time=tsim)
+        sh.synchronize()
+        torch.cuda.current_stream().synchronize()
+        tsim += DT
+    for _ in range(3):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(k):
+        one()
+    el = time.perf_counter() - t0
+    live = int(sum(int(((b["status"] & _lib.ST_SKIP_MASK) == 0).sum()) for b in io))
+    h2d, d2h = sh.host_io_bytes(io)
+    return live, el, k, h2d, d2h, parts
 
 
 def cpu_baseline(args):

@@ -219,6 +219,58 @@ class PipelinedShard:
                 if self.suites is not None and read_time is not None:
                     self.suites[i].read(e.state, read_time)
 
+    # ---- host-buffer step: the state lives in pinned HOST memory between steps (the reference keeps it in Python
+    # objects and hands the readings to its Modbus layer every step, __main__.py:398-457) -------------------------------
+    def alloc_host_io(self):
+        """Pinned host buffers of ``step_host``, one dict per sub-ensemble: in  y [3, n, P], time [P], bnd [10, P];
+        out y, time, flow [P], status [P] and, with sensor suites, sensor [5, 7, P] (value, raw_value, uncertainty,
+        quality, timestamp), sensor_status [7, P], sensor_fault [7, P]."""
+        io = []
+        for i, e in enumerate(self.engines):
+            P, n = e.n_plants, e.n_zones
+            pin = lambda *shape, dtype=torch.float64: torch.zeros(shape, dtype=dtype).pin_memory()
+            d = {"y": pin(3, n, P), "time": pin(P), "bnd": pin(self.bnd[i].shape[0], P), "flow": pin(P),
+                 "status": pin(P, dtype=torch.int32)}
+            d["y"].copy_(e._y)
+            d["time"].copy_(e._time)
+            d["bnd"].copy_(self.bnd[i])
+            if self.suites is not None:
+                d.update(sensor=pin(5, 7, P), sensor_status=pin(7, P, dtype=torch.int32), sensor_fault=pin(7, P, dtype=torch.int32))
+            io.append(d)
+        return io
+
+    def step_host(self, io, dt: float, read_time: Optional[float] = None) -> None:
+        """One ``step(dt)`` (+ one suite read at ``read_time``) of every plant with inputs FROM and results TO the pinned
+        host buffers of ``alloc_host_io``.  Every sub-ensemble runs upload -> step kernels -> sensor read -> download on
+        its own stream, so the copies of one overlap the kernels of the others (the DMA engines serve the uploads in
+        issue order).  Asynchronous: ``synchronize()`` + a stream synchronize before the host reads the buffers."""
+        for i, (e, s) in enumerate(zip(self.engines, self.streams)):
+            b = io[i]
+            with torch.cuda.stream(s):
+                e._y.copy_(b["y"], non_blocking=True)
+                e._time.copy_(b["time"], non_blocking=True)
+                self.bnd[i].copy_(b["bnd"], non_blocking=True)
+                e.step(dt, self.bnd[i])
+                if self.suites is not None and read_time is not None:
+                    self.suites[i].read(e.state, read_time)
+                b["y"].copy_(e._y, non_blocking=True)
+                b["time"].copy_(e._time, non_blocking=True)
+                b["flow"].copy_(e._flow, non_blocking=True)
+                b["status"].copy_(e._status, non_blocking=True)
+                if self.suites is not None and read_time is not None:
+                    su = self.suites[i]
+                    b["sensor"].copy_(su._out, non_blocking=True)
+                    b["sensor_status"].copy_(su._out_status, non_blocking=True)
+                    b["sensor_fault"].copy_(su._out_fault, non_blocking=True)
+
+    def host_io_bytes(self, io, sensors: bool = True):
+        """(H2D, D2H) bytes of one ``step_host`` call."""
+        nb = lambda t: t.numel() * t.element_size()
+        h2d = sum(nb(b["y"]) + nb(b["time"]) + nb(b["bnd"]) for b in io)
+        d2h = sum(nb(b["y"]) + nb(b["time"]) + nb(b["flow"]) + nb(b["status"])
+                  + ((nb(b["sensor"]) + nb(b["sensor_status"]) + nb(b["sensor_fault"])) if sensors and "sensor" in b else 0) for b in io)
+        return h2d, d2h
+
     def _block(self, n_steps: int, dt: float, read) -> None:
         """One block of steps of every sub-ensemble on its stream; ``read(i)`` reads sub-ensemble i's sensors.  With
         deferral: the plants that ran out of budget during the PREVIOUS block are collected at the start, caught up on
