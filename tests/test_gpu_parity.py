@@ -666,3 +666,34 @@ def test_floor_mode_catch_up_equals_the_oracle_and_nobody_stays_halted(oracle, g
     assert lost_plain >= 10
     settled = (sd & _lib.ST_SKIP_MASK) == 0
     assert settled.mean() > 0.999 and np.all(td[settled] == (blocks + 1) * B)
+
+
+def test_step_host_of_a_shard_equals_the_device_resident_steps():
+    """PipelinedShard.step_host (state, time and boundary rows from pinned host buffers, state / time / flow / status and
+    the suite's readings back to them, every step) gives bit for bit what the device-resident steps give."""
+    from ics_wt_physicsengine_b200.partition import PipelinedShard
+    P, n = 5003, 10
+    e = ens.config5(P, n)
+    mk = lambda: PipelinedShard(e, parts=3, plant0=77, sensor_seed=13, max_attempts=CAP, sort_every=1)
+    a, b = mk(), mk()
+    for sh in (a, b):
+        sh.initialize_sensors(-50.0)
+    io = b.alloc_host_io()
+    h2d, d2h = b.host_io_bytes(io)
+    assert h2d == P * (3 * n + 1 + 10) * 8 and d2h == P * ((3 * n + 2) * 8 + 4 + 7 * 5 * 8 + 2 * 7 * 4)
+    for k in range(4):
+        a.step(1.0, read_time=float(k))
+        b.fork()
+        b.step_host(io, 1.0, read_time=float(k))
+        b.synchronize()
+        torch.cuda.synchronize()
+        for i, (ea, sa) in enumerate(zip(a.engines, a.suites)):
+            assert torch.equal(io[i]["y"], ea._y.cpu()) and torch.equal(io[i]["time"], ea._time.cpu())
+            assert torch.equal(io[i]["status"], ea._status.cpu()) and torch.equal(io[i]["flow"], ea._flow.cpu())
+            assert torch.equal(torch.nan_to_num(io[i]["sensor"], nan=-1.0), torch.nan_to_num(sa._out.cpu(), nan=-1.0))
+            assert torch.equal(io[i]["sensor_status"], sa._out_status.cpu()) and torch.equal(io[i]["sensor_fault"], sa._out_fault.cpu())
+    # the host owns the state: what it writes into the buffers is what the next step starts from
+    io[0]["y"][2] += 1.0   # + 1 K in every zone of the first sub-ensemble
+    b.fork(); b.step_host(io, 1.0, read_time=4.0); b.synchronize(); torch.cuda.synchronize()
+    a.step(1.0, read_time=4.0); torch.cuda.synchronize()
+    assert not torch.equal(io[0]["y"], a.engines[0]._y.cpu()) and torch.equal(io[1]["y"], a.engines[1]._y.cpu())
