@@ -245,8 +245,11 @@ def main():
         if shard.defer:
             shard.start_deferral(float(sim["k"]))
         shard.capture(block, DT, t_next=float(sim["k"]), with_stats=True)
-        shard.replay()            # one untimed replay (graph upload)
-        sim["k"] += block
+        # two untimed replays: graph upload, and both staging buffers of the overlapped all-reduce allocated and used once
+        for _ in range(2):
+            shard.replay(overlap=not args.blocking_allreduce)
+            sim["k"] += block
+        shard.finish_stats()
     shard.reset_counters()
     torch.cuda.synchronize()
     if world > 1:
