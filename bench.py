@@ -393,14 +393,15 @@ def main():
                           "serialised (3 extra steps after the timed region)"}
         if shard.suites is not None:
             # K3: algorithmic bytes of one suite read per plant: 7 sensors x (10 state doubles r/w + 4 ints r/w
-            # + 5 outputs + 2 ints) + 4 delay-ring scans x 100 slots x 8 B + 4 ring appends x 16 B + 6 state doubles
-            b_read = 7 * (10 * 8 * 2 + 4 * 4 * 2 + 5 * 8 + 2 * 4) + 4 * 100 * 8 + 4 * 16 + 6 * 8
+            # + 5 outputs + 2 ints) + 4 delay-line searches x (8 timestamps + 1 value) x 8 B + 4 ring appends x 16 B + 6 state doubles
+            b_read = 7 * (10 * 8 * 2 + 4 * 4 * 2 + 5 * 8 + 2 * 4) + 4 * 9 * 8 + 4 * 16 + 6 * 8
             ach = b_read * ppl / (sens_t / n_launch * 1e-3) / 1e9
             sensors_rf = {"kernel": "wt_sensors_read_kernel", "bound": "hbm", "ms_per_launch": sens_t / n_launch,
                           "algorithmic_bytes_per_plant_read": b_read, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                           "frac": ach / hbm_peak, "peak_source": hbm_src,
-                          "state": "all sensors warm, delay rings full (100 of 100 slots scanned per line)",
-                          "traffic": 5030.0 * ppl, "traffic_source": "ncu dram bytes per plant-read of the same launch shape (profiles/r2_sensor_kernel.txt)"}
+                          "state": "all sensors warm, delay rings full (one window of 8 timestamps read per search)",
+                          "traffic": None, "traffic_source": "not captured for this kernel revision (profiles/r2_sensor_kernel.txt is the "
+                                                             "full-scan revision: 5,030 B per plant-read)"}
     hbm_ach = bytes_alg(timed_plant_steps, N_ZONES) / world / (ms * 1e-3) / 1e9
 
     cpu = None

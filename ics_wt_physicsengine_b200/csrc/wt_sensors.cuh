@@ -125,7 +125,7 @@ __host__ __device__ __forceinline__ int wt_sensor_type(int s) { return s < 2 ? S
 
 // SampleLine.transport_sample (base_sensor.py:177-216): append, then the buffered sample whose
 // timestamp is nearest to t - delay; ties keep the FIRST (oldest) entry (strict '<').
-__device__ double wt_transport_sample(const SensorArgs &a, int p, int line, double value, double t) {
+__device__ double wt_transport_sample(const SensorArgs &a, int p, int line, double value, double t, double dt_hint) {
   const size_t P = (size_t)a.P;
   int *hd = a.ring_i + ((size_t)line * 2 + 0) * P + p, *ct = a.ring_i + ((size_t)line * 2 + 1) * P + p;
   int head = *hd, count = *ct;
@@ -145,6 +145,42 @@ __device__ double wt_transport_sample(const SensorArgs &a, int p, int line, doub
   // 16 independent loads: one load per iteration with a data-dependent exit made the kernel latency-bound (measured:
   // 1.7x slower than the full scan it replaced).
   int slot = head == 0 ? WT_RING - 1 : head - 1;  // newest entry
+  // Fast path: reads normally come at a steady interval, so the wanted sample sits ~delay / interval entries behind the
+  // newest one.  ONE round of 8 independent loads around that guess finds it whenever the minimum of the (unimodal)
+  // distance lies strictly inside the window -- or at a window edge that is also an end of the deque (checked against a
+  // brute-force first-minimum on 400,000 random non-decreasing sequences with plateaus, tests/test_sensor_search.py); anything else
+  // (irregular read times, a window on a slope, the first reads) falls through to the scan below.  j counts entries
+  // back from the newest; the reference's FIRST minimum in deque order is the LARGEST such j.
+  if (dt_hint > 0.0 && count > 0) {
+    // (both sample lines of the suite are shared by a pH and a temperature sensor, sensors/__init__.py:62-67: two entries
+    // per read; a wrong guess only costs the fall-through)
+    const double q = 2.0 * a.s.line_delay_s / dt_hint;
+    int jg = q < (double)(count - 1) ? (int)(q + 0.5) : count - 1;
+    int ja = jg - 3;
+    ja = ja < 0 ? 0 : ja;
+    int jb = ja + 7;
+    jb = jb > count - 1 ? count - 1 : jb;
+    double d[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int sj = slot - (ja + k);
+      sj = sj < 0 ? sj + WT_RING : sj;
+      d[k] = (ja + k <= jb) ? fabs(base[((size_t)sj * 2) * P] - target) : INFINITY;
+    }
+    double dmin = d[0];
+    int m = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k)
+      if (d[k] <= dmin) { dmin = d[k]; m = k; }   // ties: the larger j (the older entry)
+    const int jm = ja + m;
+    // newer edge: strictly larger than the minimum (a tie there -- the deque holds equal timestamps in pairs -- could be a
+    // plateau that goes on falling beyond the window); older edge: the minimum (its LARGEST j) strictly inside
+    if ((ja == 0 || d[0] > dmin) && (jm < jb || jb == count - 1) && dmin < INFINITY) {
+      int sj = slot - jm;
+      sj = sj < 0 ? sj + WT_RING : sj;
+      return base[((size_t)sj * 2 + 1) * P];
+    }
+  }
   int best = slot, remaining = count;
   double best_d = INFINITY;
   bool done = false;
@@ -265,7 +301,7 @@ __global__ void __launch_bounds__(128, WT_SENS_MINBLOCKS) wt_sensors_read_kernel
       truev = Clz * (0.5 + 0.5 * (ratio / (1.0 + ratio)));
     } else if (type == ST_FLOW_MAG) truev = a.flow[p];
     else truev = Tz;
-    if (line >= 0) truev = wt_transport_sample(a, p, line, truev, t);                     // :603-614
+    if (line >= 0) truev = wt_transport_sample(a, p, line, truev, t, dt_read);            // :603-614
 
     const double drift = drift_rate * ((t - tcal) / 3600.0) + SF(WT_SF_CALOFF);          // :617-620
     const double noise = z1 * prec;                                                       // :623
