@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--catch-up-attempts", type=int, default=0,
                     help="budget of the side-stream catch-up of plants that exhaust --max-attempts (0 = halt them for good, or "
                          "8 x --catch-up-floor-div when that is given)")
-    ap.add_argument("--catch-up-floor-div", type=int, default=16,
+    ap.add_argument("--catch-up-floor-div", type=int, default=8,
                     help="0: no deferral unless --catch-up-attempts is given.  > 0: the catch-up runs in floor mode (step sizes >= dt / floor_div, forced acceptance at the floor, "
                          "WT_ST_DEGRADED): bounded-cost continuation of the plants on the 8 C density discontinuity, DESIGN.md section 7")
     args = ap.parse_args()

@@ -151,10 +151,12 @@ __device__ double wt_transport_sample(const SensorArgs &a, int p, int line, doub
   // brute-force first-minimum on 400,000 random non-decreasing sequences with plateaus, tests/test_sensor_search.py); anything else
   // (irregular read times, a window on a slope, the first reads) falls through to the scan below.  j counts entries
   // back from the newest; the reference's FIRST minimum in deque order is the LARGEST such j.
-  if (dt_hint > 0.0 && count > 0) {
-    // (both sample lines of the suite are shared by a pH and a temperature sensor, sensors/__init__.py:62-67: two entries
-    // per read; a wrong guess only costs the fall-through)
-    const double q = 2.0 * a.s.line_delay_s / dt_hint;
+  // Two guesses: two entries per read (both sample lines of the suite are shared by a pH and a temperature sensor,
+  // sensors/__init__.py:62-67), then one (a line whose other sensor is dead -- absorbing power fault, open / short circuit
+  // -- or still warming up gets one entry per read).  A wrong guess only costs the fall-through.
+#pragma unroll 1
+  for (int per_read = 2; per_read >= 1 && dt_hint > 0.0 && count > 0; --per_read) {
+    const double q = (double)per_read * a.s.line_delay_s / dt_hint;
     int jg = q < (double)(count - 1) ? (int)(q + 0.5) : count - 1;
     int ja = jg - 3;
     ja = ja < 0 ? 0 : ja;
