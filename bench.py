@@ -342,7 +342,8 @@ def main():
            "copy_only_floor": "the same H2D and D2H bytes per step moved concurrently on two streams with no kernel, all ranks at "
                               "once (max over ranks): what the host links of this box allow for this call",
            "api": "wt_step_host (C ABI, pinned host buffers: H2D of state+boundary, step, D2H of state+time+flow+status per call, "
-                  "pipelined over >= 12 column slabs on three streams; per-plant constants resident after the first call)", "n_gpus": world}
+                  "pipelined over column slabs that ramp up and down (16k .. 128k .. 16k plants) on a copy-in, three compute and a "
+                  "copy-out stream; per-plant constants resident after the first call)", "n_gpus": world}
 
     # ---- the same work as `value` (step + suite read) from and to host buffers, through the Python API
     e2e_s = None
@@ -508,7 +509,7 @@ def calc_ph_roofline(dev, fp64_peak):
     return {"kernel": "wt_calc_ph_kernel", "bound": "fp64", "iterations_total": iters, "ms_per_launch": best,
             "solves": int(alk.numel()), "flops_per_iteration": 255.0, "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": ach / fp64_peak if fp64_peak else None,
-            "note": "one thread per buffer system; iteration counts 1..100 diverge inside a warp, so the bound is the slowest lane"}
+            "note": "persistent warps; a lane that finishes a solve draws the next system from a global queue (iteration counts 1..100)"}
 
 
 def e2e_measure(e, shard, args):

@@ -39,7 +39,7 @@ EXPORTS = (
     "wt_sensors_init", "wt_sensors_calibrate", "wt_sensors_read", "wt_diagnostics", "wt_register_image",
     "wt_sensors_maintain", "wt_sensor_window_stats", "wt_sensors_reset", "wt_clock_tick", "wt_sensor_stats_size",
     "wt_sensor_stats_scratch_doubles", "wt_sensor_stats", "wt_cost_order", "wt_apply_commands", "wt_scenario_commands",
-    "wt_defer_collect", "wt_catch_up", "wt_defer_rejoin", "wt_sum_rows",
+    "wt_defer_collect", "wt_catch_up", "wt_defer_rejoin", "wt_sum_rows", "wt_step_host_plan",
 )
 
 
@@ -79,6 +79,8 @@ def lib() -> C.CDLL:
     L.wt_derivatives.restype = C.c_int
     L.wt_step_host.argtypes = [C.c_int, C.c_int, C.c_double, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int]
     L.wt_step_host.restype = C.c_int
+    L.wt_step_host_plan.argtypes = [C.c_int, ip, C.c_int]
+    L.wt_step_host_plan.restype = C.c_int
     L.wt_calc_ph.argtypes = [C.c_int, dp, dp, dp, dp, dp, ip, ip, vp]
     L.wt_calc_ph.restype = C.c_int
     L.wt_stats_size.argtypes = [C.c_int]

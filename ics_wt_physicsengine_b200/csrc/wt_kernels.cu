@@ -1,8 +1,12 @@
 // wt_kernels.cu -- sm_100a kernels and the C ABI (include/wt_b200.h).
 //
-// K1  wt_step_kernel         fused plant step (wt_step_core.h): zones -> lanes, PCR solves
-// K1b wt_derivatives_kernel  batched RHS only
+// K1  wt_step_begin_kernel + wt_step_run_kernel   the plant step (wt_step_core.h): zones -> lanes, PCR solves;
+//     wt_catch_up_kernel     the same step, fused, for the deferred plants of a block of steps (exact or floor mode)
+//     wt_derivatives_kernel  batched RHS only
 // K2  wt_calc_ph_kernel      batched charge-balance Newton-Raphson (chemistry.py:271-330)
+// K3  wt_sensors_read_kernel the 7-sensor suite (wt_sensors.cuh) + maintenance / reset / statistics kernels
+// K4  wt_stats_* / wt_sensor_stats_*   the payload of the one collective;  K5 diagnostics;  K6 register image
+//     wt_cost_* (counting sort of the cost order), wt_apply_commands / wt_scenario_commands (orchestrator),
 //     wt_dfma_peak_kernel    FP64 pipe saturation probe for the roofline denominator
 //
 // Nothing here is GEMM shaped, so there are no tensor-core / TMA paths: the step kernel is
@@ -1579,6 +1583,14 @@ static int wt_host_slab_plan(int P, int *sizes) {
   long long left = mid;
   for (int i = 0; i < nm && left > 0; ++i) { const int w = left < per ? (int)left : per; sizes[c++] = w; left -= w; }
   for (int i = nh - 1; i >= 0; --i) sizes[c++] = head[i];
+  return c;
+}
+
+int wt_step_host_plan(int P, int *sizes, int cap) {
+  if (P <= 0) return 0;
+  int plan[WT_HOST_MAX_SLABS];
+  const int c = wt_host_slab_plan(P, plan);
+  for (int i = 0; i < c && sizes && i < cap; ++i) sizes[i] = plan[i];
   return c;
 }
 

@@ -162,9 +162,14 @@ int wt_derivatives(int P, int n_zones, const double *par_dev, const double *bnd_
  * and waits for completion.  All pointers are HOST pointers with the SoA layouts above;
  * bnd_stride is P or 0.  flags: WT_HOST_PARAMS_RESIDENT = the per-plant constants `par` are
  * unchanged since the previous call with the same (P, n_zones) and are not uploaded again.
- * Internally the call is pipelined over column slabs of the arrays on three streams (H2D of one slab
- * overlaps the kernel of another and the D2H of a third); pinned host buffers are needed for the overlap. */
+ * Internally the call is pipelined over column slabs of the arrays: a copy-in stream, three compute streams and a
+ * copy-out stream chained per slab by events (the upload of one slab overlaps the kernels of another and the download
+ * of a third), with slab widths that ramp up and down (wt_step_host_plan); pinned host buffers are needed for the
+ * overlap. */
 #define WT_HOST_PARAMS_RESIDENT 1
+/* The slab widths (plants) wt_step_host uses for P plants, in order: returns their number (<= 64) and writes up to `cap`
+ * of them to sizes (may be NULL).  Host-only, no device needed.  Tuning: WT_B200_HOST_SLAB_MIN / _MAX / WT_B200_HOST_SLABS. */
+int wt_step_host_plan(int P, int *sizes, int cap);
 int wt_step_host(int P, int n_zones, double dt, const double *par, const double *bnd,
                  int bnd_stride, double *time, double *y, double *flow_rate, uint32_t *status,
                  int max_attempts, int flags);

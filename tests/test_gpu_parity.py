@@ -361,7 +361,7 @@ def test_sorted_scheduling_does_not_change_results():
 
 @pytest.mark.parametrize("P,bcast", [(33, False), (70001, False), (70001, True), (131072 + 77, False)])
 def test_host_buffer_entry_point_equals_the_device_path(P, bcast):
-    """wt_step_host (host SoA buffers in, pipelined over column slabs on three streams) runs the same kernel
+    """wt_step_host (host SoA buffers in, pipelined over column slabs on copy-in / compute / copy-out streams) runs the same kernel
     as the device-resident path: bit-identical state, time, flow and status, for ragged sizes, one and several
     slabs, per-plant and broadcast boundaries, repeated calls with the constants kept resident."""
     import ctypes as C

@@ -98,3 +98,21 @@ def test_product_package_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "wt_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+def test_host_slab_plan_covers_every_plant_and_ramps():
+    """wt_step_host's slab schedule (host-only): the widths add up to P, stay within the 64 slabs the call has events
+    for, start small (the first upload is in the open), stay at most 131,072 plants wide and end small again."""
+    import ctypes as C
+    L = _lib.lib()
+    for P in (1, 95, 96, 1000, 40000, 131072, 200003, 262144, 524288, 1048576, 4194304, 33554432):
+        sizes = (C.c_int * 64)()
+        n = L.wt_step_host_plan(P, sizes, 64)
+        w = list(sizes[:n])
+        assert 1 <= n <= 64 and sum(w) == P and min(w) >= 1, (P, w)
+        if P >= 131072:
+            assert w[0] == 16384 and w[-1] == 16384, (P, w)          # short first upload / last download
+            assert all(b >= a for a, b in zip(w[:len(w) // 2], w[1:len(w) // 2 + 1])), (P, w)   # ramp up
+        if P <= 4194304:
+            assert max(w) <= 131072 + 32, (P, w)
+    assert L.wt_step_host_plan(1048576, None, 0) == 13 and L.wt_step_host_plan(0, None, 0) == 0
