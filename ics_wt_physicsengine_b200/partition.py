@@ -148,6 +148,37 @@ class EnsembleStatistics:
         return finalize_stats(self.allreduce(group).cpu().numpy(), self.ens.n_zones, self.spec)
 
 
+class OverlappedAllReduce:
+    """Sum all-reduce of a small vector BESIDE the work that follows it ("issued every K steps on a side
+    stream overlapping the next step").  ``submit(vec)`` copies the vector to one of two staging buffers and starts an
+    asynchronous all-reduce on it; the caller's stream only waits for a reduction when its buffer comes round again,
+    two submissions later (or in ``finish``).  Works on any backend (NCCL: the waits are stream-level; gloo in the CPU
+    tests: they block the host)."""
+
+    def __init__(self, like: torch.Tensor, group=None):
+        self.buf = [torch.zeros_like(like) for _ in range(2)]
+        self.work = [None, None]
+        self.k = 0
+        self.group = group
+
+    def submit(self, vec: torch.Tensor) -> torch.Tensor:
+        """Returns the staging buffer that will hold the reduced vector (valid after ``finish`` or two submissions)."""
+        import torch.distributed as dist
+        k = self.k % 2
+        if self.work[k] is not None:
+            self.work[k].wait()          # the reduction of two submissions ago
+        self.buf[k].copy_(vec)           # after the producer of `vec` in stream order
+        self.work[k] = dist.all_reduce(self.buf[k], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.k += 1
+        return self.buf[k]
+
+    def finish(self) -> None:
+        for k, w in enumerate(self.work):
+            if w is not None:
+                w.wait()
+                self.work[k] = None
+
+
 class PipelinedShard:
     """One rank's shard run as ``parts`` independent sub-ensembles, each on its own CUDA stream.
 
@@ -185,6 +216,7 @@ class PipelinedShard:
                             for i, e in enumerate(self.engines)]
         self._sum = torch.zeros(nstat, dtype=torch.float64, device=self.device)
         self._graph = None
+        self._overlapped = None
         # side streams of the deferral (PlantEnsemble(catch_up_attempts=...)): catch-up launches of one block overlap the
         # ordinary steps of the next
         self.defer = bool(self.engines[0].catch_up_attempts > 0)
@@ -375,25 +407,15 @@ class PipelinedShard:
             if not overlap:
                 dist.all_reduce(self._sum, op=dist.ReduceOp.SUM, group=group)
                 return self._sum
-            if not hasattr(self, "_ar_buf"):
-                self._ar_buf = [torch.zeros_like(self._sum) for _ in range(2)]
-                self._ar_work = [None, None]
-                self._ar_k = 0
-            k = self._ar_k % 2
-            if self._ar_work[k] is not None:
-                self._ar_work[k].wait()          # stream-level: the reduction of two blocks ago
-            self._ar_buf[k].copy_(self._sum)     # after the graph in stream order
-            self._ar_work[k] = dist.all_reduce(self._ar_buf[k], op=dist.ReduceOp.SUM, group=group, async_op=True)
-            self._ar_k += 1
-            return self._ar_buf[k]
+            if self._overlapped is None:
+                self._overlapped = OverlappedAllReduce(self._sum, group)
+            return self._overlapped.submit(self._sum)
         return self._sum
 
     def finish_stats(self) -> None:
         """The compute stream waits for the outstanding overlapped all-reduces (``replay(overlap=True)``)."""
-        for k, w in enumerate(getattr(self, "_ar_work", [])):
-            if w is not None:
-                w.wait()
-                self._ar_work[k] = None
+        if self._overlapped is not None:
+            self._overlapped.finish()
 
     # aggregate views (they join the streams first)
     def time_sum(self) -> torch.Tensor:

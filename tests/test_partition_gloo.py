@@ -131,3 +131,46 @@ def test_gloo_allreduce_of_statistics_world2():
     assert np.allclose(r["mean_pH"], full.pH0[live].mean(axis=0), rtol=1e-12)
     assert np.allclose(r["var_temperature"], full.T0[live].var(axis=0), rtol=1e-9)
     assert 0 <= r["frac_outlet_chlorine_low"] <= 1
+
+
+def _worker_overlap(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ics_wt_physicsengine_b200.partition import OverlappedAllReduce
+    local = torch.zeros(222, dtype=torch.float64)
+    ar = OverlappedAllReduce(local)
+    outs = []
+    for blk in range(5):                       # five "blocks": the local vector changes while reductions are in flight
+        local.copy_(torch.arange(222, dtype=torch.float64) * (rank + 1) + 1000.0 * blk)
+        outs.append((blk, ar.submit(local)))
+        if blk >= 1:                           # the buffer of the previous block is not touched by this submission
+            assert outs[-1][1].data_ptr() != outs[-2][1].data_ptr()
+        local.fill_(-1.0)                      # the producer overwrites its vector right away (the next block's statistics)
+    ar.finish()
+    got = {blk: t.clone() for blk, t in outs[-2:]}   # the two staging buffers hold the last two blocks
+    if rank == 0:
+        q.put({k: v.numpy() for k, v in got.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_allreduce_world2():
+    """The statistics all-reduce that runs beside the next block (PipelinedShard.replay(overlap=True)): two staging
+    buffers, a wait only when a buffer comes round again; every block's reduced vector is the sum over the ranks of the
+    vector that was submitted, although the producer overwrites it immediately."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = 29700 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker_overlap, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    base = np.arange(222, dtype=np.float64)
+    for blk in (3, 4):
+        want = base * 1 + 1000.0 * blk + base * 2 + 1000.0 * blk
+        assert np.array_equal(got[blk], want), blk
