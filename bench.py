@@ -141,7 +141,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config5 physics: first {sample} of {TOTAL_PLANTS} plants x {N_ZONES} zones, dt=1s "
+        "config": {"workload": f"config5 physics: first {sample} of {args.plants} plants x {N_ZONES} zones, dt=1s "
                                f"(bounded CPU sample)", "max_attempts": args.max_attempts},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} plants x {args.steps} steps, oracle C port (pthreads), "
